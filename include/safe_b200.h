@@ -1,0 +1,149 @@
+/*
+ * safe_b200.h -- C ABI of libsafe_b200.so: SAFE's two data-parallel stages on one B200 (sm_100a).
+ *
+ * The reference (baryshnikova-lab/safepy) has no FFI; its boundary for this path is the Python method
+ * surface of class SAFE plus two free functions.  Each entry point below names the reference code it
+ * replaces (paths are relative to the reference checkout):
+ *
+ *   stage 1  SAFE.define_neighborhoods            safepy/safe.py:369-430
+ *   stage 2  compute_neighborhood_score           safepy/safe_extras.py:6-33
+ *            run_permutations                     safepy/safe_extras.py:36-70
+ *            SAFE.compute_pvalues_by_hypergeom    safepy/safe.py:556-608
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only; no Python / torch / C++ types cross the boundary.
+ *   - every function returns 0 on success, non-zero on failure; sb_last_error() then describes the
+ *     failure (thread-local, valid until the next call on that thread).
+ *   - "_host" pointers are ordinary host memory owned by the caller; "_dev" pointers are device memory on
+ *     the context's device (e.g. torch tensor data_ptr()).  The library owns whatever it allocates behind the
+ *     opaque handles and frees it in the matching *_destroy.
+ *   - one context = one CUDA device = one caller thread at a time.  Multi-GPU = one process (and one context)
+ *     per device; the only exchanges (all-gather of packed rows, all-reduce of counts) are done by the host
+ *     program over NCCL on the *_dev buffers.
+ *   - there is NO CPU fallback: without a usable sm_100 device sb_ctx_create fails.
+ *
+ * Packed neighborhood matrix: row-major uint32 words, element (s,t) is bit (t & 31) of word [s*ld + (t >> 5)],
+ * ld = sb_neigh_ld(n) words per row (multiple of 4 -> 16-byte aligned rows), padding bits are zero.
+ */
+#ifndef SAFE_B200_H
+#define SAFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SB_ABI_VERSION 1
+
+/* dtype codes for attribute matrices */
+#define SB_F32 0
+#define SB_F64 1
+
+/* neighborhood_score_type (safepy/safe_extras.py:6) */
+#define SB_SCORE_SUM 0
+#define SB_SCORE_ZSCORE 1
+
+/* engine selection for the permutation null */
+#define SB_ENGINE_AUTO 0   /* tcgen05 int8 digit GEMM + exact fix-up for 'sum'; SIMT fp64 for 'z-score' */
+#define SB_ENGINE_SIMT 1   /* fp64 CUDA-core sparse kernel (exact by construction; validation / z-score) */
+#define SB_ENGINE_TC 2     /* force the tensor-core path ('sum' only) */
+
+typedef struct sb_ctx sb_ctx;       /* one device + stream + workspaces */
+typedef struct sb_neigh sb_neigh;   /* bit-packed N x N neighborhood matrix on the device */
+typedef struct sb_enrich sb_enrich; /* stage-2 plan: neighborhoods x attribute matrix, prepared operands */
+
+/* ------------------------------------------------------------------ library / context */
+int sb_abi_version(void);
+const char* sb_last_error(void);
+
+/* device < 0: use the current CUDA device. Fails unless the device is compute capability 10.x. */
+int sb_ctx_create(int device, sb_ctx** out);
+int sb_ctx_destroy(sb_ctx* ctx);
+/* run all subsequent work of this context on an existing cudaStream_t (e.g. torch's current stream) */
+int sb_ctx_set_stream(sb_ctx* ctx, void* cuda_stream);
+int sb_ctx_synchronize(sb_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t sb_ctx_launch_count(sb_ctx* ctx);
+/* pin / unpin a caller-owned host buffer so the *_host entry points copy at full PCIe speed */
+int sb_host_register(void* ptr, int64_t bytes);
+int sb_host_unregister(void* ptr);
+
+/* ------------------------------------------------------------------ stage 1: neighborhoods
+ * replaces SAFE.define_neighborhoods, safepy/safe.py:369-430 */
+
+int64_t sb_neigh_ld(int64_t n); /* words per packed row */
+
+/* empty (all-zero) N x N packed matrix owned by the library */
+int sb_neigh_create(sb_ctx* ctx, int64_t n, sb_neigh** out);
+/* wrap a caller-owned device buffer of n*sb_neigh_ld(n) words (not freed by destroy) */
+int sb_neigh_wrap_dev(sb_ctx* ctx, int64_t n, uint32_t* words_dev, sb_neigh** out);
+int sb_neigh_destroy(sb_neigh* a);
+int64_t sb_neigh_n(const sb_neigh* a);
+uint32_t* sb_neigh_words_dev(sb_neigh* a);
+
+/* Shortest-path neighborhoods (safe.py:403-415; networkx all_pairs_dijkstra_path_length semantics):
+ * rows row0..row1-1 get A[s,t] = 1 iff dist(s,t) <= cutoff, distances are fp64 left-to-right path sums,
+ * the source itself is always a member.  CSR is the symmetric adjacency (both directions present).
+ * length_host == NULL means every edge has length 1 (metric 'shortpath' without a 'weight' attribute). */
+int sb_neigh_shortpath(sb_neigh* a, const int64_t* indptr_host, const int32_t* indices_host,
+                       const double* length_host, double cutoff, int64_t row0, int64_t row1);
+
+/* Euclidean neighborhoods (safe.py:389-399; scipy pdist semantics): A[i,j] = 1 iff sqrt(dx*dx+dy*dy) < nr,
+ * evaluated without FMA contraction.  Rows row0..row1-1 are written. */
+int sb_neigh_euclid(sb_neigh* a, const double* x_host, const double* y_host, double nr, int64_t row0, int64_t row1);
+
+/* upload an already packed matrix (rows row0..row1-1, ld words each) */
+int sb_neigh_upload_packed(sb_neigh* a, const uint32_t* words_host, int64_t row0, int64_t row1);
+/* download */
+int sb_neigh_download_packed(sb_neigh* a, uint32_t* words_host, int64_t row0, int64_t row1);
+/* neighbors per row (np.sum(neighborhoods, axis=1), safe.py:423) */
+int sb_neigh_rowsums(sb_neigh* a, int64_t* out_host);
+/* dense rows r0..r1-1 as 0/1: elem_bytes 1 -> uint8, 8 -> int64 (safe.py:387 dtype) */
+int sb_neigh_unpack_rows(sb_neigh* a, int64_t r0, int64_t r1, int elem_bytes, void* out_host);
+
+/* ------------------------------------------------------------------ stage 2: enrichment */
+
+/* Prepare neighborhoods x attributes: uploads B (n x m row-major, NaN = no data), builds the CSR view of A,
+ * and (lazily, on first permutation call) the tensor-core operands. */
+int sb_enrich_create(sb_ctx* ctx, sb_neigh* a, const void* b_host, int dtype, int64_t n, int64_t m, sb_enrich** out);
+/* same, B already on the device */
+int sb_enrich_create_dev(sb_ctx* ctx, sb_neigh* a, const void* b_dev, int dtype, int64_t n, int64_t m,
+                         sb_enrich** out);
+int sb_enrich_destroy(sb_enrich* e);
+
+/* compute_neighborhood_score(A, B, type), safe_extras.py:6-33 -> fp64 [n x m] */
+int sb_enrich_score(sb_enrich* e, int score_type, double* out_host);
+int sb_enrich_score_dev(sb_enrich* e, int score_type, double* out_dev);
+
+/* run_permutations core, safe_extras.py:56-66.
+ * perm_rows[p*n + t] = row of B that sits at node t during permutation p (the caller composes the reference's
+ * cumulative in-place shuffles into gather indices).  counts_neg[i*m+j] += #{p : S_p[i,j] <= S_0[i,j]},
+ * counts_pos likewise with >=.  The _dev variant ACCUMULATES into caller-zeroed device buffers so that
+ * permutation shards can be streamed; the _host variant overwrites. */
+int sb_enrich_perm_counts(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_host, int64_t num_perm,
+                          uint32_t* counts_neg_host, uint32_t* counts_pos_host);
+int sb_enrich_perm_counts_dev(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_dev,
+                              int64_t num_perm, uint32_t* counts_neg_dev, uint32_t* counts_pos_dev);
+
+/* statistics of the last perm_counts call on this plan:
+ * [0] comparisons decided by the GEMM, [1] comparisons sent to the exact fix-up, [2] A tiles stored,
+ * [3] A tiles possible, [4] digits used, [5] MMA k-tile iterations issued, [6] flag-list overflow batches */
+int sb_enrich_stats(sb_enrich* e, int64_t* out7_host);
+
+/* SAFE.compute_pvalues_by_hypergeom core, safe.py:573-608: p = hypergeom.sf(X-1, n_total, K_j, n_i), nes = -log10 p.
+ * Either output may be NULL. */
+int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host);
+int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev);
+
+/* ------------------------------------------------------------------ self-test hook (tests only)
+ * Runs one 128 x N x K int8 tcgen05 GEMM from host operands through the production tile layouts and returns the
+ * int32 accumulators; used to pin descriptor / layout encodings against a CPU product. */
+int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int variant /*0 = production descriptors*/,
+                       const int8_t* a_host /*128 x 64*ktiles*/, const int8_t* b_host /*64*ktiles x ncols*/,
+                       int32_t* d_host /*128 x ncols*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFE_B200_H */

@@ -1,0 +1,334 @@
+"""ctypes binding of libsafe_b200.so (the C ABI declared in include/safe_b200.h).
+
+Nothing here computes: every method forwards to one C entry point and raises `SafeB200Error` with the library's
+message when the call fails.  There is no CPU fallback -- if the shared library is missing or no sm_100 device is
+visible, importing works (so that CPU-only tooling can introspect the ABI) but creating a `Context` raises.
+"""
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsafe_b200.so")
+
+SB_F32, SB_F64 = 0, 1
+SCORE_TYPES = {"sum": 0, "z-score": 1}
+ENGINES = {"auto": 0, "simt": 1, "tc": 2}
+
+_vp = C.c_void_p
+_i64 = C.c_int64
+_i32 = C.c_int32
+
+# name -> (restype, argtypes); mirrors include/safe_b200.h one to one (tests/test_abi.py checks both directions)
+SIGNATURES = {
+    "sb_abi_version": (C.c_int, []),
+    "sb_last_error": (C.c_char_p, []),
+    "sb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "sb_ctx_destroy": (C.c_int, [_vp]),
+    "sb_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "sb_ctx_synchronize": (C.c_int, [_vp]),
+    "sb_ctx_launch_count": (_i64, [_vp]),
+    "sb_host_register": (C.c_int, [_vp, _i64]),
+    "sb_host_unregister": (C.c_int, [_vp]),
+    "sb_neigh_ld": (_i64, [_i64]),
+    "sb_neigh_create": (C.c_int, [_vp, _i64, C.POINTER(_vp)]),
+    "sb_neigh_wrap_dev": (C.c_int, [_vp, _i64, _vp, C.POINTER(_vp)]),
+    "sb_neigh_destroy": (C.c_int, [_vp]),
+    "sb_neigh_n": (_i64, [_vp]),
+    "sb_neigh_words_dev": (_vp, [_vp]),
+    "sb_neigh_shortpath": (C.c_int, [_vp, _vp, _vp, _vp, C.c_double, _i64, _i64]),
+    "sb_neigh_euclid": (C.c_int, [_vp, _vp, _vp, C.c_double, _i64, _i64]),
+    "sb_neigh_upload_packed": (C.c_int, [_vp, _vp, _i64, _i64]),
+    "sb_neigh_download_packed": (C.c_int, [_vp, _vp, _i64, _i64]),
+    "sb_neigh_rowsums": (C.c_int, [_vp, _vp]),
+    "sb_neigh_unpack_rows": (C.c_int, [_vp, _i64, _i64, C.c_int, _vp]),
+    "sb_enrich_create": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.POINTER(_vp)]),
+    "sb_enrich_create_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.POINTER(_vp)]),
+    "sb_enrich_destroy": (C.c_int, [_vp]),
+    "sb_enrich_score": (C.c_int, [_vp, C.c_int, _vp]),
+    "sb_enrich_score_dev": (C.c_int, [_vp, C.c_int, _vp]),
+    "sb_enrich_perm_counts": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
+    "sb_enrich_perm_counts_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
+    "sb_enrich_stats": (C.c_int, [_vp, _vp]),
+    "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
+    "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
+    "sb_selftest_mma_i8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+}
+
+
+class SafeB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load_library(path=None):
+    """dlopen libsafe_b200.so and attach the prototypes. Raises SafeB200Error if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None and path is None:
+            return _lib
+        p = path or LIB_PATH
+        if not os.path.exists(p):
+            raise SafeB200Error(
+                "%s is missing: build it with `python -m safepy_b200.build` (needs nvcc); "
+                "safepy_b200 has no CPU fallback" % p)
+        lib = C.CDLL(p)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.sb_abi_version() != 1:
+            raise SafeB200Error("libsafe_b200.so ABI version %d, expected 1" % lib.sb_abi_version())
+        if path is None:
+            _lib = lib
+        return lib
+
+
+def _check(lib, rc):
+    if rc != 0:
+        raise SafeB200Error(lib.sb_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One CUDA device (sb_ctx). `stream` may be a raw cudaStream_t integer (e.g. torch's current stream)."""
+
+    def __init__(self, device=-1, stream=None):
+        self.lib = load_library()
+        h = _vp()
+        _check(self.lib, self.lib.sb_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        if stream is not None:
+            self.set_stream(stream)
+
+    def set_stream(self, stream):
+        _check(self.lib, self.lib.sb_ctx_set_stream(self.h, _vp(int(stream))))
+
+    def synchronize(self):
+        _check(self.lib, self.lib.sb_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.sb_ctx_launch_count(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def neigh_ld(n):
+    """Words per packed row (pure arithmetic, mirrors sb_neigh_ld without needing the library)."""
+    return ((int(n) + 31) // 32 + 3) // 4 * 4
+
+
+class Neighborhoods:
+    """Bit-packed N x N neighborhood matrix on the device (sb_neigh)."""
+
+    def __init__(self, ctx, n, words_dev=None):
+        self.ctx = ctx
+        self.lib = ctx.lib
+        self.n = int(n)
+        self.ld = neigh_ld(n)
+        h = _vp()
+        if words_dev is None:
+            _check(self.lib, self.lib.sb_neigh_create(ctx.h, self.n, C.byref(h)))
+        else:
+            _check(self.lib, self.lib.sb_neigh_wrap_dev(ctx.h, self.n, _vp(int(words_dev)), C.byref(h)))
+        self.h = h
+
+    # -- stage 1
+    def shortpath(self, indptr, indices, length, cutoff, row0=0, row1=None):
+        indptr = _as(indptr, np.int64)
+        indices = _as(indices, np.int32)
+        if indptr.shape[0] != self.n + 1:
+            raise ValueError("indptr must have n + 1 entries")
+        if length is not None:
+            length = _as(length, np.float64)
+            if length.shape[0] != indices.shape[0]:
+                raise ValueError("length and indices differ in size")
+        row1 = self.n if row1 is None else row1
+        _check(self.lib, self.lib.sb_neigh_shortpath(self.h, _ptr(indptr), _ptr(indices), _ptr(length),
+                                                     float(cutoff), int(row0), int(row1)))
+        return self
+
+    def euclid(self, x, y, nr, row0=0, row1=None):
+        x = _as(x, np.float64)
+        y = _as(y, np.float64)
+        if x.shape != (self.n,) or y.shape != (self.n,):
+            raise ValueError("x and y must have n entries")
+        row1 = self.n if row1 is None else row1
+        _check(self.lib, self.lib.sb_neigh_euclid(self.h, _ptr(x), _ptr(y), float(nr), int(row0), int(row1)))
+        return self
+
+    def upload_packed(self, words, row0=0, row1=None):
+        row1 = self.n if row1 is None else row1
+        words = _as(words, np.uint32)
+        if words.size != (row1 - row0) * self.ld:
+            raise ValueError("packed block has the wrong size")
+        _check(self.lib, self.lib.sb_neigh_upload_packed(self.h, _ptr(words), int(row0), int(row1)))
+        return self
+
+    def upload_dense(self, dense):
+        """Pack a dense 0/1 matrix on the host (np.packbits) and upload it."""
+        return self.upload_packed(pack_dense(dense))
+
+    # -- readback
+    def packed(self, row0=0, row1=None):
+        row1 = self.n if row1 is None else row1
+        out = np.empty((row1 - row0, self.ld), dtype=np.uint32)
+        _check(self.lib, self.lib.sb_neigh_download_packed(self.h, _ptr(out), int(row0), int(row1)))
+        return out
+
+    def rowsums(self):
+        out = np.empty(self.n, dtype=np.int64)
+        _check(self.lib, self.lib.sb_neigh_rowsums(self.h, _ptr(out)))
+        return out
+
+    def dense(self, row0=0, row1=None, dtype=np.uint8):
+        row1 = self.n if row1 is None else row1
+        dtype = np.dtype(dtype)
+        if dtype.itemsize not in (1, 8):
+            raise ValueError("dense(): dtype must be 1 or 8 bytes wide")
+        out = np.empty((row1 - row0, self.n), dtype=dtype)
+        _check(self.lib, self.lib.sb_neigh_unpack_rows(self.h, int(row0), int(row1), dtype.itemsize, _ptr(out)))
+        return out
+
+    @property
+    def words_dev(self):
+        return int(self.lib.sb_neigh_words_dev(self.h) or 0)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_neigh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pack_dense(dense):
+    """Dense 0/1 [n, n] -> packed uint32 [n, ld] in the library's bit order (bit t&31 of word t>>5)."""
+    dense = np.asarray(dense)
+    n = dense.shape[0]
+    if dense.ndim != 2 or dense.shape[1] != n:
+        raise ValueError("neighborhood matrix must be square")
+    ld = neigh_ld(n)
+    bits = np.zeros((n, ld * 32), dtype=np.uint8)
+    bits[:, :n] = dense != 0
+    return np.packbits(bits, axis=1, bitorder="little").view(np.uint32).reshape(n, ld)
+
+
+def unpack_packed(words, n):
+    """Packed uint32 [rows, ld] -> dense uint8 [rows, n] (host helper for tests)."""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    bits = np.unpackbits(words.view(np.uint8), axis=1, bitorder="little")
+    return bits[:, :n]
+
+
+def _attr_matrix(b):
+    b = np.asarray(b)
+    if b.ndim != 2:
+        raise ValueError("attribute matrix must be 2-D")
+    if b.dtype == np.float32:
+        return np.ascontiguousarray(b), SB_F32
+    return np.ascontiguousarray(b, dtype=np.float64), SB_F64
+
+
+class Enrichment:
+    """Stage-2 plan (sb_enrich): neighborhoods x attribute matrix."""
+
+    def __init__(self, neigh, b=None, b_dev=None, dtype=None, shape=None):
+        self.neigh = neigh
+        self.ctx = neigh.ctx
+        self.lib = neigh.lib
+        h = _vp()
+        if b_dev is None:
+            b, code = _attr_matrix(b)
+            self.n, self.m = b.shape
+            _check(self.lib, self.lib.sb_enrich_create(self.ctx.h, neigh.h, _ptr(b), code, self.n, self.m,
+                                                       C.byref(h)))
+        else:
+            self.n, self.m = shape
+            code = SB_F32 if np.dtype(dtype) == np.float32 else SB_F64
+            _check(self.lib, self.lib.sb_enrich_create_dev(self.ctx.h, neigh.h, _vp(int(b_dev)), code, self.n,
+                                                           self.m, C.byref(h)))
+        self.h = h
+
+    def score(self, score_type="sum"):
+        out = np.empty((self.n, self.m), dtype=np.float64)
+        _check(self.lib, self.lib.sb_enrich_score(self.h, SCORE_TYPES[score_type], _ptr(out)))
+        return out
+
+    def perm_counts(self, perm_rows, score_type="sum", engine="auto"):
+        perm_rows = _as(perm_rows, np.int32)
+        if perm_rows.ndim != 2 or perm_rows.shape[1] != self.n:
+            raise ValueError("perm_rows must be [num_permutations, n]")
+        cneg = np.empty((self.n, self.m), dtype=np.uint32)
+        cpos = np.empty((self.n, self.m), dtype=np.uint32)
+        _check(self.lib, self.lib.sb_enrich_perm_counts(self.h, SCORE_TYPES[score_type], ENGINES[engine],
+                                                        _ptr(perm_rows), perm_rows.shape[0], _ptr(cneg),
+                                                        _ptr(cpos)))
+        return cneg, cpos
+
+    def perm_counts_dev(self, perm_dev, num_perm, cneg_dev, cpos_dev, score_type="sum", engine="auto"):
+        _check(self.lib, self.lib.sb_enrich_perm_counts_dev(self.h, SCORE_TYPES[score_type], ENGINES[engine],
+                                                            _vp(int(perm_dev)), int(num_perm), _vp(int(cneg_dev)),
+                                                            _vp(int(cpos_dev))))
+
+    def stats(self):
+        out = np.zeros(7, dtype=np.int64)
+        _check(self.lib, self.lib.sb_enrich_stats(self.h, _ptr(out)))
+        keys = ["decided", "fixups", "a_tiles", "a_tiles_dense", "digits", "ktile_iters", "overflow_batches"]
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def hypergeom(self, want_pvalues=True, want_nes=True):
+        pv = np.empty((self.n, self.m), dtype=np.float64) if want_pvalues else None
+        nes = np.empty((self.n, self.m), dtype=np.float64) if want_nes else None
+        _check(self.lib, self.lib.sb_enrich_hypergeom(self.h, _ptr(pv), _ptr(nes)))
+        return pv, nes
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_enrich_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def selftest_mma_i8(ctx, a, b, variant=0):
+    """128 x K int8 (values 0/1) times K x ncols int8 through the production tcgen05 kernel -> int32."""
+    a = _as(a, np.int8)
+    b = _as(b, np.int8)
+    k = a.shape[1]
+    ncols = b.shape[1]
+    if a.shape[0] != 128 or k % 64 or b.shape[0] != k:
+        raise ValueError("selftest operands must be 128 x 64k and 64k x ncols")
+    d = np.empty((128, ncols), dtype=np.int32)
+    _check(ctx.lib, ctx.lib.sb_selftest_mma_i8(ctx.h, ncols, k // 64, int(variant), _ptr(a), _ptr(b), _ptr(d)))
+    return d

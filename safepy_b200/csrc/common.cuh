@@ -1,0 +1,99 @@
+// Shared host-side plumbing for libsafe_b200: error convention, context, device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/safe_b200.h"
+
+namespace sb {
+
+// thread-local last-error string (sb_last_error)
+std::string& last_error();
+void set_error(const char* fmt, ...);
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+[[noreturn]] void fail(const char* fmt, ...);
+
+#define SB_CUDA(expr)                                                                        \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            ::sb::fail("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define SB_CHECK(cond, ...)                      \
+    do {                                         \
+        if (!(cond)) ::sb::fail(__VA_ARGS__);    \
+    } while (0)
+
+// Wrap the body of every extern "C" entry point.
+#define SB_API_BEGIN try {
+#define SB_API_END                                   \
+    return 0;                                        \
+    }                                                \
+    catch (const std::exception& ex) {               \
+        ::sb::set_error("%s", ex.what());            \
+        return 1;                                    \
+    }                                                \
+    catch (...) {                                    \
+        ::sb::set_error("unknown C++ exception");    \
+        return 2;                                    \
+    }
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    // grow-only allocation
+    void reserve(size_t count) {
+        if (count <= n) return;
+        release();
+        SB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        n = count;
+    }
+};
+
+}  // namespace sb
+
+struct sb_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    void bind() const { SB_CUDA(cudaSetDevice(device)); }
+};
+
+#define SB_LAUNCH_CHECK(ctx)            \
+    do {                                \
+        (ctx)->launches++;              \
+        SB_CUDA(cudaGetLastError());    \
+    } while (0)
+
+struct sb_neigh {
+    sb_ctx* ctx = nullptr;
+    int64_t n = 0;
+    int64_t ld = 0;  // words per row
+    uint32_t* words = nullptr;
+    bool owned = false;
+};
+
+static inline int64_t sb_ld_words(int64_t n) { return ((n + 31) / 32 + 3) / 4 * 4; }
+static inline int64_t sb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

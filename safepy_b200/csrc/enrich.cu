@@ -1,0 +1,621 @@
+// Stage 2 on CUDA cores: CSR view of the packed matrix, fp64 neighborhood scores, the exact (fp64,
+// ascending-neighbor order) permutation-count kernel used for validation / z-score / GEMM fix-ups, and the
+// fused hypergeometric survival-function kernel.
+// Replaces compute_neighborhood_score + run_permutations (reference safepy/safe_extras.py:6-70) and the body of
+// SAFE.compute_pvalues_by_hypergeom (safepy/safe.py:573-608).
+#include <cmath>
+#include <vector>
+
+#include "enrich.cuh"
+
+namespace sb {
+
+// ------------------------------------------------------------------------------------------------ CSR build
+__global__ void k_rowcount(const uint32_t* __restrict__ words, int64_t n, int64_t ld, int64_t* __restrict__ cnt) {
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int64_t acc = 0;
+    for (int64_t w = lane; w < ld; w += 32) acc += __popc(words[row * ld + w]);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) cnt[row] = acc;
+}
+
+// single-block exclusive scan: row_ptr[0..n] from cnt[0..n-1] (cnt aliases row_ptr + 1 is NOT allowed)
+__global__ void __launch_bounds__(1024) k_exscan(const int64_t* __restrict__ cnt, int64_t n,
+                                                  int64_t* __restrict__ row_ptr) {
+    __shared__ int64_t part[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t b = t * chunk, e = min(n, b + chunk);
+    int64_t s = 0;
+    for (int64_t i = b; i < e; ++i) s += cnt[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int64_t v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int64_t run = t ? part[t - 1] : 0;
+    for (int64_t i = b; i < e; ++i) {
+        row_ptr[i] = run;
+        run += cnt[i];
+    }
+    if (t == 1023) row_ptr[n] = part[1023];
+}
+
+__global__ void k_fill_csr(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
+                           const int64_t* __restrict__ row_ptr, int32_t* __restrict__ col_idx) {
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int64_t pos = row_ptr[row];
+    for (int64_t w0 = 0; w0 < ld; w0 += 32) {
+        const int64_t w = w0 + lane;
+        uint32_t bits = w < ld ? words[row * ld + w] : 0u;
+        int c = __popc(bits);
+        int incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int64_t at = pos + incl - c;
+        while (bits) {
+            int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            col_idx[at++] = static_cast<int32_t>(w * 32 + b);
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ scores
+template <class T>
+__device__ __forceinline__ double sq_like_numpy(T v);
+// np.power(B, 2) keeps B's dtype: float32 squares are rounded to float32 before the fp64 dot (safe_extras.py:24)
+template <>
+__device__ __forceinline__ double sq_like_numpy<float>(float v) {
+    return static_cast<double>(__fmul_rn(v, v));
+}
+template <>
+__device__ __forceinline__ double sq_like_numpy<double>(double v) {
+    return __dmul_rn(v, v);
+}
+
+// One (node i, virtual column c) score; c = p * m + j selects permutation p (perm == nullptr: identity) and
+// attribute j.  Accumulation is fp64 in ascending neighbor order -- the order the oracle uses.
+template <class T, bool ZS>
+__device__ __forceinline__ double score_one(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                            const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                            int64_t m, int64_t i, int64_t p, int64_t j) {
+    const int64_t e0 = row_ptr[i], e1 = row_ptr[i + 1];
+    const int32_t* pr = perm ? perm + p * n : nullptr;
+    double sum = 0.0, sq = 0.0;
+    int64_t cnt = 0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int32_t t = col_idx[e];
+        const int64_t r = pr ? pr[t] : t;
+        const T v = b[r * m + j];
+        if (v == v) {
+            sum += static_cast<double>(v);
+            if (ZS) {
+                sq += sq_like_numpy<T>(v);
+                ++cnt;
+            }
+        }
+    }
+    if (!ZS) return sum;
+    // safe_extras.py:19-31
+    const double N = static_cast<double>(cnt);
+    const double M = sum / N;
+    const double EXX = sq / N;
+    const double EEX = __dmul_rn(M, M);
+    const double sd = sqrt(__dsub_rn(EXX, EEX));
+    double z = M / sd;
+    if (sd == 0.0 || cnt < 3) z = __longlong_as_double(0x7FF8000000000000ll);
+    return z;
+}
+
+template <class T, bool ZS>
+__global__ void __launch_bounds__(128) k_score(const int64_t* __restrict__ row_ptr,
+                                               const int32_t* __restrict__ col_idx, const T* __restrict__ b,
+                                               int64_t n, int64_t m, double* __restrict__ out) {
+    const int64_t i = blockIdx.x;
+    const int64_t j = blockIdx.y * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= m) return;
+    out[i * m + j] = score_one<T, ZS>(row_ptr, col_idx, b, nullptr, n, m, i, 0, j);
+}
+
+template <class T, bool ZS>
+__global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ row_ptr,
+                                                    const int32_t* __restrict__ col_idx, const T* __restrict__ b,
+                                                    const int32_t* __restrict__ perm, int64_t n, int64_t m,
+                                                    int64_t ncols, const double* __restrict__ s0,
+                                                    uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
+    const int64_t i = blockIdx.x;
+    const int64_t c = blockIdx.y * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (c >= ncols) return;
+    const int64_t p = c / m, j = c % m;
+    const double s = score_one<T, ZS>(row_ptr, col_idx, b, perm, n, m, i, p, j);
+    const double o = s0[i * m + j];
+    // safe_extras.py:65-66 (NaN compares false on both sides)
+    if (s <= o) atomicAdd(&cneg[i * m + j], 1u);
+    if (s >= o) atomicAdd(&cpos[i * m + j], 1u);
+}
+
+template <class T>
+__global__ void k_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                        const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n, int64_t m,
+                        const uint64_t* __restrict__ flag_ij, const uint32_t* __restrict__ flag_p,
+                        const unsigned int* __restrict__ flag_count, unsigned int capacity,
+                        const double* __restrict__ s0, uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
+    const unsigned int total = min(*flag_count, capacity);
+    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int step = gridDim.x * blockDim.x;
+    for (; k < total; k += step) {
+        const uint64_t ij = flag_ij[k];
+        const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
+        const double s = score_one<T, false>(row_ptr, col_idx, b, perm, n, m, i, flag_p[k], j);
+        const double o = s0[i * m + j];
+        if (s <= o) atomicAdd(&cneg[i * m + j], 1u);
+        if (s >= o) atomicAdd(&cpos[i * m + j], 1u);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ hypergeometric
+template <class T>
+__global__ void k_has_data(const T* __restrict__ b, int64_t n, int64_t m, int32_t* __restrict__ has) {
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int any = 0;
+    for (int64_t j = lane; j < m; j += 32) {
+        T v = b[row * m + j];
+        any |= (v == v);
+    }
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) has[row] = any;
+}
+
+// per-column nansum in fp64 (np.nansum(node2attribute, axis=0), safe.py:583); rows are split over blockIdx.y
+template <class T>
+__global__ void k_colsum(const T* __restrict__ b, int64_t n, int64_t m, double* __restrict__ colsum) {
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= m) return;
+    const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        T v = b[r * m + j];
+        if (v == v) s += static_cast<double>(v);
+    }
+    atomicAdd(&colsum[j], s);
+}
+
+__global__ void k_nneigh(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                         const int32_t* __restrict__ has, int64_t n, double* __restrict__ nneigh) {
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    int64_t acc = 0;
+    for (int64_t e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) acc += has[col_idx[e]];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) nneigh[row] = static_cast<double>(acc);
+}
+
+__device__ __forceinline__ bool is_integral(double v) { return v == floor(v) && isfinite(v); }
+
+// log pmf of hypergeom(M_total = N, n_group = r, N_draws = n) at x through a log-factorial table
+__device__ __forceinline__ double hg_pmf(const double* __restrict__ lf, int64_t x, int64_t r, int64_t n, int64_t N) {
+    const double lp = (lf[r] - lf[x] - lf[r - x]) + (lf[N - r] - lf[n - x] - lf[N - r - n + x]) -
+                      (lf[N] - lf[n] - lf[N - n]);
+    return exp(lp);
+}
+
+// scipy.stats.hypergeom.sf(k, M, n, N) = rv_discrete.sf masking + Boost.Math cdf(complement(...)):
+// the smaller tail is summed with the pmf ratio recurrence from a single seeded pmf value.
+__device__ double hg_sf(const double* __restrict__ lf, double k, double Mt, double nK, double Nn) {
+    const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    const bool ok = (Mt > 0) && (nK >= 0) && (Nn >= 0) && (nK <= Mt) && (Nn <= Mt) && is_integral(Mt) &&
+                    is_integral(nK) && is_integral(Nn);
+    if (!ok || k != k) return nan;
+    const double a = fmax(Nn - (Mt - nK), 0.0), bsup = fmin(nK, Nn);
+    if (k < a) return 1.0;
+    if (!(k < bsup) || !isfinite(k)) return 0.0;
+    int64_t x = static_cast<int64_t>(floor(k));
+    const int64_t r = static_cast<int64_t>(nK), n = static_cast<int64_t>(Nn), N = static_cast<int64_t>(Mt);
+    const double eps = 2.220446049250313e-16;
+    const double mode = floor(static_cast<double>(r + 1) * static_cast<double>(n + 1) / static_cast<double>(N + 2));
+    double result;
+    if (static_cast<double>(x) < mode) {
+        result = hg_pmf(lf, x, r, n, N);
+        double diff = result;
+        const int64_t lower = max(static_cast<int64_t>(0), n + r - N);
+        while (diff > eps) {
+            diff = static_cast<double>(x) * static_cast<double>((N + x) - n - r) * diff /
+                   (static_cast<double>(1 + n - x) * static_cast<double>(1 + r - x));
+            result += diff;
+            if (x == lower) break;
+            --x;
+        }
+        result = 1.0 - result;
+    } else {
+        const int64_t upper = min(r, n);
+        result = 0.0;
+        if (x != upper) {
+            ++x;
+            result = hg_pmf(lf, x, r, n, N);
+            double diff = result;
+            while (x <= upper && diff > result * eps) {
+                diff = static_cast<double>(n - x) * static_cast<double>(r - x) * diff /
+                       (static_cast<double>(x + 1) * static_cast<double>((N + x + 1) - n - r));
+                result += diff;
+                ++x;
+            }
+        }
+    }
+    return fmin(fmax(result, 0.0), 1.0);
+}
+
+__global__ void __launch_bounds__(256) k_hypergeom(const double* __restrict__ X, const double* __restrict__ colsum,
+                                                   const double* __restrict__ nneigh, const double* __restrict__ lf,
+                                                   double n_total, int64_t n, int64_t m, double* __restrict__ pv,
+                                                   double* __restrict__ nes) {
+    const int64_t total = n * m;
+    int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; idx < total; idx += step) {
+        const int64_t i = idx / m, j = idx % m;
+        const double p = hg_sf(lf, X[idx] - 1.0, n_total, colsum[j], nneigh[i]);
+        if (pv) pv[idx] = p;
+        if (nes) nes[idx] = -log10(p);
+    }
+}
+
+__global__ void k_sum_i32(const int32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    unsigned long long s = 0;
+    for (; i < n; i += step) s += static_cast<unsigned long long>(v[i]);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void build_csr(sb_enrich* e) {
+    sb_ctx* ctx = e->ctx;
+    const int64_t n = e->n;
+    DevBuf<int64_t> cnt;
+    cnt.reserve(n);
+    e->row_ptr.reserve(n + 1);
+    const unsigned wblocks = static_cast<unsigned>(sb_ceil_div(n * 32, 256));
+    k_rowcount<<<wblocks, 256, 0, ctx->stream>>>(e->a->words, n, e->a->ld, cnt.p);
+    SB_LAUNCH_CHECK(ctx);
+    k_exscan<<<1, 1024, 0, ctx->stream>>>(cnt.p, n, e->row_ptr.p);
+    SB_LAUNCH_CHECK(ctx);
+    int64_t nnz = 0;
+    SB_CUDA(cudaMemcpyAsync(&nnz, e->row_ptr.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    e->nnz = nnz;
+    e->col_idx.reserve(std::max<int64_t>(nnz, 1));
+    k_fill_csr<<<wblocks, 256, 0, ctx->stream>>>(e->a->words, n, e->a->ld, e->row_ptr.p, e->col_idx.p);
+    SB_LAUNCH_CHECK(ctx);
+}
+
+void enrich_score_into(sb_enrich* e, int score_type, double* out_dev) {
+    sb_ctx* ctx = e->ctx;
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    dim3 grid(static_cast<unsigned>(e->n), static_cast<unsigned>(sb_ceil_div(e->m, 128)));
+    SB_CHECK(grid.y <= 65535, "attribute count %lld too large for one launch", (long long)e->m);
+    const bool zs = score_type == SB_SCORE_ZSCORE;
+    if (e->dtype == SB_F32) {
+        const float* b = static_cast<const float*>(e->b);
+        if (zs)
+            k_score<float, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+        else
+            k_score<float, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+    } else {
+        const double* b = static_cast<const double*>(e->b);
+        if (zs)
+            k_score<double, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+        else
+            k_score<double, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m,
+                                                                  out_dev);
+    }
+    SB_LAUNCH_CHECK(ctx);
+}
+
+const double* enrich_observed(sb_enrich* e, int score_type) {
+    if (score_type == SB_SCORE_SUM) {
+        if (!e->have_s0_sum) {
+            e->s0_sum.reserve(static_cast<size_t>(e->n) * e->m);
+            enrich_score_into(e, SB_SCORE_SUM, e->s0_sum.p);
+            e->have_s0_sum = true;
+        }
+        return e->s0_sum.p;
+    }
+    if (!e->have_s0_z) {
+        e->s0_z.reserve(static_cast<size_t>(e->n) * e->m);
+        enrich_score_into(e, SB_SCORE_ZSCORE, e->s0_z.p);
+        e->have_s0_z = true;
+    }
+    return e->s0_z.p;
+}
+
+void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg,
+                      uint32_t* cpos) {
+    sb_ctx* ctx = e->ctx;
+    const double* s0 = enrich_observed(e, score_type);
+    const bool zs = score_type == SB_SCORE_ZSCORE;
+    const int64_t max_cols = 65535ll * 128;
+    const int64_t pb = std::max<int64_t>(1, std::min(num_perm, max_cols / e->m));
+    SB_CHECK(e->m <= max_cols, "attribute count %lld too large", (long long)e->m);
+    for (int64_t p0 = 0; p0 < num_perm; p0 += pb) {
+        const int64_t np = std::min(pb, num_perm - p0);
+        const int64_t ncols = np * e->m;
+        dim3 grid(static_cast<unsigned>(e->n), static_cast<unsigned>(sb_ceil_div(ncols, 128)));
+        const int32_t* perm = perm_dev + p0 * e->n;
+#define SB_LAUNCH_PC(T, Z)                                                                                     \
+    k_perm_count<T, Z><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const T*>(e->b), \
+                                                      perm, e->n, e->m, ncols, s0, cneg, cpos)
+        if (e->dtype == SB_F32) {
+            if (zs)
+                SB_LAUNCH_PC(float, true);
+            else
+                SB_LAUNCH_PC(float, false);
+        } else {
+            if (zs)
+                SB_LAUNCH_PC(double, true);
+            else
+                SB_LAUNCH_PC(double, false);
+        }
+#undef SB_LAUNCH_PC
+        SB_LAUNCH_CHECK(ctx);
+    }
+}
+
+void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
+                 const unsigned int* flag_count_dev, unsigned int capacity, uint32_t* cneg, uint32_t* cpos) {
+    sb_ctx* ctx = e->ctx;
+    const double* s0 = enrich_observed(e, SB_SCORE_SUM);
+    const unsigned blocks = static_cast<unsigned>(ctx->num_sms * 8);
+    if (e->dtype == SB_F32)
+        k_fixup<float><<<blocks, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
+                                                        perm_dev, e->n, e->m, flag_ij, flag_p, flag_count_dev,
+                                                        capacity, s0, cneg, cpos);
+    else
+        k_fixup<double><<<blocks, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p,
+                                                         static_cast<const double*>(e->b), perm_dev, e->n, e->m,
+                                                         flag_ij, flag_p, flag_count_dev, capacity, s0, cneg, cpos);
+    SB_LAUNCH_CHECK(ctx);
+}
+
+static void hypergeom_dev(sb_enrich* e, double* pv_dev, double* nes_dev) {
+    sb_ctx* ctx = e->ctx;
+    const int64_t n = e->n, m = e->m;
+    const double* X = enrich_observed(e, SB_SCORE_SUM);
+    DevBuf<int32_t> has;
+    DevBuf<double> colsum, nneigh, lf;
+    DevBuf<unsigned long long> total;
+    has.reserve(n);
+    colsum.reserve(m);
+    nneigh.reserve(n);
+    total.reserve(1);
+    cudaStream_t st = ctx->stream;
+    const unsigned wblocks = static_cast<unsigned>(sb_ceil_div(n * 32, 256));
+    SB_CUDA(cudaMemsetAsync(colsum.p, 0, m * sizeof(double), st));
+    SB_CUDA(cudaMemsetAsync(total.p, 0, sizeof(unsigned long long), st));
+    dim3 cgrid(static_cast<unsigned>(sb_ceil_div(m, 128)),
+               static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, n / 256))));
+    if (e->dtype == SB_F32) {
+        k_has_data<float><<<wblocks, 256, 0, st>>>(static_cast<const float*>(e->b), n, m, has.p);
+        SB_LAUNCH_CHECK(ctx);
+        k_colsum<float><<<cgrid, 128, 0, st>>>(static_cast<const float*>(e->b), n, m, colsum.p);
+    } else {
+        k_has_data<double><<<wblocks, 256, 0, st>>>(static_cast<const double*>(e->b), n, m, has.p);
+        SB_LAUNCH_CHECK(ctx);
+        k_colsum<double><<<cgrid, 128, 0, st>>>(static_cast<const double*>(e->b), n, m, colsum.p);
+    }
+    SB_LAUNCH_CHECK(ctx);
+    k_sum_i32<<<64, 256, 0, st>>>(has.p, n, total.p);
+    SB_LAUNCH_CHECK(ctx);
+    k_nneigh<<<wblocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, has.p, n, nneigh.p);
+    SB_LAUNCH_CHECK(ctx);
+    unsigned long long n_total = 0;
+    SB_CUDA(cudaMemcpyAsync(&n_total, total.p, sizeof n_total, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    // log-factorial table lf[k] = lgamma(k + 1), k = 0..n_total
+    std::vector<double> h_lf(n_total + 2);
+    for (unsigned long long k = 0; k < h_lf.size(); ++k) h_lf[k] = std::lgamma(static_cast<double>(k) + 1.0);
+    lf.reserve(h_lf.size());
+    SB_CUDA(cudaMemcpyAsync(lf.p, h_lf.data(), h_lf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * m, 256), ctx->num_sms * 16));
+    k_hypergeom<<<blocks, 256, 0, st>>>(X, colsum.p, nneigh.p, lf.p, static_cast<double>(n_total), n, m, pv_dev,
+                                        nes_dev);
+    SB_LAUNCH_CHECK(ctx);
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+static size_t elem_size(int dtype) { return dtype == SB_F32 ? 4 : 8; }
+
+static sb_enrich* enrich_new(sb_ctx* ctx, sb_neigh* a, int dtype, int64_t n, int64_t m) {
+    SB_CHECK(ctx && a, "sb_enrich_create: NULL handle");
+    SB_CHECK(a->ctx == ctx, "sb_enrich_create: neighborhoods belong to another context");
+    SB_CHECK(dtype == SB_F32 || dtype == SB_F64, "sb_enrich_create: dtype must be SB_F32 or SB_F64");
+    SB_CHECK(n == a->n, "sb_enrich_create: attribute rows (%lld) != nodes (%lld)", (long long)n, (long long)a->n);
+    SB_CHECK(m > 0 && m < (1ll << 31), "sb_enrich_create: m=%lld out of range", (long long)m);
+    sb_enrich* e = new sb_enrich;
+    e->ctx = ctx;
+    e->a = a;
+    e->n = n;
+    e->m = m;
+    e->dtype = dtype;
+    return e;
+}
+
+extern "C" {
+
+int sb_enrich_create(sb_ctx* ctx, sb_neigh* a, const void* b_host, int dtype, int64_t n, int64_t m,
+                     sb_enrich** out) {
+    SB_API_BEGIN
+    SB_CHECK(out && b_host, "sb_enrich_create: NULL argument");
+    sb_enrich* e = enrich_new(ctx, a, dtype, n, m);
+    try {
+        ctx->bind();
+        void* d = nullptr;
+        const size_t bytes = static_cast<size_t>(n) * m * elem_size(dtype);
+        SB_CUDA(cudaMalloc(&d, bytes));
+        e->b = d;
+        e->b_owned = true;
+        SB_CUDA(cudaMemcpyAsync(d, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        build_csr(e);
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        sb_enrich_destroy(e);
+        throw;
+    }
+    *out = e;
+    SB_API_END
+}
+
+int sb_enrich_create_dev(sb_ctx* ctx, sb_neigh* a, const void* b_dev, int dtype, int64_t n, int64_t m,
+                         sb_enrich** out) {
+    SB_API_BEGIN
+    SB_CHECK(out && b_dev, "sb_enrich_create_dev: NULL argument");
+    sb_enrich* e = enrich_new(ctx, a, dtype, n, m);
+    try {
+        ctx->bind();
+        e->b = b_dev;
+        e->b_owned = false;
+        build_csr(e);
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    } catch (...) {
+        sb_enrich_destroy(e);
+        throw;
+    }
+    *out = e;
+    SB_API_END
+}
+
+int sb_enrich_destroy(sb_enrich* e) {
+    SB_API_BEGIN
+    if (e) {
+        e->ctx->bind();
+        if (e->tc) tc_plan_destroy(e->tc);
+        if (e->b_owned && e->b) cudaFree(const_cast<void*>(e->b));
+        delete e;
+    }
+    SB_API_END
+}
+
+int sb_enrich_score_dev(sb_enrich* e, int score_type, double* out_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e && out_dev, "sb_enrich_score_dev: NULL argument");
+    e->ctx->bind();
+    enrich_score_into(e, score_type, out_dev);
+    SB_API_END
+}
+
+int sb_enrich_score(sb_enrich* e, int score_type, double* out_host) {
+    SB_API_BEGIN
+    SB_CHECK(e && out_host, "sb_enrich_score: NULL argument");
+    e->ctx->bind();
+    const double* s = enrich_observed(e, score_type);
+    SB_CUDA(cudaMemcpyAsync(out_host, s, static_cast<size_t>(e->n) * e->m * sizeof(double), cudaMemcpyDeviceToHost,
+                            e->ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    SB_API_END
+}
+
+int sb_enrich_perm_counts_dev(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_dev,
+                              int64_t num_perm, uint32_t* counts_neg_dev, uint32_t* counts_pos_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e && perm_rows_dev && counts_neg_dev && counts_pos_dev, "sb_enrich_perm_counts_dev: NULL argument");
+    SB_CHECK(num_perm >= 0, "sb_enrich_perm_counts_dev: num_perm < 0");
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
+             engine);
+    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
+             "the tensor-core engine implements neighborhood_score_type 'sum' only");
+    e->ctx->bind();
+    if (num_perm == 0) return 0;
+    const bool use_tc = engine == SB_ENGINE_TC || (engine == SB_ENGINE_AUTO && score_type == SB_SCORE_SUM);
+    if (use_tc)
+        tc_perm_counts(e, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
+    else
+        simt_perm_counts(e, score_type, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
+    SB_API_END
+}
+
+int sb_enrich_perm_counts(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_host, int64_t num_perm,
+                          uint32_t* counts_neg_host, uint32_t* counts_pos_host) {
+    SB_API_BEGIN
+    SB_CHECK(e && perm_rows_host && counts_neg_host && counts_pos_host, "sb_enrich_perm_counts: NULL argument");
+    SB_CHECK(num_perm >= 0, "sb_enrich_perm_counts: num_perm < 0");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    DevBuf<uint32_t> cnt;
+    cnt.reserve(2 * cells);
+    SB_CUDA(cudaMemsetAsync(cnt.p, 0, 2 * cells * sizeof(uint32_t), ctx->stream));
+    // stream permutation indices in chunks of <= 1 GiB
+    const int64_t chunk = std::max<int64_t>(1, (256ll << 20) / e->n);
+    DevBuf<int32_t> perm;
+    perm.reserve(static_cast<size_t>(std::min(chunk, std::max<int64_t>(num_perm, 1))) * e->n);
+    for (int64_t p0 = 0; p0 < num_perm; p0 += chunk) {
+        const int64_t np = std::min(chunk, num_perm - p0);
+        SB_CUDA(cudaMemcpyAsync(perm.p, perm_rows_host + p0 * e->n, static_cast<size_t>(np) * e->n * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        int rc = sb_enrich_perm_counts_dev(e, score_type, engine, perm.p, np, cnt.p, cnt.p + cells);
+        if (rc) fail("%s", sb_last_error());
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    SB_CUDA(cudaMemcpyAsync(counts_neg_host, cnt.p, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(counts_pos_host, cnt.p + cells, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_API_END
+}
+
+int sb_enrich_stats(sb_enrich* e, int64_t* out7_host) {
+    SB_API_BEGIN
+    SB_CHECK(e && out7_host, "sb_enrich_stats: NULL argument");
+    for (int i = 0; i < 7; ++i) out7_host[i] = e->stats[i];
+    SB_API_END
+}
+
+int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_hypergeom_dev: NULL handle");
+    e->ctx->bind();
+    hypergeom_dev(e, pvalues_dev, nes_dev);
+    SB_API_END
+}
+
+int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_hypergeom: NULL handle");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    DevBuf<double> pv, nes;
+    if (pvalues_host) pv.reserve(cells);
+    if (nes_host) nes.reserve(cells);
+    hypergeom_dev(e, pv.p, nes.p);
+    if (pvalues_host)
+        SB_CUDA(cudaMemcpyAsync(pvalues_host, pv.p, cells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (nes_host)
+        SB_CUDA(cudaMemcpyAsync(nes_host, nes.p, cells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,893 @@
+// Stage 2 on the 5th-generation tensor cores: permutation null as a block-sparse int8 digit GEMM with the
+// "null vs observed" comparison fused into the TMEM epilogue (permuted scores never reach HBM).
+// Replaces the hot loop of run_permutations (reference safepy/safe_extras.py:56-66) for 'sum' scores.
+//
+// Arithmetic.  A is {0,1}.  Every attribute column j of nan0(B) is turned into a fixed-point integer
+// q = rint(v * 2^s_j) and written as D balanced base-256 digits (int8).  S_fix = A @ q is then computed EXACTLY by
+// tcgen05.mma.kind::i8 (int32 accumulators in TMEM, one accumulator per digit plane, recombined in int64 in the
+// epilogue).  If a column is exactly representable (binary / integer / dyadic data) S_fix comparisons ARE the
+// reference's comparisons.  Otherwise |S_fix - 2^s * S_true| <= n_i / 2, so |S_fix(p) - S_fix(0)| > n_i decides the
+// comparison rigorously and the rare remainder is appended to a list that enrich.cu re-evaluates in fp64.
+//
+// Data movement.  A lives as a list of non-empty 128 x 64 int8 tiles per 128-row block (empty tiles are skipped:
+// with spatially ordered nodes most of them are).  The permuted operand of a batch of permutations is gathered
+// once into "Bcat" tiles (64 x 64*D int8).  Both tile kinds are stored in HBM in the tensor core's canonical
+// no-swizzle core-matrix order, so one 1-D bulk async copy (TMA engine, UBLKCP) per tile lands them in shared
+// memory ready for the MMA.  Per CTA: warp 0 = copy producer, warp 1 = MMA issuer, warps 2-5 = epilogue;
+// smem ring of STAGES (A,B) tile pairs; two TMEM accumulator buffers so the epilogue of slot q overlaps the MMAs
+// of slot q+1.
+#include <algorithm>
+#include <climits>
+#include <vector>
+
+#include "enrich.cuh"
+#include "sm100_ptx.cuh"
+
+namespace sb {
+
+constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
+constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
+constexpr int TC_TILE_A = TC_ROWS * TC_KT;
+constexpr int TC_THREADS = 192;
+constexpr int TC_KT_CAP = 2048;          // k-tile ids of one row block staged in smem by the producer
+constexpr int TC_S0_BYTES = 64 * TC_ROWS * 8;
+
+enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
+
+struct GemmParams {
+    const int8_t* a_tiles;
+    const int32_t* tile_ptr;  // [n_rb + 1]
+    const int32_t* tile_kt;   // [n_tiles]
+    const int8_t* bcat;       // [slot][kt][64 x 64*D]
+    int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;
+    int32_t mode;
+    int64_t n, m, mpad;
+    int32_t log2_mpad, pps, batch_perms;
+    int64_t* s0fix;           // [n_rb * 128][mpad]
+    const int64_t* row_ptr;   // band_i = row_ptr[i+1] - row_ptr[i]
+    const uint8_t* inexact;   // [mpad]
+    uint32_t* cneg;
+    uint32_t* cpos;
+    uint64_t* flag_ij;
+    uint32_t* flag_p;
+    unsigned int* flag_count;
+    unsigned int flag_cap;
+    int32_t* raw_out;         // TCM_RAW: [128][64*D]
+    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+};
+
+template <int D>
+struct TcCfg {
+    static constexpr int NCOLS = 64 * D;
+    static constexpr int TILE_B = TC_KT * NCOLS;
+    static constexpr int STAGE = TC_TILE_A + TILE_B;
+    static constexpr int STAGES = D == 3 ? 7 : 8;
+    static constexpr int SMEM = STAGES * STAGE + TC_S0_BYTES + TC_KT_CAP * 4 + 256;
+};
+
+template <int D>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
+    using C = TcCfg<D>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + C::STAGES * TC_TILE_A;
+    long long* s0s = reinterpret_cast<long long*>(smem + C::STAGES * C::STAGE);
+    int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES + TC_KT_CAP * 4);
+    uint64_t* full = bars;                      // [STAGES]
+    uint64_t* empty = bars + C::STAGES;         // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;     // [2]
+    uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tfull[b], 1);
+            mbar_init(&tempty[b], 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tbase = *tmem_slot;
+
+    const int n_units = p.n_rb * p.n_cg * p.q_chunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ producer: bulk copies into the smem ring
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
+            const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
+            const int t0 = p.tile_ptr[rb], nk = p.tile_ptr[rb + 1] - t0;
+            __syncwarp();
+            for (int i = lane; i < min(nk, TC_KT_CAP); i += 32) s_kt[i] = p.tile_kt[t0 + i];
+            __syncwarp();
+            if (lane == 0) {
+                for (int q = q0; q < q1; ++q) {
+                    const int8_t* bslot =
+                        p.bcat + (static_cast<size_t>(q) * p.n_cg + cg) * static_cast<size_t>(p.n_kt) * C::TILE_B;
+                    for (int i = 0; i < nk; ++i) {
+                        const int kt = i < TC_KT_CAP ? s_kt[i] : p.tile_kt[t0 + i];
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], C::STAGE);
+                        bulk_g2s(sA + stage * TC_TILE_A, p.a_tiles + static_cast<size_t>(t0 + i) * TC_TILE_A,
+                                 TC_TILE_A, &full[stage]);
+                        bulk_g2s(sB + stage * C::TILE_B, bslot + static_cast<size_t>(kt) * C::TILE_B, C::TILE_B,
+                                 &full[stage]);
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0,
+                                                /*b MN*/ 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc_it = 0;  // accumulations issued so far: buffer = it & 1, barrier phase = (it >> 1) & 1
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                const int rb = u % p.n_rb, qc = (u / p.n_rb) / p.n_cg;
+                const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
+                const int nk = p.tile_ptr[rb + 1] - p.tile_ptr[rb];
+                for (int q = q0; q < q1; ++q) {
+                    const uint32_t buf = acc_it & 1u, tpar = (acc_it >> 1) & 1u;
+                    mbar_wait(&tempty[buf], tpar ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tbase + buf * 256;
+                    for (int i = 0; i < nk; ++i) {
+                        mbar_wait(&full[stage], phase);
+                        tc_fence_after();
+                        const uint32_t a0 = smem_u32(sA + stage * TC_TILE_A);
+                        const uint32_t b0 = smem_u32(sB + stage * C::TILE_B);
+#pragma unroll
+                        for (int ks = 0; ks < TC_KT / 32; ++ks) {
+                            // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
+                            // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
+                            const uint64_t adesc = smem_desc_noswz(a0 + ks * 2 * 2048, p.a_lbo, p.a_sbo);
+                            const uint64_t bdesc = smem_desc_noswz(b0 + ks * 4 * (C::NCOLS * 8), p.b_lbo, p.b_sbo);
+                            mma_i8_ss(d_tmem, adesc, bdesc, idesc, (i | ks) != 0);
+                        }
+                        mma_commit(&empty[stage]);
+                        if (++stage == C::STAGES) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                    mma_commit(&tfull[buf]);
+                    ++acc_it;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
+        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int row_in_tile = quarter * 32 + lane;
+        uint32_t acc_it = 0;
+        const bool small_m = p.mpad < 64;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
+            const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
+            const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + row_in_tile;
+            const bool row_ok = row < p.n;
+            const int64_t jbase = small_m ? 0 : static_cast<int64_t>(cg) * 64;
+            long long band = 0;
+            unsigned long long inexact_mask = 0;
+            if (p.mode & (TCM_COUNT | TCM_FLAG)) {
+                band = row_ok ? (p.row_ptr[row + 1] - p.row_ptr[row]) : 0;
+#pragma unroll 4
+                for (int c = 0; c < 64; ++c) {
+                    const int64_t j = small_m ? (c & (p.mpad - 1)) : jbase + c;
+                    if (p.inexact[j]) inexact_mask |= 1ull << c;
+                    // thread-private column of the observed fixed-point score tile
+                    s0s[c * TC_ROWS + row_in_tile] = p.s0fix[row * p.mpad + j];
+                }
+            }
+            uint32_t cnt[64];
+#pragma unroll
+            for (int c = 0; c < 64; ++c) cnt[c] = 0;
+
+            for (int q = q0; q < q1; ++q) {
+                const uint32_t buf = acc_it & 1u, tpar = (acc_it >> 1) & 1u;
+                mbar_wait(&tfull[buf], tpar);
+                tc_fence_after();
+                const uint32_t t_addr = tbase + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256;
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) {
+                    uint32_t acc[D][16];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) tmem_ld16(t_addr + d * 64 + ch * 16, acc[d]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int cc = 0; cc < 16; ++cc) {
+                        const int c = ch * 16 + cc;
+                        if (p.mode & TCM_RAW) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d)
+                                p.raw_out[row_in_tile * C::NCOLS + d * 64 + c] = static_cast<int32_t>(acc[d][cc]);
+                            continue;
+                        }
+                        long long S = static_cast<int32_t>(acc[0][cc]);
+                        if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][cc])) << 8;
+                        if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][cc])) << 16;
+                        if (p.mode & TCM_STORE) {
+                            const bool col_ok = small_m ? (c < p.mpad) : true;
+                            if (col_ok) p.s0fix[row * p.mpad + jbase + c] = S;
+                            continue;
+                        }
+                        const int pl = small_m ? q * p.pps + (c >> p.log2_mpad) : q;
+                        const bool valid = pl < p.batch_perms;
+                        const long long diff = S - s0s[c * TC_ROWS + row_in_tile];
+                        const long long b = ((inexact_mask >> c) & 1ull) ? band : 0;
+                        const bool gt = diff > b, lt = diff < -b;
+                        const bool und = !(gt | lt);
+                        const bool tie = und && b == 0;
+                        if (p.mode & TCM_COUNT)
+                            cnt[c] += valid ? ((static_cast<uint32_t>(gt | tie) << 16) | static_cast<uint32_t>(lt | tie))
+                                            : 0u;
+                        if ((p.mode & TCM_FLAG) && und && b != 0 && valid && row_ok) {
+                            const int64_t j = small_m ? (c & (p.mpad - 1)) : jbase + c;
+                            if (j < p.m) {
+                                const unsigned int k = atomicAdd(p.flag_count, 1u);
+                                if (k < p.flag_cap) {
+                                    p.flag_ij[k] = (static_cast<uint64_t>(row) << 32) | static_cast<uint64_t>(j);
+                                    p.flag_p[k] = static_cast<uint32_t>(pl);
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                ++acc_it;
+            }
+            if ((p.mode & TCM_COUNT) && row_ok) {
+                if (small_m) {
+                    // columns c and c' with c % mpad == c' % mpad carry different permutations of the same attribute
+                    for (int j = 0; j < p.mpad && j < p.m; ++j) {
+                        uint32_t pos = 0, neg = 0;
+#pragma unroll
+                        for (int c = 0; c < 64; ++c)
+                            if ((c & (p.mpad - 1)) == j) {
+                                pos += cnt[c] >> 16;
+                                neg += cnt[c] & 0xffffu;
+                            }
+                        if (pos) atomicAdd(&p.cpos[row * p.m + j], pos);
+                        if (neg) atomicAdd(&p.cneg[row * p.m + j], neg);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) {
+                        const int64_t j = jbase + c;
+                        if (j < p.m) {
+                            const uint32_t pos = cnt[c] >> 16, neg = cnt[c] & 0xffffu;
+                            if (pos) atomicAdd(&p.cpos[row * p.m + j], pos);
+                            if (neg) atomicAdd(&p.cneg[row * p.m + j], neg);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ operand builders
+// occupancy of 128 x 64 tiles of the packed matrix; one block per row block
+__global__ void __launch_bounds__(256) k_tile_occ(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
+                                                  int32_t n_kt, uint8_t* __restrict__ occ,
+                                                  int32_t* __restrict__ rb_count) {
+    const int rb = blockIdx.x;
+    const int64_t r0 = static_cast<int64_t>(rb) * TC_ROWS, r1 = min(n, r0 + TC_ROWS);
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int kt = threadIdx.x; kt < n_kt; kt += blockDim.x) {
+        uint32_t any = 0;
+        for (int64_t r = r0; r < r1; ++r) {
+            const uint2 w = *reinterpret_cast<const uint2*>(words + r * ld + 2 * kt);
+            any |= w.x | w.y;
+        }
+        occ[static_cast<size_t>(rb) * n_kt + kt] = any ? 1 : 0;
+        mine += any ? 1 : 0;
+    }
+    if (mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_total == 0) {  // keep at least one (all-zero) tile so every row block still runs its epilogue
+            occ[static_cast<size_t>(rb) * n_kt] = 1;
+            s_total = 1;
+        }
+        rb_count[rb] = s_total;
+    }
+}
+
+// tile_kt / tile_rb lists from the occupancy flags; one block per row block (serial chunks + block scan)
+__global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ occ, int32_t n_kt,
+                                                   const int32_t* __restrict__ tile_ptr, int32_t* __restrict__ tile_kt,
+                                                   int32_t* __restrict__ tile_rb) {
+    const int rb = blockIdx.x;
+    __shared__ int part[256];
+    const int chunk = (n_kt + 255) / 256;
+    const int b = threadIdx.x * chunk, e = min(n_kt, b + chunk);
+    int c = 0;
+    for (int kt = b; kt < e; ++kt) c += occ[static_cast<size_t>(rb) * n_kt + kt];
+    part[threadIdx.x] = c;
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int at = tile_ptr[rb] + (threadIdx.x ? part[threadIdx.x - 1] : 0);
+    for (int kt = b; kt < e; ++kt)
+        if (occ[static_cast<size_t>(rb) * n_kt + kt]) {
+            tile_kt[at] = kt;
+            tile_rb[at] = rb;
+            ++at;
+        }
+}
+
+// expand one 128 x 64 bit tile into int8 {0,1} in K-major core-matrix order:
+//   byte offset = kc * 2048 + row * 16 + (k & 15),  kc = k >> 4
+__global__ void __launch_bounds__(256) k_expand_tiles(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
+                                                      const int32_t* __restrict__ tile_kt,
+                                                      const int32_t* __restrict__ tile_rb, int8_t* __restrict__ out) {
+    const int tile = blockIdx.x;
+    const int kt = tile_kt[tile], rb = tile_rb[tile];
+    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(tile) * TC_TILE_A);
+    for (int it = threadIdx.x; it < 512; it += blockDim.x) {
+        const int kc = it >> 7, r = it & 127;
+        const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + r;
+        uint32_t bits = 0;
+        if (row < n) bits = (words[row * ld + 2 * kt + (kc >> 1)] >> ((kc & 1) * 16)) & 0xffffu;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t nib = (bits >> (4 * q)) & 0xfu;
+            w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        dst[it] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+// per-column exponent range of nan0(B): kmax = exponent of the largest magnitude, lmin = exponent of the lowest
+// set mantissa bit over all non-zero values.  flags: bit0 = some value is +-inf
+template <class T>
+__global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32_t* __restrict__ kmax,
+                            int32_t* __restrict__ lmin, int32_t* __restrict__ flags) {
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= m) return;
+    const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
+    int hi = INT_MIN, lo = INT_MAX, bad = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const double v = static_cast<double>(b[r * m + j]);
+        if (v != v || v == 0.0) continue;
+        if (isinf(v)) {
+            bad = 1;
+            continue;
+        }
+        int e;
+        const double f = frexp(fabs(v), &e);  // |v| = f * 2^e, f in [0.5, 1)
+        const long long mant = static_cast<long long>(ldexp(f, 53));
+        hi = max(hi, e - 1);
+        lo = min(lo, e - 53 + (__ffsll(mant) - 1));
+    }
+    if (hi != INT_MIN) {
+        atomicMax(&kmax[j], hi);
+        atomicMin(&lmin[j], lo);
+    }
+    if (bad) atomicOr(flags, 1);
+}
+
+// fixed-point digits: q = rint(v * 2^shift[j]) as D balanced base-256 int8 digits, plane d at digits + d*n*mpad
+template <class T, int D>
+__global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_t mpad,
+                           const int32_t* __restrict__ shift, int8_t* __restrict__ digits) {
+    const int64_t total = n * mpad;
+    int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; idx < total; idx += step) {
+        const int64_t r = idx / mpad, j = idx % mpad;
+        int q = 0;
+        if (j < m) {
+            const double v = static_cast<double>(b[r * m + j]);
+            if (v == v) q = static_cast<int>(rint(ldexp(v, shift[j])));
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            int dig;
+            if (d == D - 1) {
+                dig = q;
+            } else {
+                dig = static_cast<int>(static_cast<int8_t>(q & 0xff));
+                q = (q - dig) >> 8;
+            }
+            digits[static_cast<size_t>(d) * total + idx] = static_cast<int8_t>(dig);
+        }
+    }
+}
+
+// Bcat tiles for a batch: tile (slot, kt) = 64 K-rows x 64*D columns in MN-major core-matrix order:
+//   16-byte chunk index ch = kg * (NC16*8) + nc * 8 + r   (k = kg*8 + r, columns nc*16 .. nc*16+15)
+// column nc*16+x of the tile = digit plane (nc / 4), attribute/permutation column c = (nc & 3) * 16 + x.
+template <int D>
+__global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digits, const int32_t* __restrict__ perm,
+                                                int64_t n, int64_t mpad, int32_t n_kt, int32_t n_cg, int32_t pps,
+                                                int32_t log2_mpad, int32_t batch_perms, int8_t* __restrict__ bcat) {
+    constexpr int NC16 = 4 * D;
+    constexpr int CHUNKS = TC_KT * NC16;
+    const int kt = blockIdx.x;
+    const int slot = blockIdx.y;
+    const int q = slot / n_cg, cg = slot % n_cg;
+    uint4* dst = reinterpret_cast<uint4*>(bcat + (static_cast<size_t>(slot) * n_kt + kt) * (TC_KT * 64 * D));
+    const size_t plane = static_cast<size_t>(n) * mpad;
+    for (int ch = threadIdx.x; ch < CHUNKS; ch += blockDim.x) {
+        const int kg = ch / (NC16 * 8), rem = ch % (NC16 * 8), nc = rem >> 3, r = rem & 7;
+        const int64_t t = static_cast<int64_t>(kt) * TC_KT + kg * 8 + r;
+        const int d = nc >> 2, jc = nc & 3;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (t < n) {
+            if (mpad >= 64) {
+                const int64_t src = perm ? perm[static_cast<int64_t>(q) * n + t] : t;
+                v = *reinterpret_cast<const uint4*>(digits + d * plane + src * mpad + static_cast<int64_t>(cg) * 64 +
+                                                    jc * 16);
+            } else {
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int x = 0; x < 16; ++x) {
+                    const int c = jc * 16 + x;
+                    const int pl = q * pps + (c >> log2_mpad);
+                    const int j = c & (static_cast<int>(mpad) - 1);
+                    if (pl < batch_perms) {
+                        const int64_t src = perm ? perm[static_cast<int64_t>(pl) * n + t] : t;
+                        const uint32_t byte = static_cast<uint8_t>(digits[d * plane + src * mpad + j]);
+                        w[x >> 2] |= byte << ((x & 3) * 8);
+                    }
+                }
+                v = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        dst[ch] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ plan
+struct TcPlan {
+    int D = 0;
+    int64_t n = 0, m = 0, mpad = 0;
+    int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
+    int64_t n_tiles = 0;
+    bool usable = true;  // false: data contains +-inf -> SIMT engine
+    DevBuf<int8_t> a_tiles;
+    DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
+    DevBuf<int8_t> digits;
+    DevBuf<uint8_t> inexact;
+    DevBuf<int64_t> s0fix;
+    DevBuf<int8_t> bcat;
+    DevBuf<uint64_t> flag_ij;
+    DevBuf<uint32_t> flag_p;
+    DevBuf<unsigned int> flag_count;
+    unsigned int flag_cap = 0;
+    int64_t slots_cap = 0;
+};
+
+void tc_plan_destroy(TcPlan* p) { delete p; }
+
+template <int D>
+static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
+    using C = TcCfg<D>;
+    static bool configured = false;
+    if (!configured) {
+        SB_CUDA(cudaFuncSetAttribute(k_gemm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    k_gemm<D><<<grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
+    SB_LAUNCH_CHECK(ctx);
+}
+
+static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp, int grid) {
+    if (D == 1)
+        launch_gemm<1>(ctx, gp, grid);
+    else if (D == 2)
+        launch_gemm<2>(ctx, gp, grid);
+    else
+        launch_gemm<3>(ctx, gp, grid);
+}
+
+static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
+    dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
+    SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
+#define SB_G(DD)                                                                                              \
+    k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->n, pl->mpad, pl->n_kt, pl->n_cg, pl->pps, \
+                                                pl->log2_mpad, batch_perms, pl->bcat.p)
+    if (pl->D == 1)
+        SB_G(1);
+    else if (pl->D == 2)
+        SB_G(2);
+    else
+        SB_G(3);
+#undef SB_G
+    SB_LAUNCH_CHECK(ctx);
+}
+
+static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
+    GemmParams gp{};
+    gp.a_tiles = pl->a_tiles.p;
+    gp.tile_ptr = pl->tile_ptr.p;
+    gp.tile_kt = pl->tile_kt.p;
+    gp.bcat = pl->bcat.p;
+    gp.n_kt = pl->n_kt;
+    gp.n_rb = pl->n_rb;
+    gp.n_cg = pl->n_cg;
+    gp.n = pl->n;
+    gp.m = pl->m;
+    gp.mpad = pl->mpad;
+    gp.log2_mpad = pl->log2_mpad;
+    gp.pps = pl->pps;
+    gp.s0fix = pl->s0fix.p;
+    gp.row_ptr = e->row_ptr.p;
+    gp.inexact = pl->inexact.p;
+    gp.flag_ij = pl->flag_ij.p;
+    gp.flag_p = pl->flag_p.p;
+    gp.flag_count = pl->flag_count.p;
+    gp.flag_cap = pl->flag_cap;
+    const uint32_t ncols = 64u * pl->D;
+    gp.a_lbo = 2048;       // K-major A: stride between the two 16-byte K chunks of one MMA
+    gp.a_sbo = 128;        //            stride between 8-row groups
+    gp.b_lbo = ncols * 8;  // MN-major B: stride between 8-row K groups
+    gp.b_sbo = 128;        //             stride between 16-column chunks
+    return gp;
+}
+
+static int64_t slots_for(const TcPlan* pl, int64_t perms) {
+    return pl->mpad >= 64 ? perms * pl->n_cg : sb_ceil_div(perms, pl->pps);
+}
+
+static TcPlan* build_plan(sb_enrich* e) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    TcPlan* pl = new TcPlan;
+    try {
+        const int64_t n = e->n, m = e->m;
+        pl->n = n;
+        pl->m = m;
+        if (m >= 64) {
+            pl->mpad = sb_ceil_div(m, 64) * 64;
+            pl->n_cg = static_cast<int32_t>(pl->mpad / 64);
+            pl->pps = 1;
+            pl->log2_mpad = 0;
+        } else {
+            int lg = 0;
+            while ((1 << lg) < m) ++lg;
+            pl->mpad = 1 << lg;
+            pl->log2_mpad = lg;
+            pl->n_cg = 1;
+            pl->pps = static_cast<int32_t>(64 / pl->mpad);
+        }
+        pl->n_rb = static_cast<int32_t>(sb_ceil_div(n, TC_ROWS));
+        pl->n_kt = static_cast<int32_t>(sb_ceil_div(n, TC_KT));
+
+        // ---- A tiles
+        DevBuf<uint8_t> occ;
+        DevBuf<int32_t> rb_count;
+        occ.reserve(static_cast<size_t>(pl->n_rb) * pl->n_kt);
+        rb_count.reserve(pl->n_rb);
+        k_tile_occ<<<pl->n_rb, 256, 0, st>>>(e->a->words, n, e->a->ld, pl->n_kt, occ.p, rb_count.p);
+        SB_LAUNCH_CHECK(ctx);
+        std::vector<int32_t> h_cnt(pl->n_rb), h_ptr(pl->n_rb + 1);
+        SB_CUDA(cudaMemcpyAsync(h_cnt.data(), rb_count.p, pl->n_rb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        int64_t run = 0;
+        for (int i = 0; i < pl->n_rb; ++i) {
+            h_ptr[i] = static_cast<int32_t>(run);
+            run += h_cnt[i];
+        }
+        SB_CHECK(run < (1ll << 31), "too many non-empty neighborhood tiles (%lld)", (long long)run);
+        h_ptr[pl->n_rb] = static_cast<int32_t>(run);
+        pl->n_tiles = run;
+        pl->tile_ptr.reserve(pl->n_rb + 1);
+        pl->tile_kt.reserve(run);
+        pl->tile_rb.reserve(run);
+        pl->a_tiles.reserve(static_cast<size_t>(run) * TC_TILE_A);
+        SB_CUDA(cudaMemcpyAsync(pl->tile_ptr.p, h_ptr.data(), (pl->n_rb + 1) * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, st));
+        k_tile_list<<<pl->n_rb, 256, 0, st>>>(occ.p, pl->n_kt, pl->tile_ptr.p, pl->tile_kt.p, pl->tile_rb.p);
+        SB_LAUNCH_CHECK(ctx);
+        k_expand_tiles<<<static_cast<unsigned>(run), 256, 0, st>>>(e->a->words, n, e->a->ld, pl->tile_kt.p,
+                                                                  pl->tile_rb.p, pl->a_tiles.p);
+        SB_LAUNCH_CHECK(ctx);
+
+        // ---- digit planes
+        DevBuf<int32_t> kmax, lmin, flags, shift;
+        kmax.reserve(m);
+        lmin.reserve(m);
+        flags.reserve(1);
+        std::vector<int32_t> h_kmax(m, INT_MIN), h_lmin(m, INT_MAX);
+        SB_CUDA(cudaMemcpyAsync(kmax.p, h_kmax.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpyAsync(lmin.p, h_lmin.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t), st));
+        dim3 cgrid(static_cast<unsigned>(sb_ceil_div(m, 128)),
+                   static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, n / 256))));
+        if (e->dtype == SB_F32)
+            k_col_range<float><<<cgrid, 128, 0, st>>>(static_cast<const float*>(e->b), n, m, kmax.p, lmin.p, flags.p);
+        else
+            k_col_range<double><<<cgrid, 128, 0, st>>>(static_cast<const double*>(e->b), n, m, kmax.p, lmin.p,
+                                                       flags.p);
+        SB_LAUNCH_CHECK(ctx);
+        int32_t h_flags = 0;
+        SB_CUDA(cudaMemcpyAsync(h_kmax.data(), kmax.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(h_lmin.data(), lmin.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (h_flags & 1) {
+            pl->usable = false;
+            return pl;
+        }
+        // digits needed for exactness: a column needs bits = kmax - lmin + 1 magnitude bits; D balanced digits hold
+        // |q| <= 127 * (256^D - 1) / 255, i.e. bits <= 8 D - 2
+        int D = 1;
+        for (int64_t j = 0; j < m; ++j)
+            if (h_kmax[j] != INT_MIN) {
+                const int bits = h_kmax[j] - h_lmin[j] + 1;
+                D = std::max(D, std::min(3, (bits + 2 + 7) / 8));
+            }
+        pl->D = D;
+        std::vector<int32_t> h_shift(m, 0);
+        std::vector<uint8_t> h_inexact(pl->mpad, 0);
+        for (int64_t j = 0; j < m; ++j) {
+            if (h_kmax[j] == INT_MIN) continue;
+            const int bits = h_kmax[j] - h_lmin[j] + 1;
+            if (bits <= 8 * D - 2) {
+                h_shift[j] = -h_lmin[j];  // lowest set bit lands on 2^0: every value is an exact integer
+            } else {
+                h_shift[j] = (8 * D - 3) - h_kmax[j];  // |q| < 2^(8D-2)
+                h_inexact[j] = 1;
+            }
+        }
+        shift.reserve(m);
+        pl->inexact.reserve(pl->mpad);
+        SB_CUDA(cudaMemcpyAsync(shift.p, h_shift.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpyAsync(pl->inexact.p, h_inexact.data(), pl->mpad, cudaMemcpyHostToDevice, st));
+        pl->digits.reserve(static_cast<size_t>(D) * n * pl->mpad);
+        const unsigned qblocks =
+            static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * pl->mpad, 256), ctx->num_sms * 32));
+#define SB_Q(T, DD) \
+    k_quantize<T, DD><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad, shift.p, pl->digits.p)
+        if (e->dtype == SB_F32) {
+            if (D == 1) SB_Q(float, 1);
+            else if (D == 2) SB_Q(float, 2);
+            else SB_Q(float, 3);
+        } else {
+            if (D == 1) SB_Q(double, 1);
+            else if (D == 2) SB_Q(double, 2);
+            else SB_Q(double, 3);
+        }
+#undef SB_Q
+        SB_LAUNCH_CHECK(ctx);
+        SB_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
+
+        // ---- flag list (capacity >= one slot's worst case so that overflow recovery always terminates)
+        const int64_t worst_slot = static_cast<int64_t>(pl->n_rb) * TC_ROWS * 64 * (pl->mpad >= 64 ? pl->n_cg : 1);
+        pl->flag_cap = static_cast<unsigned int>(std::min<int64_t>(std::max<int64_t>(4ll << 20, worst_slot), 1ll << 31));
+        pl->flag_ij.reserve(pl->flag_cap);
+        pl->flag_p.reserve(pl->flag_cap);
+        pl->flag_count.reserve(1);
+
+        // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
+        const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
+        const int64_t slots1 = slots_for(pl, 1);
+        pl->bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
+        pl->slots_cap = slots1;
+        pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_ROWS * pl->mpad);
+        launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1);
+        GemmParams gp = base_params(e, pl);
+        gp.mode = TCM_STORE;
+        gp.q_total = 1;
+        gp.q_chunks = 1;
+        gp.q_per = 1;
+        gp.batch_perms = 1;
+        const int units = pl->n_rb * pl->n_cg;
+        launch_gemm_d(ctx, D, gp, std::min(units, ctx->num_sms));
+        SB_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        delete pl;
+        throw;
+    }
+    return pl;
+}
+
+// one GEMM launch over slots [0, q_total) of the gathered batch
+static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int batch_perms, uint32_t* cneg,
+                           uint32_t* cpos) {
+    sb_ctx* ctx = e->ctx;
+    GemmParams gp = base_params(e, pl);
+    gp.mode = mode;
+    gp.q_total = q_total;
+    gp.batch_perms = batch_perms;
+    gp.cneg = cneg;
+    gp.cpos = cpos;
+    const int base_units = pl->n_rb * pl->n_cg;
+    int q_chunks = 1;
+    if (base_units < 2 * ctx->num_sms) q_chunks = std::min<int>(q_total, sb_ceil_div(2 * ctx->num_sms, base_units));
+    gp.q_per = static_cast<int32_t>(sb_ceil_div(q_total, q_chunks));
+    gp.q_chunks = static_cast<int32_t>(sb_ceil_div(q_total, gp.q_per));
+    const int units = base_units * gp.q_chunks;
+    launch_gemm_d(ctx, pl->D, gp, std::min(units, ctx->num_sms));
+}
+
+void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    if (!e->tc) e->tc = build_plan(e);
+    TcPlan* pl = e->tc;
+    if (!pl->usable) {  // +-inf in the data: fixed point cannot represent it
+        simt_perm_counts(e, SB_SCORE_SUM, perm_dev, num_perm, cneg, cpos);
+        return;
+    }
+    enrich_observed(e, SB_SCORE_SUM);  // fp64 observed scores for the fix-up kernel
+
+    // batch size: Bcat workspace <= ~1/8 of free memory (at most 16 GiB), q per unit < 32768 (16-bit counters)
+    size_t free_b = 0, total_b = 0;
+    SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
+    const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
+    const size_t budget = std::min<size_t>(std::max<size_t>(free_b / 8, slot_bytes * slots_for(pl, 1)), 16ull << 30);
+    int64_t max_slots = std::max<int64_t>(slots_for(pl, 1), static_cast<int64_t>(budget / slot_bytes));
+    max_slots = std::min<int64_t>(max_slots, 65535);
+    int64_t pb = pl->mpad >= 64 ? max_slots / pl->n_cg : max_slots * pl->pps;
+    pb = std::max<int64_t>(1, std::min<int64_t>(pb, 16384));
+    pb = std::min(pb, num_perm);
+    const int64_t need_slots = slots_for(pl, pb);
+    if (need_slots > pl->slots_cap) {
+        pl->bcat.reserve(static_cast<size_t>(need_slots) * slot_bytes);
+        pl->slots_cap = need_slots;
+    }
+
+    int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
+    int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;
+    for (int64_t p0 = 0; p0 < num_perm; p0 += pb) {
+        const int64_t np = std::min(pb, num_perm - p0);
+        const int32_t* perm = perm_dev + p0 * e->n;
+        const int slots = static_cast<int>(slots_for(pl, np));
+        const int q_total = pl->mpad >= 64 ? static_cast<int>(np) : slots;
+        launch_gather(ctx, pl, perm, slots, static_cast<int>(np));
+        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+        run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, q_total, static_cast<int>(np), cneg, cpos);
+        ktile_iters += tiles_per_pass * q_total;
+        unsigned int h_flags = 0;
+        SB_CUDA(cudaMemcpyAsync(&h_flags, pl->flag_count.p, sizeof h_flags, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (h_flags <= pl->flag_cap) {
+            if (h_flags)
+                fixup_flags(e, perm, pl->flag_ij.p, pl->flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
+            flagged += h_flags;
+        } else {
+            // The list overflowed: nothing of it is used.  Re-emit the flags slot by slot (one slot's worst case
+            // always fits) without re-adding the decided counts.
+            ++overflow_batches;
+            for (int q = 0; q < q_total; ++q) {
+                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+                GemmParams gp = base_params(e, pl);
+                gp.mode = TCM_FLAG;
+                gp.bcat = pl->bcat.p + static_cast<size_t>(q) * pl->n_cg * slot_bytes;
+                gp.q_total = 1;
+                gp.q_chunks = 1;
+                gp.q_per = 1;
+                // batch-local permutation index of column block q is recovered by offsetting perm instead
+                gp.batch_perms = static_cast<int32_t>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
+                if (pl->mpad >= 64) gp.batch_perms = 1;
+                launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms));
+                ktile_iters += tiles_per_pass;
+                const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
+                fixup_flags(e, perm_q, pl->flag_ij.p, pl->flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
+                unsigned int hq = 0;
+                SB_CUDA(cudaMemcpyAsync(&hq, pl->flag_count.p, sizeof hq, cudaMemcpyDeviceToHost, st));
+                SB_CUDA(cudaStreamSynchronize(st));
+                SB_CHECK(hq <= pl->flag_cap, "internal error: flag list overflow in single-slot recovery");
+                flagged += hq;
+            }
+        }
+    }
+    e->stats[0] = e->n * e->m * num_perm - flagged;
+    e->stats[1] = flagged;
+    e->stats[2] = pl->n_tiles;
+    e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
+    e->stats[4] = pl->D;
+    e->stats[5] = ktile_iters;
+    e->stats[6] = overflow_batches;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+// ================================================================================================ self-test hook
+extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int variant, const int8_t* a_host,
+                                  const int8_t* b_host, int32_t* d_host) {
+    SB_API_BEGIN
+    SB_CHECK(ctx && a_host && b_host && d_host, "sb_selftest_mma_i8: NULL argument");
+    SB_CHECK(ncols == 64 || ncols == 128 || ncols == 192, "sb_selftest_mma_i8: ncols must be 64, 128 or 192");
+    SB_CHECK(ktiles >= 1 && ktiles <= 4096, "sb_selftest_mma_i8: ktiles out of range");
+    ctx->bind();
+    const int D = ncols / 64;
+    const int K = ktiles * TC_KT;
+    const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
+    // host-side tiling into the production layouts
+    std::vector<int8_t> at(static_cast<size_t>(ktiles) * TC_TILE_A), bt(static_cast<size_t>(ktiles) * tile_b);
+    for (int kt = 0; kt < ktiles; ++kt)
+        for (int r = 0; r < TC_ROWS; ++r)
+            for (int k = 0; k < TC_KT; ++k)
+                at[static_cast<size_t>(kt) * TC_TILE_A + (k >> 4) * 2048 + r * 16 + (k & 15)] =
+                    a_host[static_cast<size_t>(r) * K + kt * TC_KT + k];
+    const int nc16 = ncols / 16;
+    for (int kt = 0; kt < ktiles; ++kt)
+        for (int k = 0; k < TC_KT; ++k)
+            for (int c = 0; c < ncols; ++c)
+                bt[static_cast<size_t>(kt) * tile_b + (k >> 3) * (nc16 * 128) + (c >> 4) * 128 + (k & 7) * 16 + (c & 15)] =
+                    b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
+    std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
+    for (int i = 0; i < ktiles; ++i) kts[i] = i;
+    DevBuf<int8_t> d_a, d_b;
+    DevBuf<int32_t> d_ptr, d_kt, d_out;
+    d_a.reserve(at.size());
+    d_b.reserve(bt.size());
+    d_ptr.reserve(2);
+    d_kt.reserve(ktiles);
+    d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
+    cudaStream_t st = ctx->stream;
+    SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_b.p, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), ktiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemsetAsync(d_out.p, 0xff, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t), st));
+    GemmParams gp{};
+    gp.a_tiles = d_a.p;
+    gp.tile_ptr = d_ptr.p;
+    gp.tile_kt = d_kt.p;
+    gp.bcat = d_b.p;
+    gp.n_kt = ktiles;
+    gp.n_rb = 1;
+    gp.n_cg = 1;
+    gp.q_total = 1;
+    gp.q_chunks = 1;
+    gp.q_per = 1;
+    gp.mode = TCM_RAW;
+    gp.n = TC_ROWS;
+    gp.m = 64;
+    gp.mpad = 64;
+    gp.pps = 1;
+    gp.batch_perms = 1;
+    gp.raw_out = d_out.p;
+    gp.a_lbo = 2048;
+    gp.a_sbo = 128;
+    gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
+    gp.b_sbo = 128;
+    if (variant & 1) std::swap(gp.a_lbo, gp.a_sbo);
+    if (variant & 2) std::swap(gp.b_lbo, gp.b_sbo);
+    launch_gemm_d(ctx, D, gp, 1);
+    SB_CUDA(cudaMemcpyAsync(d_host, d_out.p, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t),
+                            cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}

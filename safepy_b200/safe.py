@@ -1,0 +1,403 @@
+"""SAFE class surface for the neighborhood + enrichment path, backed by libsafe_b200 (sm_100a CUDA).
+
+Mirrors the reference's method names, keyword arguments, sticky-override behaviour, validation errors, log lines
+and output attributes for
+    SAFE.define_neighborhoods                 safepy/safe.py:369-430
+    SAFE.compute_pvalues                      safepy/safe.py:432-472
+    SAFE.compute_pvalues_by_randomization     safepy/safe.py:474-554
+    SAFE.compute_pvalues_by_hypergeom         safepy/safe.py:556-608
+Everything else of the reference class (file loaders, layouts, plotting, domains) is outside this package: use
+`accelerate(safepy.safe.SAFE)` to graft these four methods onto the reference class, or the standalone `SAFE`
+below, which takes graphs / arrays / DataFrames directly.
+
+There is no CPU fallback: the methods raise `SafeB200Error` when the CUDA library or a B200 is missing.
+"""
+import logging
+
+import numpy as np
+
+from . import _lib
+from .neighborhood_matrix import PackedNeighborhoods, as_packed
+from .permutations import make_perm_rows
+
+DEFAULTS = {
+    # safepy/safe_default.ini:1-24 and safepy/safe.py:57-107
+    "background": "attribute_file",
+    "node_distance_metric": "shortpath_weighted_layout",
+    "neighborhood_radius_type": "diameter",
+    "neighborhood_radius": 0.1,
+    "attribute_sign": "both",
+    "num_permutations": 1000,
+    "multiple_testing": False,
+    "neighborhood_score_type": "sum",
+    "enrichment_type": "auto",
+    "enrichment_threshold": 0.05,
+    "enrichment_max_log10": 16,
+    "attribute_enrichment_min_size": 10,
+    "attribute_unimodality_metric": "connectivity",
+    "attribute_distance_metric": "jaccard",
+    "attribute_distance_threshold": 0.75,
+    "random_seed": None,
+}
+
+_CONTEXTS = {}
+
+
+def get_context(device=-1):
+    """Process-wide libsafe_b200 context per device (created on first use)."""
+    ctx = _CONTEXTS.get(device)
+    if ctx is None or ctx.h is None:
+        ctx = _lib.Context(device)
+        _CONTEXTS[device] = ctx
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------------ graph -> arrays
+def _node_coordinates(graph):
+    nodes = list(graph)
+    n = len(nodes)
+    if nodes != list(range(n)):
+        # the reference indexes the matrix with node ids (safe.py:412-415); every loader yields 0..N-1
+        raise ValueError("graph nodes must be the integers 0..N-1 in order (as produced by the SAFE loaders)")
+    x = np.fromiter((d for _, d in graph.nodes.data("x")), dtype=np.float64, count=n)
+    y = np.fromiter((d for _, d in graph.nodes.data("y")), dtype=np.float64, count=n)
+    return x, y
+
+
+def graph_csr(graph, weight):
+    """Symmetric CSR of the graph with the cost rule of networkx's Dijkstra: data.get(weight, 1)
+    (what safe.py:406-410 hands to all_pairs_dijkstra_path_length).  Cached on the graph object."""
+    key = (weight, graph.number_of_nodes(), graph.number_of_edges())
+    cache = graph.graph.get("_safe_b200_csr")
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    n = graph.number_of_nodes()
+    ne = graph.number_of_edges()
+    eu = np.empty(ne, dtype=np.int64)
+    ev = np.empty(ne, dtype=np.int64)
+    w = np.empty(ne, dtype=np.float64)
+    for k, (u, v, c) in enumerate(graph.edges(data=weight, default=1)):
+        eu[k], ev[k], w[k] = u, v, c
+    loop = eu == ev
+    src = np.concatenate([eu, ev[~loop]])
+    dst = np.concatenate([ev, eu[~loop]])
+    ww = np.concatenate([w, w[~loop]])
+    order = np.lexsort((dst, src))
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.add.at(indptr, src + 1, 1)
+    csr = (np.cumsum(indptr), dst[order].astype(np.int32), np.ascontiguousarray(ww[order]))
+    graph.graph["_safe_b200_csr"] = (key, csr)
+    return csr
+
+
+class SafeB200Mixin:
+    """The four hot-path methods; the host class supplies graph / node2attribute / attributes / settings."""
+
+    device = -1
+
+    # ---------------------------------------------------------------------------------- stage 1
+    def define_neighborhoods(self, **kwargs):
+        # sticky keyword overrides, safe.py:374-381
+        for k in ("node_distance_metric", "neighborhood_radius_type", "neighborhood_radius"):
+            if k in kwargs:
+                setattr(self, k, kwargs[k])
+        self.validate_config()
+
+        ctx = get_context(self.device)
+        x, y = _node_coordinates(self.graph)
+        n = x.shape[0]
+        dev = _lib.Neighborhoods(ctx, n)
+        metric = self.node_distance_metric
+        if metric == "euclidean":
+            nr = self.neighborhood_radius * (np.max(x) - np.min(x))          # safe.py:390-391 (x extent only)
+            dev.euclid(x, y, nr)
+        else:
+            if metric == "shortpath_weighted_layout":
+                nr = self.neighborhood_radius * (np.max(x) - np.min(x))      # safe.py:404-405
+                indptr, indices, cost = graph_csr(self.graph, "length")
+            else:
+                nr = self.neighborhood_radius                                # safe.py:409
+                indptr, indices, cost = graph_csr(self.graph, "weight")
+            dev.shortpath(indptr, indices, cost, nr)
+            # safe.py:417 stores the dict-of-dicts of distances; nothing in safepy reads it
+            self.node_distances = None
+
+        packed = PackedNeighborhoods(dev.packed(), n, device=dev)
+        num_neighbors = packed.row_sums()
+        if self.verbose:
+            logging.info("Node distance metric: %s" % self.node_distance_metric)
+            logging.info("Neighborhood definition: %.2f x %s" % (self.neighborhood_radius,
+                                                                 self.neighborhood_radius_type))
+            logging.info("Number of nodes per neighborhood (mean +/- std): %.2f +/- %.2f"
+                         % (np.mean(num_neighbors), np.std(num_neighbors)))
+        self.neighborhoods = packed
+
+    # ---------------------------------------------------------------------------------- stage 2
+    def compute_pvalues(self, **kwargs):
+        if "how" in kwargs:
+            self.enrichment_type = kwargs["how"]
+        for k in ("neighborhood_score_type", "multiple_testing", "background"):
+            if k in kwargs:
+                setattr(self, k, kwargs[k])
+        self.validate_config()
+
+        if self.background == "network":
+            logging.info("Setting all null attribute values to 0. Using the network as background for enrichment.")
+            self.node2attribute[np.isnan(self.node2attribute)] = 0
+
+        nan_mask = np.isnan(self.node2attribute)
+        if np.any(np.sum(nan_mask, axis=0) / self.node2attribute.shape[0] > 0.5):
+            logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored for "
+                            "calculating enrichment.\n'Consider setting sf.background = ''network''.'")
+        num_other_values = np.sum(~nan_mask & ~np.isin(self.node2attribute, [0, 1]))
+
+        if self.enrichment_type == "hypergeometric" or (self.enrichment_type == "auto" and num_other_values == 0):
+            self.compute_pvalues_by_hypergeom(**kwargs)
+        else:
+            self.compute_pvalues_by_randomization(**kwargs)
+
+        idx = ~np.isnan(self.nes)
+        self.nes_binary = np.zeros(self.nes.shape)
+        self.nes_binary[idx] = np.abs(self.nes[idx]) > -np.log10(self.enrichment_threshold)
+        self.attributes["num_neighborhoods_enriched"] = np.sum(self.nes_binary, axis=0)
+
+    def _enrichment_plan(self):
+        ctx = get_context(self.device)
+        packed = as_packed(self.neighborhoods)
+        b = np.asarray(self.node2attribute)
+        if b.shape[0] != packed.n:
+            raise ValueError("node2attribute has %d rows but the network has %d nodes" % (b.shape[0], packed.n))
+        return _lib.Enrichment(packed.on_device(ctx), b)
+
+    def compute_pvalues_by_randomization(self, **kwargs):
+        if kwargs:
+            logging.warning("Current settings (possibly overwriting global ones):")
+            for k in kwargs:
+                logging.warning("\t%s=%s" % (k, str(kwargs[k])))
+        logging.info("Using randomization to calculate enrichment...")
+        # (the reference sleeps 1 s here to keep its progress bar tidy, safe.py:484; not reproduced)
+
+        if "num_permutations" in kwargs:
+            self.num_permutations = kwargs["num_permutations"]
+        num_processes = kwargs.get("processes", 1)
+        self.validate_config()
+        if num_processes > 1:
+            # safe.py:503-504 rounds the permutation count up to a multiple of the worker count
+            per = int(np.ceil(self.num_permutations / num_processes))
+            self.num_permutations = per * num_processes
+
+        plan = self._enrichment_plan()
+        try:
+            self.ns = plan.score(self.neighborhood_score_type)
+            rows = make_perm_rows(self.node2attribute, self.num_permutations, self.random_seed)
+            cneg, cpos = plan.perm_counts(rows, self.neighborhood_score_type, getattr(self, "engine", "auto"))
+            self.last_enrichment_stats = plan.stats()
+        finally:
+            plan.close()
+
+        counts_neg = cneg.astype(np.float64)
+        counts_pos = cpos.astype(np.float64)
+        idx = np.isnan(self.ns)                                              # safe.py:528-530
+        counts_neg[idx] = np.nan
+        counts_pos[idx] = np.nan
+        self.pvalues_neg = counts_neg / self.num_permutations
+        self.pvalues_pos = counts_pos / self.num_permutations
+
+        if self.multiple_testing:
+            logging.info("Running FDR-adjustment of p-values...")
+            self.pvalues_neg = _fdr_rows(self.pvalues_neg)
+            self.pvalues_pos = _fdr_rows(self.pvalues_pos)
+
+        floor = 1 / self.num_permutations                                    # safe.py:546-547
+        nes_pos = -np.log10(np.where(self.pvalues_pos == 0, floor, self.pvalues_pos))
+        nes_neg = -np.log10(np.where(self.pvalues_neg == 0, floor, self.pvalues_neg))
+        if self.attribute_sign == "highest":
+            self.nes = nes_pos
+        elif self.attribute_sign == "lowest":
+            self.nes = nes_neg
+        elif self.attribute_sign == "both":
+            self.nes = nes_pos - nes_neg
+
+    def compute_pvalues_by_hypergeom(self, **kwargs):
+        if kwargs:
+            if "verbose" in kwargs:
+                self.verbose = kwargs["verbose"]
+            if self.verbose:
+                logging.warning("Overwriting global settings:")
+                for k in kwargs:
+                    logging.warning("\t%s=%s" % (k, str(kwargs[k])))
+        self.validate_config()
+        if self.verbose:
+            logging.info("Using the hypergeometric test to calculate enrichment...")
+        plan = self._enrichment_plan()
+        try:
+            self.pvalues_pos, nes = plan.hypergeom(want_pvalues=True, want_nes=not self.multiple_testing)
+        finally:
+            plan.close()
+        if self.multiple_testing:
+            if self.verbose:
+                logging.info("Running FDR-adjustment of p-values...")
+            self.pvalues_pos = _fdr_rows(self.pvalues_pos)
+            with np.errstate(divide="ignore"):
+                nes = -np.log10(self.pvalues_pos)
+        self.nes = nes
+
+
+def _fdr_rows(pvalues):
+    """Benjamini-Hochberg adjustment of every row across attributes (what safe.py:536-542 / 599-605 obtain from
+    statsmodels.stats.multitest.fdrcorrection(method='indep')[1] per row)."""
+    p = np.asarray(pvalues, dtype=np.float64)
+    m = p.shape[1]
+    order = np.argsort(p, axis=1)
+    ranked = np.take_along_axis(p, order, axis=1) * (m / np.arange(1, m + 1))[None, :]
+    ranked = np.minimum.accumulate(ranked[:, ::-1], axis=1)[:, ::-1]
+    ranked = np.minimum(ranked, 1.0)
+    out = np.empty_like(p)
+    np.put_along_axis(out, order, ranked, axis=1)
+    return out
+
+
+class SAFE(SafeB200Mixin):
+    """Standalone host class: same settings, validation and method names as safepy.safe.SAFE (safe.py:37-235) for
+    the neighborhood/enrichment path, fed from in-memory objects instead of the reference's file loaders."""
+
+    def __init__(self, path_to_ini_file="", path_to_safe_data=None, verbose=True, device=-1):
+        self.verbose = verbose
+        self.device = device
+        self.path_to_safe_data = path_to_safe_data
+        self.graph = None
+        self.graph_euclidean = None
+        self.node_key_attribute = "label_orf"
+        self.attributes = None
+        self.nodes = None
+        self.node2attribute = None
+        for k, v in DEFAULTS.items():
+            setattr(self, k, v)
+        self.neighborhoods = None
+        self.node_distances = None
+        self.ns = None
+        self.pvalues_neg = None
+        self.pvalues_pos = None
+        self.nes = None
+        self.nes_threshold = None
+        self.nes_binary = None
+        self.domains = None
+        self.node2domain = None
+        if path_to_ini_file:
+            self.read_config(path_to_ini_file)
+        self.validate_config()
+
+    def read_config(self, path_to_ini_file):
+        """The 'Input files' / 'Analysis parameters' keys safe.py:147-184 reads (others are ignored upstream too)."""
+        import configparser
+        cfg = configparser.ConfigParser(allow_no_value=True, comment_prefixes=("#", ";", "{"),
+                                        inline_comment_prefixes="#")
+        cfg.read(path_to_ini_file)
+
+        def get(section, key, cast=str):
+            for sec in (section, "DEFAULT"):
+                if cfg.has_option(sec, key) and cfg.get(sec, key) not in (None, ""):
+                    return cast(cfg.get(sec, key).strip())
+            return None
+
+        for attr, section, key, cast in (
+                ("attribute_sign", "Input files", "annotationsign", str),
+                ("background", "Analysis parameters", "background", str),
+                ("node_distance_metric", "Analysis parameters", "nodeDistanceType", str),
+                ("neighborhood_radius_type", "Analysis parameters", "neighborhoodRadiusType", str),
+                ("neighborhood_radius", "Analysis parameters", "neighborhoodRadius", float),
+                ("attribute_unimodality_metric", "Analysis parameters", "unimodalityType", str),
+                ("attribute_distance_metric", "Analysis parameters", "groupDistanceType", str),
+                ("attribute_distance_threshold", "Analysis parameters", "groupDistanceThreshold", float)):
+            val = get(section, key, cast)
+            if val is not None:
+                setattr(self, attr, val)
+        try:
+            self.random_seed = int(get("Analysis parameters", "randomSeed"))
+        except (ValueError, TypeError):
+            self.random_seed = None
+
+    def validate_config(self):
+        """Same checks, messages and restore-the-default behaviour as safe.py:190-235."""
+        def option(attr, valid, label=None):
+            val = getattr(self, attr)
+            if val not in valid:
+                setattr(self, attr, DEFAULTS[attr])
+                raise ValueError("%s is not a valid setting for %s. Valid options are: %s"
+                                 % (val, label or attr, ", ".join(valid)))
+
+        option("background", ["attribute_file", "network"])
+        option("node_distance_metric", ["euclidean", "shortpath", "shortpath_weighted_layout"])
+        option("attribute_sign", ["highest", "lowest", "both"])
+        if not isinstance(self.num_permutations, (int, np.integer)) or self.num_permutations < 10:
+            self.num_permutations = DEFAULTS["num_permutations"]
+            raise ValueError("num_permutations must be an integer equal or greater than 10.")
+        if not isinstance(self.enrichment_threshold, float) or not (0 < self.enrichment_threshold < 1):
+            self.enrichment_threshold = DEFAULTS["enrichment_threshold"]
+            raise ValueError("enrichment_threshold must be in the (0,1) range.")
+        if not isinstance(self.enrichment_max_log10, (int, float)):
+            self.enrichment_max_log10 = DEFAULTS["enrichment_max_log10"]
+            raise ValueError("enrichment_max_log10 must be a number.")
+        if not isinstance(self.attribute_enrichment_min_size, int) or self.attribute_enrichment_min_size < 2:
+            self.attribute_enrichment_min_size = DEFAULTS["attribute_enrichment_min_size"]
+            raise ValueError("attribute_enrichment_min_size must be an integer equal or greater than 2.")
+        if not isinstance(self.attribute_distance_threshold, float) or not (0 < self.attribute_distance_threshold < 1):
+            self.attribute_distance_threshold = DEFAULTS["attribute_distance_threshold"]
+            raise ValueError("attribute_distance_threshold must be a float number in the (0,1) range.")
+
+    # -- in-memory loaders (the reference's file formats are out of scope here)
+    def load_network(self, graph=None, edges=None, x=None, y=None, length=None, **kwargs):
+        """Either an nx.Graph in the reference's conventions (nodes 0..N-1 with 'x', 'y'; edges with 'length'), or
+        arrays: edges [E, 2], coordinates x, y and optional edge lengths (default: Euclidean layout distance, the
+        value safe_io.calculate_edge_lengths assigns for unit adjacency weights, safe_io.py:311-333)."""
+        import networkx as nx
+        if "node_key_attribute" in kwargs:
+            self.node_key_attribute = kwargs["node_key_attribute"]
+        self.validate_config()
+        if graph is None:
+            x = np.asarray(x, dtype=np.float64)
+            y = np.asarray(y, dtype=np.float64)
+            edges = np.zeros((0, 2), dtype=np.int64) if edges is None else np.asarray(edges, dtype=np.int64)
+            if length is None and len(edges):
+                dx, dy = x[edges[:, 0]] - x[edges[:, 1]], y[edges[:, 0]] - y[edges[:, 1]]
+                length = np.sqrt(dx * dx + dy * dy)
+            graph = nx.Graph()
+            graph.add_nodes_from((i, {"key": i, "x": float(x[i]), "y": float(y[i]), "label": str(i),
+                                      self.node_key_attribute: str(i)}) for i in range(x.shape[0]))
+            if len(edges):
+                graph.add_edges_from((int(u), int(v), {"length": float(w)}) for (u, v), w in zip(edges, length))
+        self.graph = graph
+
+    def load_attributes(self, attribute_file=None, **kwargs):
+        """DataFrame (index = node labels, as read_attributes accepts, safe_io.py:375-379) or a plain [N, M] array
+        already aligned to node order."""
+        import pandas as pd
+        self.validate_config()
+        if isinstance(attribute_file, pd.DataFrame):
+            frame = attribute_file.apply(pd.to_numeric, errors="coerce")
+            names = [str(c) for c in frame.columns]
+            import networkx as nx
+            labels = list(nx.get_node_attributes(self.graph, self.node_key_attribute).values())
+            if not frame.index.is_unique:
+                frame = frame.groupby(frame.index).mean()
+            if labels:
+                frame = frame.reindex(index=labels, fill_value=np.nan)
+            values = frame.values
+        else:
+            values = np.asarray(attribute_file)
+            if values.ndim == 1:
+                values = values[:, None]
+            names = [str(j) for j in range(values.shape[1])]
+        self.attributes = pd.DataFrame({"id": np.arange(len(names)), "name": names})
+        self.node2attribute = values
+
+
+def accelerate(reference_class):
+    """Subclass of the reference's SAFE whose neighborhood/enrichment methods run on the B200:
+
+        from safepy import safe
+        from safepy_b200 import accelerate
+        SAFE = accelerate(safe.SAFE)
+        sf = SAFE(); sf.load_network(); sf.define_neighborhoods(); sf.load_attributes(); sf.compute_pvalues()
+    """
+    return type("SAFE", (SafeB200Mixin, reference_class), {"__doc__": reference_class.__doc__})

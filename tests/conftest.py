@@ -1,0 +1,52 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` on the GPU box)")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def stage1_small():
+    return load_golden("stage1_small.npz")
+
+
+@pytest.fixture(scope="session")
+def stage1_mid():
+    return load_golden("stage1_mid.npz")
+
+
+@pytest.fixture(scope="session")
+def stage2_small():
+    return load_golden("stage2_small.npz")
+
+
+@pytest.fixture(scope="session")
+def ctx():
+    """libsafe_b200 context on cuda:0 -- fails loudly (no skip) if the CUDA path is unavailable."""
+    from safepy_b200 import get_context
+    return get_context()
+
+
+def net_from_golden(g):
+    """Rebuild the synthetic-network dict (incl. symmetric CSR) from a golden file's inputs."""
+    from safepy_b200 import synthetic as syn
+    n = g["x"].shape[0]
+    indptr, indices, csr_len = syn.edges_to_csr(n, g["edges"][:, 0], g["edges"][:, 1], g["length"])
+    return dict(n=n, x=g["x"], y=g["y"], edges=g["edges"], length=g["length"], indptr=indptr, indices=indices,
+                csr_length=csr_len)

@@ -37,8 +37,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 0x3ffu) == 0 && clock64() - t0 > 20000000000ll) __trap();  // ~10 s at 2 GHz
     }
 }
 

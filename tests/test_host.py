@@ -1,0 +1,141 @@
+"""CPU: host-side logic of the drop-in layer (settings, permutation stream, packed matrix view, CSR extraction)."""
+import pickle
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import safe_oracle as orc
+from conftest import net_from_golden
+from safepy_b200 import SAFE, PackedNeighborhoods, synthetic as syn
+from safepy_b200._lib import pack_dense, unpack_packed
+from safepy_b200.neighborhood_matrix import as_packed
+from safepy_b200.permutations import make_perm_rows, shard_bounds
+from safepy_b200.safe import _fdr_rows, graph_csr
+
+
+def test_defaults_match_reference_ini():
+    sf = SAFE(verbose=False)
+    assert sf.node_distance_metric == "shortpath_weighted_layout"
+    assert sf.neighborhood_radius == 0.1 and sf.neighborhood_radius_type == "diameter"
+    assert sf.background == "attribute_file" and sf.attribute_sign == "both"
+    assert sf.num_permutations == 1000 and sf.neighborhood_score_type == "sum"
+    assert sf.enrichment_type == "auto" and sf.enrichment_threshold == 0.05 and sf.random_seed is None
+
+
+@pytest.mark.parametrize("attr,bad,default", [
+    ("node_distance_metric", "manhattan", "shortpath_weighted_layout"),
+    ("background", "genome", "attribute_file"),
+    ("attribute_sign", "up", "both"),
+    ("num_permutations", 5, 1000),
+    ("enrichment_threshold", 2.0, 0.05),
+])
+def test_validate_config_raises_and_restores_default(attr, bad, default):
+    """safepy/safe.py:190-235: ValueError and the setting snaps back to its default."""
+    sf = SAFE(verbose=False)
+    setattr(sf, attr, bad)
+    with pytest.raises(ValueError):
+        sf.validate_config()
+    assert getattr(sf, attr) == default
+
+
+def test_kwargs_are_sticky_and_validated_before_any_gpu_work():
+    sf = SAFE(verbose=False)
+    with pytest.raises(ValueError):
+        sf.define_neighborhoods(node_distance_metric="bogus")
+    assert sf.node_distance_metric == "shortpath_weighted_layout"
+    with pytest.raises(ValueError):
+        sf.compute_pvalues(background="bogus")
+
+
+@pytest.mark.parametrize("kind", ["normal32", "single", "binary"])
+def test_perm_rows_replay_the_reference_stream(stage2_small, kind):
+    """Gather rows composed from the legacy RNG reproduce the reference's in-place cumulative shuffles: applying
+    them to the original matrix and scoring on the CPU gives the reference's counts."""
+    g = stage2_small
+    attrs = g["attr_" + kind]
+    P, seed = int(g["num_permutations"]), int(g["seed"])
+    rows = make_perm_rows(attrs, P, seed)
+    assert rows.dtype == np.int32 and rows.shape == (P, attrs.shape[0])
+    assert np.array_equal(rows, orc.perm_gather_rows(attrs, P, seed))
+    # each row is a permutation and leaves all-NaN rows in place
+    nodata = np.all(np.isnan(attrs), axis=1)
+    for p in (0, P - 1):
+        assert np.array_equal(np.sort(rows[p]), np.arange(attrs.shape[0]))
+        assert np.array_equal(rows[p][nodata], np.nonzero(nodata)[0])
+    nb = unpack_packed(g["neighborhoods"], attrs.shape[0]).astype(np.int64)
+    cneg, cpos = orc.perm_counts_from_rows(nb, attrs, "sum", rows)
+    assert np.array_equal(cneg, g["cneg_%s_sum" % kind]) and np.array_equal(cpos, g["cpos_%s_sum" % kind])
+
+
+def test_shard_bounds_cover_all_permutations():
+    for P in (10, 1000, 1001):
+        for ws in (1, 2, 3, 8):
+            spans = [shard_bounds(P, ws, r) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == P
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_packed_neighborhoods_behaves_like_the_dense_matrix(stage1_small):
+    g = stage1_small
+    n = g["x"].shape[0]
+    dense = unpack_packed(g["nb_layout"], n).astype(np.int64)
+    pk = PackedNeighborhoods(g["nb_layout"], n)
+    assert pk.shape == (n, n)
+    assert np.array_equal(np.sum(pk, axis=1), dense.sum(axis=1))      # reference tests' usage
+    assert np.array_equal(np.asarray(pk), dense)
+    v = np.arange(n, dtype=np.float64)
+    assert np.array_equal(np.dot(pk, v), np.dot(dense, v))
+    assert pk[3, 3] == 1 and np.array_equal(pk[5], dense[5])
+    clone = pickle.loads(pickle.dumps(pk))
+    assert np.array_equal(clone.words, pk.words) and clone._device is None
+    assert np.array_equal(as_packed(dense).words, pk.words)
+    with pytest.raises(ValueError):
+        as_packed(dense * 2)
+
+
+def test_graph_csr_follows_networkx_weight_rule(stage1_small):
+    net = net_from_golden(stage1_small)
+    g = syn.to_networkx(net)
+    ip, ix, w = graph_csr(g, "length")
+    assert np.array_equal(ip, net["indptr"]) and np.array_equal(ix, net["indices"])
+    assert np.array_equal(w, net["csr_length"])
+    ip2, ix2, w2 = graph_csr(g, "weight")          # attribute absent -> every edge costs 1
+    assert np.array_equal(ix2, ix) and np.all(w2 == 1.0)
+    ipo, ixo, wo = orc.graph_to_csr(g, "length")
+    assert np.array_equal(ipo, ip) and np.array_equal(ixo, ix) and np.array_equal(wo, w)
+
+
+def test_fdr_rows_is_benjamini_hochberg():
+    rng = np.random.default_rng(3)
+    p = rng.uniform(size=(7, 40))
+    adj = _fdr_rows(p)
+    for r in range(p.shape[0]):
+        order = np.argsort(p[r])
+        expect = np.empty(40)
+        run = 1.0
+        for rank in range(40, 0, -1):
+            run = min(run, p[r][order[rank - 1]] * 40 / rank)
+            expect[order[rank - 1]] = run
+        assert np.allclose(adj[r], expect, rtol=0, atol=1e-15)
+
+
+def test_loaders_accept_arrays_and_frames(stage1_small):
+    net = net_from_golden(stage1_small)
+    sf = SAFE(verbose=False)
+    sf.load_network(edges=net["edges"], x=net["x"], y=net["y"])
+    assert sf.graph.number_of_nodes() == net["n"] and sf.graph.number_of_edges() == len(net["edges"])
+    _, _, w = graph_csr(sf.graph, "length")
+    assert np.array_equal(w, net["csr_length"])
+    frame = pd.DataFrame(np.arange(2 * net["n"], dtype=float).reshape(net["n"], 2), index=[str(i) for i in range(net["n"])],
+                         columns=["a", "b"])
+    sf.load_attributes(attribute_file=frame)
+    assert sf.node2attribute.shape == (net["n"], 2) and list(sf.attributes["name"]) == ["a", "b"]
+
+
+def test_synthetic_configs_are_deterministic():
+    a = syn.make_config("C1", scale=0.1)
+    b = syn.make_config("C1", scale=0.1)
+    assert np.array_equal(a["net"]["edges"], b["net"]["edges"]) and np.array_equal(a["net"]["x"], b["net"]["x"])
+    assert np.array_equal(a["attributes"], b["attributes"], equal_nan=True)
+    assert a["attributes"].dtype == np.float32

@@ -1,0 +1,410 @@
+#!/usr/bin/env python
+"""Benchmark of the SAFE randomization null (BASELINE.json metric: enrichment node-attr-perm scores/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C3] [--scale S]
+
+Workload (default C3, BASELINE.json configs[2] -- the configuration the scores/s metric and the 1/2/4/8-GPU sharding are
+quoted on; configs[1] is the hypergeometric case and has no permutations): synthetic 20k-node / 150k-edge network,
+2000 float32 attributes, shortpath_weighted_layout r=0.10, 1000 permutations.
+One step = the whole permutation null: all P permutations scored against all N x M (node, attribute) cells
+(N*M*P scores), permutations sharded over the ranks and combined by ONE all-reduce of the count arrays (strong
+scaling).  `value` times it with neighborhoods, attributes and permutation indices resident in HBM; `e2e` times the
+host-buffer C-ABI call (H2D of packed neighborhoods + attributes + indices, D2H of the counts, inside the region).
+
+--impl reference times the reference's CPU algorithm for the same path (oracle/safe_oracle.py restating
+safepy/safe_extras.py:36-70: dense int64 neighborhoods, np.dot per permutation, all BLAS threads), one permutation
+per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (smoke runs only)")
+    ap.add_argument("--perms", type=int, default=None)
+    ap.add_argument("--cpu-sample-perms", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="auto")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ workload
+def build_workload(args):
+    from safepy_b200 import synthetic as syn
+    cfg = syn.make_config(args.workload, args.scale)
+    if args.perms:
+        cfg["perms"] = args.perms
+    if cfg["perms"] <= 0:
+        raise SystemExit("workload %s has no permutation null; pick C1/C3/C4/C5" % args.workload)
+    net = cfg["net"]
+    cfg["nr"] = cfg["radius"] * (np.max(net["x"]) - np.min(net["x"]))
+    return cfg
+
+
+def workload_name(cfg, args):
+    return "%s%s: N=%d E=%d M=%d P=%d %s r=%.2f float32 N(0,1) attributes" % (
+        args.workload, "" if args.scale == 1.0 else "(scale %.3g)" % args.scale, cfg["n"], len(cfg["net"]["edges"]),
+        cfg["m"], cfg["perms"], cfg["metric"], cfg["radius"])
+
+
+def cpu_reference_setup(cfg):
+    """Dense int64 neighborhoods exactly as the reference holds them (safe.py:387), via the oracle."""
+    import safe_oracle as orc
+    net = cfg["net"]
+    if cfg["metric"] == "euclidean":
+        nb = orc.neighborhoods_euclidean(net["x"], net["y"], cfg["nr"])
+    else:
+        nb = orc.neighborhoods_shortpath_csr(net["indptr"], net["indices"], net["csr_length"], cfg["nr"])
+    return nb.astype(np.int64)
+
+
+def cpu_reference_steps(cfg, nb, steps, warmup):
+    """The reference's permutation loop body (safe_extras.py:56-66), one permutation per step."""
+    import safe_oracle as orc
+    attrs = cfg["attributes"]
+    np.random.seed(7)
+    s0 = orc.compute_neighborhood_score(nb, attrs, "sum")
+    n2a = np.copy(attrs)
+    indx_vals = np.nonzero(np.sum(~np.isnan(n2a), axis=1))[0]
+    counts_neg = np.zeros(s0.shape)
+    counts_pos = np.zeros(s0.shape)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        n2a[indx_vals, :] = n2a[np.random.permutation(indx_vals), :]
+        sp = orc.compute_neighborhood_score(nb, n2a, "sum")
+        counts_neg = np.add(counts_neg, sp <= s0)
+        counts_pos = np.add(counts_pos, sp >= s0)
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    cfg = build_workload(args)
+    nb = cpu_reference_setup(cfg)
+    times = cpu_reference_steps(cfg, nb, args.steps, args.warmup)
+    t = float(np.sum(times))
+    scores = float(cfg["n"]) * cfg["m"] * args.steps
+    value = scores / t
+    cores = os.cpu_count()
+    out = {
+        "impl": "reference", "metric": "enrichment node-attr-perm scores/s", "value": value, "unit": "scores/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args), "step": "one permutation of the reference loop "
+                   "(row shuffle + np.dot of the dense int64 neighborhood matrix + 2 compares)"},
+        "cpu_baseline": {"value": value, "unit": "scores/s", "cores": cores, "kind": "port",
+                         "sample": "%d permutations of %d (NumPy/OpenBLAS, all threads)" % (args.steps, cfg["perms"])},
+        "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from safepy_b200 import _lib
+    from safepy_b200.permutations import make_perm_rows, shard_bounds
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    cfg = build_workload(args)
+    n, m, P = cfg["n"], cfg["m"], cfg["perms"]
+    net, attrs = cfg["net"], cfg["attributes"]
+
+    ctx = _lib.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
+
+    # ---- stage 1 (timed separately; reported as define_neighborhoods seconds)
+    def stage1():
+        nbh = _lib.Neighborhoods(ctx, n)
+        if cfg["metric"] == "euclidean":
+            nbh.euclid(net["x"], net["y"], cfg["nr"])
+        else:
+            nbh.shortpath(net["indptr"], net["indices"], net["csr_length"], cfg["nr"])
+        return nbh
+
+    stage1().close()
+    ctx.profile(True)
+    t0 = time.perf_counter()
+    nb = stage1()
+    ctx.synchronize()
+    t_stage1 = time.perf_counter() - t0
+    k1_ms, _ = ctx.kernel_ms("euclid" if cfg["metric"] == "euclidean" else "sssp")
+    ctx.profile(False)
+    rowsums = nb.rowsums()
+
+    # ---- permutation indices: replay of the reference's legacy RNG stream (host, sequential by nature)
+    t0 = time.perf_counter()
+    rows_all = make_perm_rows(attrs, P, 7)
+    t_rng = time.perf_counter() - t0
+    lo, hi = shard_bounds(P, world, rank)
+    rows_host = torch.from_numpy(rows_all[lo:hi]).pin_memory()
+    attrs_host = torch.from_numpy(attrs).pin_memory()
+    packed_host = torch.from_numpy(nb.packed().view(np.int32)).pin_memory()
+
+    rows_dev = rows_host.to(dev)
+    attrs_dev = attrs_host.to(dev)
+    counts = torch.zeros((2, n, m), dtype=torch.int32, device=dev)
+    counts_host = torch.empty((2, n, m), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_resident():
+        counts.zero_()
+        plan = _lib.Enrichment(nb, b_dev=attrs_dev.data_ptr(), dtype=np.float32, shape=(n, m))
+        plan.perm_counts_dev(rows_dev.data_ptr(), hi - lo, counts[0].data_ptr(), counts[1].data_ptr(), "sum",
+                             args.engine)
+        if world > 1:
+            dist.all_reduce(counts)
+        st = plan.stats()
+        plan.close()
+        return st
+
+    def step_e2e():
+        if world == 1:
+            # the host-buffer C-ABI entry points: sb_neigh_upload_packed + sb_enrich_create + sb_enrich_perm_counts
+            nbh = _lib.Neighborhoods(ctx, n).upload_packed(packed_host.numpy().view(np.uint32))
+            plan = _lib.Enrichment(nbh, attrs_host.numpy())
+            out = counts_host.numpy().view(np.uint32)
+            plan.perm_counts(rows_host.numpy(), "sum", args.engine, out=(out[0], out[1]))
+            plan.close()
+            nbh.close()
+        else:
+            pk = packed_host.to(dev, non_blocking=True)
+            b = attrs_host.to(dev, non_blocking=True)
+            r = rows_host.to(dev, non_blocking=True)
+            counts.zero_()
+            nbh = _lib.Neighborhoods(ctx, n, words_dev=pk.data_ptr())
+            plan = _lib.Enrichment(nbh, b_dev=b.data_ptr(), dtype=np.float32, shape=(n, m))
+            plan.perm_counts_dev(r.data_ptr(), hi - lo, counts[0].data_ptr(), counts[1].data_ptr(), "sum", args.engine)
+            dist.all_reduce(counts)
+            counts_host.copy_(counts, non_blocking=True)
+            torch.cuda.synchronize()
+            plan.close()
+            nbh.close()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, wall * 1e3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, wall = float(t[0]), float(t[1]) / 1e3
+        return ms, wall, last
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count
+    ctx.profile(True)
+    for k in _lib.KERNEL_CLASSES:
+        ctx.kernel_ms(k)
+    # warm-up outside the profiled window, then the timed steps with per-kernel event brackets on
+    ctx.profile(False)
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.profile(True)
+    launches0 = ctx.launch_count
+    ms_total, wall_total, stats = timed(step_resident, args.steps, 0)
+    launches = ctx.launch_count - launches0
+    kern = {k: ctx.kernel_ms(k) for k in ("gemm", "gather", "fixup", "prep", "score")}
+    ctx.profile(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    e2e_ms, e2e_wall, _ = timed(step_e2e, max(1, min(args.steps, 3)), 1)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    # correctness spot check inside the bench run: resident and e2e paths agree
+    step_resident()
+    torch.cuda.synchronize()
+    agree = bool(torch.equal(counts.cpu(), counts_host)) if world == 1 or rank == 0 else True
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1408.3)
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained"
+        scores_per_step = float(n) * m * P
+        sec_per_step = ms_total / 1e3 / args.steps
+        value = scores_per_step / sec_per_step
+        gemm_ms, gemm_launches = kern["gemm"]
+        # algorithmic FLOPs of the score GEMM: 2 * (cells of non-empty A tiles) * M per permutation,
+        # digit passes and padding are implementation factors and are NOT counted
+        tiles = stats["a_tiles"]
+        flops_total = 2.0 * tiles * 128 * 64 * m * (hi - lo) * args.steps
+        achieved_tf = flops_total / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
+        int8_ops = 2.0 * stats["ktile_iters"] * 128 * 64 * 64 * stats["digits"] * args.steps
+        out = {
+            "metric": "enrichment node-attr-perm scores/s", "value": value, "unit": "scores/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int8 digits -> int32/int64",
+            "data": "synthetic",
+            "config": {
+                "workload": workload_name(cfg, args),
+                "step": "whole permutation null (operand prep + gather + tcgen05 digit GEMM with fused compare + "
+                        "fp64 fix-up%s)" % (" + NCCL all-reduce of counts" if world > 1 else ""),
+                "parallelism": "permutations sharded %d-way" % world,
+                "l2": "working set per batch (gathered operand %.0f MB/permutation) exceeds the 126 MB L2"
+                      % (n * ((m + 63) // 64 * 64) * stats["digits"] / 1e6),
+                "mean_neighborhood": float(rowsums.mean()), "nonempty_a_tiles": tiles,
+                "dense_a_tiles": stats["a_tiles_dense"], "digits": stats["digits"],
+                "fixup_fraction": stats["fixups"] / max(1, stats["fixups"] + stats["decided"]),
+            },
+            "e2e": {
+                "value": scores_per_step / (e2e_ms / 1e3 / e2e_steps), "unit": "scores/s",
+                "h2d_bytes_per_step": int(packed_host.numel() * 4 + attrs_host.numel() * 4 + rows_host.numel() * 4),
+                "d2h_bytes_per_step": int(counts_host.numel() * 4),
+                "ms_per_step": e2e_ms / e2e_steps,
+                "path": "sb_neigh_upload_packed + sb_enrich_create + sb_enrich_perm_counts (host buffers, pinned)"
+                        if world == 1 else "pinned H2D + sb_enrich_perm_counts_dev + NCCL all-reduce + D2H",
+                "resident_and_e2e_counts_equal": agree,
+            },
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {
+                "kernel": "k_gemm<%d> (tcgen05.mma.kind::i8, %d launches)" % (stats["digits"], gemm_launches),
+                "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": None,
+                "peak_source": peak_src,
+                "executed_int8_tops": int8_ops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None,
+                "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
+            },
+            "stages": {"define_neighborhoods_s": t_stage1, "define_neighborhoods_kernel_ms": k1_ms,
+                       "perm_index_replay_host_s": t_rng, "compute_pvalues_null_s": sec_per_step},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            nbd = nb.dense(dtype=np.int64) if n * n * 8 <= (16 << 30) else None
+            if nbd is not None:
+                times = cpu_reference_steps(cfg, nbd, args.cpu_sample_perms, 1)
+                t = float(np.sum(times))
+                out["cpu_baseline"] = {
+                    "value": float(n) * m * len(times) / t, "unit": "scores/s", "cores": os.cpu_count(),
+                    "kind": "port",
+                    "sample": "%d of %d permutations of the same workload through oracle/safe_oracle.py "
+                              "(NumPy/OpenBLAS np.dot on the dense int64 matrix, all threads), %.1f s"
+                              % (len(times), P, t)}
+            else:
+                out["cpu_baseline"] = {"value": None, "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "dense int64 neighborhood matrix does not fit in host memory"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -65,6 +65,12 @@ int sb_ctx_set_stream(sb_ctx* ctx, void* cuda_stream);
 int sb_ctx_synchronize(sb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t sb_ctx_launch_count(sb_ctx* ctx);
+/* Device-time accounting: with profiling on, launches are bracketed by CUDA events on the context's stream.
+ * sb_ctx_kernel_ms synchronizes, returns the summed milliseconds and the number of brackets of one kernel class
+ * (0 score GEMM, 1 operand gather, 2 fp64 fix-up, 3 SSSP, 4 euclid, 5 hypergeom, 6 fp64 scores, 7 operand prep)
+ * and clears that class. */
+int sb_ctx_profile(sb_ctx* ctx, int enable);
+int sb_ctx_kernel_ms(sb_ctx* ctx, int kernel_class, double* ms_out, int64_t* count_out);
 /* pin / unpin a caller-owned host buffer so the *_host entry points copy at full PCIe speed */
 int sb_host_register(void* ptr, int64_t bytes);
 int sb_host_unregister(void* ptr);

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libsafe_b200.so")
 SB_F32, SB_F64 = 0, 1
 SCORE_TYPES = {"sum": 0, "z-score": 1}
 ENGINES = {"auto": 0, "simt": 1, "tc": 2}
+KERNEL_CLASSES = {"gemm": 0, "gather": 1, "fixup": 2, "sssp": 3, "euclid": 4, "hypergeom": 5, "score": 6, "prep": 7}
 
 _vp = C.c_void_p
 _i64 = C.c_int64
@@ -30,6 +31,8 @@ SIGNATURES = {
     "sb_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "sb_ctx_synchronize": (C.c_int, [_vp]),
     "sb_ctx_launch_count": (_i64, [_vp]),
+    "sb_ctx_profile": (C.c_int, [_vp, C.c_int]),
+    "sb_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
     "sb_host_register": (C.c_int, [_vp, _i64]),
     "sb_host_unregister": (C.c_int, [_vp]),
     "sb_neigh_ld": (_i64, [_i64]),
@@ -122,6 +125,15 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.sb_ctx_launch_count(self.h))
+
+    def profile(self, enable=True):
+        _check(self.lib, self.lib.sb_ctx_profile(self.h, int(bool(enable))))
+
+    def kernel_ms(self, kernel_class):
+        """(milliseconds, brackets) accumulated for one kernel class since the last query; see KERNEL_CLASSES."""
+        ms, cnt = C.c_double(), _i64()
+        _check(self.lib, self.lib.sb_ctx_kernel_ms(self.h, KERNEL_CLASSES[kernel_class], C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     def close(self):
         if getattr(self, "h", None):
@@ -281,12 +293,18 @@ class Enrichment:
         _check(self.lib, self.lib.sb_enrich_score(self.h, SCORE_TYPES[score_type], _ptr(out)))
         return out
 
-    def perm_counts(self, perm_rows, score_type="sum", engine="auto"):
+    def perm_counts(self, perm_rows, score_type="sum", engine="auto", out=None):
         perm_rows = _as(perm_rows, np.int32)
         if perm_rows.ndim != 2 or perm_rows.shape[1] != self.n:
             raise ValueError("perm_rows must be [num_permutations, n]")
-        cneg = np.empty((self.n, self.m), dtype=np.uint32)
-        cpos = np.empty((self.n, self.m), dtype=np.uint32)
+        if out is None:
+            cneg = np.empty((self.n, self.m), dtype=np.uint32)
+            cpos = np.empty((self.n, self.m), dtype=np.uint32)
+        else:
+            cneg, cpos = out
+            for a in (cneg, cpos):
+                if a.dtype != np.uint32 or a.shape != (self.n, self.m) or not a.flags.c_contiguous:
+                    raise ValueError("out arrays must be C-contiguous uint32 [n, m]")
         _check(self.lib, self.lib.sb_enrich_perm_counts(self.h, SCORE_TYPES[score_type], ENGINES[engine],
                                                         _ptr(perm_rows), perm_rows.shape[0], _ptr(cneg),
                                                         _ptr(cpos)))

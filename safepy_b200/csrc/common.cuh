@@ -8,6 +8,8 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "../../include/safe_b200.h"
 
@@ -73,13 +75,39 @@ struct DevBuf {
 
 }  // namespace sb
 
+// kernel classes whose device time can be accumulated with CUDA events (sb_ctx_profile / sb_ctx_kernel_ms)
+enum { SB_K_GEMM = 0, SB_K_GATHER = 1, SB_K_FIXUP = 2, SB_K_SSSP = 3, SB_K_EUCLID = 4, SB_K_HYPERGEOM = 5,
+       SB_K_SCORE = 6, SB_K_PREP = 7, SB_K_CLASSES = 8 };
+
 struct sb_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers[SB_K_CLASSES];
     void bind() const { SB_CUDA(cudaSetDevice(device)); }
 };
+
+namespace sb {
+// RAII: when profiling is on, brackets the launches issued in its scope with an event pair on the ctx stream
+struct KernelTimer {
+    sb_ctx* ctx;
+    int cls;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    KernelTimer(sb_ctx* c, int k) : ctx(c), cls(k) {
+        if (!ctx->profile) return;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+    }
+    ~KernelTimer() {
+        if (!e0) return;
+        cudaEventRecord(e1, ctx->stream);
+        ctx->timers[cls].emplace_back(e0, e1);
+    }
+};
+}  // namespace sb
 
 #define SB_LAUNCH_CHECK(ctx)            \
     do {                                \

@@ -311,6 +311,7 @@ void enrich_score_into(sb_enrich* e, int score_type, double* out_dev) {
     dim3 grid(static_cast<unsigned>(e->n), static_cast<unsigned>(sb_ceil_div(e->m, 128)));
     SB_CHECK(grid.y <= 65535, "attribute count %lld too large for one launch", (long long)e->m);
     const bool zs = score_type == SB_SCORE_ZSCORE;
+    KernelTimer kt(ctx, SB_K_SCORE);
     if (e->dtype == SB_F32) {
         const float* b = static_cast<const float*>(e->b);
         if (zs)
@@ -382,6 +383,7 @@ void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij,
     sb_ctx* ctx = e->ctx;
     const double* s0 = enrich_observed(e, SB_SCORE_SUM);
     const unsigned blocks = static_cast<unsigned>(ctx->num_sms * 8);
+    KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
         k_fixup<float><<<blocks, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
                                                         perm_dev, e->n, e->m, flag_ij, flag_p, flag_count_dev,
@@ -433,9 +435,12 @@ static void hypergeom_dev(sb_enrich* e, double* pv_dev, double* nes_dev) {
     lf.reserve(h_lf.size());
     SB_CUDA(cudaMemcpyAsync(lf.p, h_lf.data(), h_lf.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * m, 256), ctx->num_sms * 16));
-    k_hypergeom<<<blocks, 256, 0, st>>>(X, colsum.p, nneigh.p, lf.p, static_cast<double>(n_total), n, m, pv_dev,
-                                        nes_dev);
-    SB_LAUNCH_CHECK(ctx);
+    {
+        KernelTimer kt(ctx, SB_K_HYPERGEOM);
+        k_hypergeom<<<blocks, 256, 0, st>>>(X, colsum.p, nneigh.p, lf.p, static_cast<double>(n_total), n, m, pv_dev,
+                                            nes_dev);
+        SB_LAUNCH_CHECK(ctx);
+    }
     SB_CUDA(cudaStreamSynchronize(st));
 }
 

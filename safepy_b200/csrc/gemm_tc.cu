@@ -502,6 +502,7 @@ static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
         SB_CUDA(cudaFuncSetAttribute(k_gemm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
+    KernelTimer kt(ctx, SB_K_GEMM);
     k_gemm<D><<<grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
     SB_LAUNCH_CHECK(ctx);
 }
@@ -518,6 +519,7 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp, int grid) {
 static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
     dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
     SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
+    KernelTimer kt(ctx, SB_K_GATHER);
 #define SB_G(DD)                                                                                              \
     k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->n, pl->mpad, pl->n_kt, pl->n_cg, pl->pps, \
                                                 pl->log2_mpad, batch_perms, pl->bcat.p)
@@ -569,6 +571,7 @@ static TcPlan* build_plan(sb_enrich* e) {
     cudaStream_t st = ctx->stream;
     TcPlan* pl = new TcPlan;
     try {
+        KernelTimer kt_prep(ctx, SB_K_PREP);
         const int64_t n = e->n, m = e->m;
         pl->n = n;
         pl->m = m;

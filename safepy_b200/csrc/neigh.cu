@@ -276,6 +276,35 @@ int sb_ctx_synchronize(sb_ctx* ctx) {
 
 int64_t sb_ctx_launch_count(sb_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+int sb_ctx_profile(sb_ctx* ctx, int enable) {
+    SB_API_BEGIN
+    SB_CHECK(ctx, "sb_ctx_profile: ctx is NULL");
+    ctx->profile = enable != 0;
+    SB_API_END
+}
+
+int sb_ctx_kernel_ms(sb_ctx* ctx, int kernel_class, double* ms_out, int64_t* count_out) {
+    SB_API_BEGIN
+    SB_CHECK(ctx && ms_out && count_out, "sb_ctx_kernel_ms: NULL argument");
+    SB_CHECK(kernel_class >= 0 && kernel_class < SB_K_CLASSES, "sb_ctx_kernel_ms: unknown kernel class %d",
+             kernel_class);
+    ctx->bind();
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double total = 0.0;
+    auto& v = ctx->timers[kernel_class];
+    for (auto& pr : v) {
+        float ms = 0.f;
+        SB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        total += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    *ms_out = total;
+    *count_out = static_cast<int64_t>(v.size());
+    v.clear();
+    SB_API_END
+}
+
 int sb_host_register(void* ptr, int64_t bytes) {
     SB_API_BEGIN
     SB_CUDA(cudaHostRegister(ptr, static_cast<size_t>(bytes), cudaHostRegisterDefault));
@@ -381,9 +410,12 @@ int sb_neigh_euclid(sb_neigh* a, const double* x_host, const double* y_host, dou
               static_cast<unsigned>(sb_ceil_div(row1 - row0, EU_ROWS)));
     SB_CHECK(grid.y <= 65535, "sb_neigh_euclid: row range too large for one launch (%lld rows)",
              (long long)(row1 - row0));
-    k_euclid<<<grid, EU_WARPS * 32, 0, ctx->stream>>>(xy.p, xy.p + n, n, s_star, any_pair, row0, row1, a->words,
-                                                      a->ld);
-    SB_LAUNCH_CHECK(ctx);
+    {
+        KernelTimer kt(ctx, SB_K_EUCLID);
+        k_euclid<<<grid, EU_WARPS * 32, 0, ctx->stream>>>(xy.p, xy.p + n, n, s_star, any_pair, row0, row1, a->words,
+                                                          a->ld);
+        SB_LAUNCH_CHECK(ctx);
+    }
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_API_END
 }
@@ -445,10 +477,13 @@ int sb_neigh_shortpath(sb_neigh* a, const int64_t* indptr_host, const int32_t* i
     SB_CUDA(cudaMemsetAsync(d_stamp.p, 0, static_cast<size_t>(grid) * n * sizeof(uint32_t), st));
     SB_CUDA(cudaMemsetAsync(d_next.p, 0, sizeof(unsigned int), st));
     SsspWs ws{d_dist.p, d_stamp.p, d_queue.p, d_next.p};
-    k_sssp<<<static_cast<unsigned>(grid), SP_THREADS, smem, st>>>(d_indptr.p, d_indices.p,
-                                                                  length_host ? d_len.p : nullptr, n, cutoff, row0,
-                                                                  row1, ws, a->words, a->ld);
-    SB_LAUNCH_CHECK(ctx);
+    {
+        KernelTimer kt(ctx, SB_K_SSSP);
+        k_sssp<<<static_cast<unsigned>(grid), SP_THREADS, smem, st>>>(d_indptr.p, d_indices.p,
+                                                                      length_host ? d_len.p : nullptr, n, cutoff,
+                                                                      row0, row1, ws, a->words, a->ld);
+        SB_LAUNCH_CHECK(ctx);
+    }
     SB_CUDA(cudaStreamSynchronize(st));
     SB_API_END
 }

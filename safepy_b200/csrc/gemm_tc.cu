@@ -28,7 +28,8 @@ namespace sb {
 constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
 constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
 constexpr int TC_TILE_A = TC_ROWS * TC_KT;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
 constexpr int TC_KT_CAP = 2048;          // k-tile ids of one row block staged in smem by the producer
 constexpr int TC_S0_BYTES = 64 * TC_ROWS * 8;
 
@@ -65,18 +66,23 @@ struct TcCfg {
     static constexpr int SMEM = STAGES * STAGE + TC_S0_BYTES + TC_KT_CAP * 4 + 256;
 };
 
-template <int D>
+// kernel flavours (compile-time, so the hot epilogue carries no mode tests)
+enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
+
+// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (+ TMEM alloc), 2..9 = epilogue.
+// Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half ((w - 2) >> 2) of every digit plane.
+template <int D, int KIND, bool SMALL_M>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
     uint8_t* sB = smem + C::STAGES * TC_TILE_A;
-    long long* s0s = reinterpret_cast<long long*>(smem + C::STAGES * C::STAGE);
+    int2* s0s = reinterpret_cast<int2*>(smem + C::STAGES * C::STAGE);  // [64 cols][128 rows] (hi, lo) of S0
     int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES + TC_KT_CAP * 4);
-    uint64_t* full = bars;                      // [STAGES]
-    uint64_t* empty = bars + C::STAGES;         // [STAGES]
-    uint64_t* tfull = bars + 2 * C::STAGES;     // [2]
+    uint64_t* full = bars;                        // [STAGES]
+    uint64_t* empty = bars + C::STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]
     uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
 
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], 4);
+            mbar_init(&tempty[b], TC_EPI_WARPS);
         }
         mbar_fence_init();
     }
@@ -175,72 +181,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
-        const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+        const int half = (warp - 2) >> 2;        // which 32 of the slot's 64 (permutation, attribute) columns
         const int row_in_tile = quarter * 32 + lane;
+        const int c0 = half * 32;
         uint32_t acc_it = 0;
-        const bool small_m = p.mpad < 64;
         for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
             const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
             const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
             const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + row_in_tile;
             const bool row_ok = row < p.n;
-            const int64_t jbase = small_m ? 0 : static_cast<int64_t>(cg) * 64;
-            long long band = 0;
-            unsigned long long inexact_mask = 0;
-            if (p.mode & (TCM_COUNT | TCM_FLAG)) {
-                band = row_ok ? (p.row_ptr[row + 1] - p.row_ptr[row]) : 0;
+            const int64_t jbase = SMALL_M ? 0 : static_cast<int64_t>(cg) * 64;
+            int band = 0;
+            uint32_t inexact_mask = 0;
+            uint32_t cnt[32];
+            if (KIND == TCK_COUNT) {
+                band = row_ok ? static_cast<int>(p.row_ptr[row + 1] - p.row_ptr[row]) : 0;
 #pragma unroll 4
-                for (int c = 0; c < 64; ++c) {
-                    const int64_t j = small_m ? (c & (p.mpad - 1)) : jbase + c;
-                    if (p.inexact[j]) inexact_mask |= 1ull << c;
-                    // thread-private column of the observed fixed-point score tile
-                    s0s[c * TC_ROWS + row_in_tile] = p.s0fix[row * p.mpad + j];
+                for (int cc = 0; cc < 32; ++cc) {
+                    const int c = c0 + cc;
+                    const int64_t j = SMALL_M ? (c & (p.mpad - 1)) : jbase + c;
+                    if (p.inexact[j]) inexact_mask |= 1u << cc;
+                    // thread-private copy of the observed fixed-point score, split as S0 = hi * 256 + lo
+                    const long long s0 = p.s0fix[row * p.mpad + j];
+                    s0s[c * TC_ROWS + row_in_tile] = make_int2(static_cast<int>(s0 >> 8), static_cast<int>(s0 & 255));
                 }
-            }
-            uint32_t cnt[64];
 #pragma unroll
-            for (int c = 0; c < 64; ++c) cnt[c] = 0;
+                for (int cc = 0; cc < 32; ++cc) cnt[cc] = 0;
+            }
+            // one band per warp-uniform test: columns of a group are normally all exact or all inexact
+            const bool all_exact = __all_sync(0xffffffffu, inexact_mask == 0);
+            const bool all_inexact = __all_sync(0xffffffffu, inexact_mask == 0xffffffffu);
 
             for (int q = q0; q < q1; ++q) {
                 const uint32_t buf = acc_it & 1u, tpar = (acc_it >> 1) & 1u;
                 mbar_wait(&tfull[buf], tpar);
                 tc_fence_after();
-                const uint32_t t_addr = tbase + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256;
+                const uint32_t t_addr = tbase + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + c0;
+                uint32_t flagmask = 0;
 #pragma unroll
-                for (int ch = 0; ch < 4; ++ch) {
+                for (int ch = 0; ch < 2; ++ch) {
                     uint32_t acc[D][16];
 #pragma unroll
                     for (int d = 0; d < D; ++d) tmem_ld16(t_addr + d * 64 + ch * 16, acc[d]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int cc = 0; cc < 16; ++cc) {
-                        const int c = ch * 16 + cc;
-                        if (p.mode & TCM_RAW) {
+                    for (int x = 0; x < 16; ++x) {
+                        const int cc = ch * 16 + x;   // column inside this warp's half
+                        const int c = c0 + cc;        // column inside the slot
+                        if (KIND == TCK_RAW) {
 #pragma unroll
                             for (int d = 0; d < D; ++d)
-                                p.raw_out[row_in_tile * C::NCOLS + d * 64 + c] = static_cast<int32_t>(acc[d][cc]);
-                            continue;
-                        }
-                        long long S = static_cast<int32_t>(acc[0][cc]);
-                        if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][cc])) << 8;
-                        if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][cc])) << 16;
-                        if (p.mode & TCM_STORE) {
-                            const bool col_ok = small_m ? (c < p.mpad) : true;
+                                p.raw_out[row_in_tile * C::NCOLS + d * 64 + c] = static_cast<int32_t>(acc[d][x]);
+                        } else if (KIND == TCK_STORE) {
+                            long long S = static_cast<int32_t>(acc[0][x]);
+                            if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][x])) << 8;
+                            if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][x])) << 16;
+                            const bool col_ok = SMALL_M ? (c < p.mpad) : true;
                             if (col_ok) p.s0fix[row * p.mpad + jbase + c] = S;
-                            continue;
+                        } else {
+                            // S = hi * 256 + lo with lo in [0, 256); all int32 (|S| < 2^38 is checked on the host)
+                            const int a0 = static_cast<int32_t>(acc[0][x]);
+                            int hi = a0 >> 8;
+                            if (D > 1) hi += static_cast<int32_t>(acc[1][x]);
+                            if (D > 2) hi += static_cast<int32_t>(acc[D - 1][x]) << 8;
+                            const int lo = a0 & 255;
+                            const int2 o = s0s[c * TC_ROWS + row_in_tile];
+                            int dh = hi - o.x;
+                            dh = max(min(dh, 1 << 22), -(1 << 22));  // keeps sign and |diff| >> band, avoids overflow
+                            const int diff = dh * 256 + (lo - o.y);
+                            uint32_t add;
+                            if (all_exact) {
+                                add = (diff >= 0 ? 0x10000u : 0u) + (diff <= 0 ? 1u : 0u);
+                            } else {
+                                const int b = (all_inexact || ((inexact_mask >> cc) & 1u)) ? band : 0;
+                                const bool gt = diff > b, lt = diff < -b;
+                                const bool und = !(gt | lt);
+                                const bool tie = und && b == 0;
+                                add = ((gt | tie) ? 0x10000u : 0u) + ((lt | tie) ? 1u : 0u);
+                                if (und && b != 0) flagmask |= 1u << cc;
+                            }
+                            if (SMALL_M) {
+                                const int pl = q * p.pps + (c >> p.log2_mpad);
+                                if (pl >= p.batch_perms) {
+                                    add = 0;
+                                    flagmask &= ~(1u << cc);
+                                }
+                            }
+                            cnt[cc] += add;
                         }
-                        const int pl = small_m ? q * p.pps + (c >> p.log2_mpad) : q;
-                        const bool valid = pl < p.batch_perms;
-                        const long long diff = S - s0s[c * TC_ROWS + row_in_tile];
-                        const long long b = ((inexact_mask >> c) & 1ull) ? band : 0;
-                        const bool gt = diff > b, lt = diff < -b;
-                        const bool und = !(gt | lt);
-                        const bool tie = und && b == 0;
-                        if (p.mode & TCM_COUNT)
-                            cnt[c] += valid ? ((static_cast<uint32_t>(gt | tie) << 16) | static_cast<uint32_t>(lt | tie))
-                                            : 0u;
-                        if ((p.mode & TCM_FLAG) && und && b != 0 && valid && row_ok) {
-                            const int64_t j = small_m ? (c & (p.mpad - 1)) : jbase + c;
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                ++acc_it;
+                if (KIND == TCK_COUNT) {
+                    if (!(p.mode & TCM_COUNT)) {
+#pragma unroll
+                        for (int cc = 0; cc < 32; ++cc) cnt[cc] = 0;
+                    }
+                    // rare: comparisons the fixed-point scores cannot decide go to the exact fp64 fix-up list
+                    if (flagmask && (p.mode & TCM_FLAG) && row_ok) {
+                        while (flagmask) {
+                            const int cc = __ffs(flagmask) - 1;
+                            flagmask &= flagmask - 1;
+                            const int c = c0 + cc;
+                            const int64_t j = SMALL_M ? (c & (p.mpad - 1)) : jbase + c;
+                            const int pl = SMALL_M ? q * p.pps + (c >> p.log2_mpad) : q;
                             if (j < p.m) {
                                 const unsigned int k = atomicAdd(p.flag_count, 1u);
                                 if (k < p.flag_cap) {
@@ -251,31 +299,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
-                ++acc_it;
             }
-            if ((p.mode & TCM_COUNT) && row_ok) {
-                if (small_m) {
+            if (KIND == TCK_COUNT && (p.mode & TCM_COUNT) && row_ok) {
+                if (SMALL_M) {
                     // columns c and c' with c % mpad == c' % mpad carry different permutations of the same attribute
                     for (int j = 0; j < p.mpad && j < p.m; ++j) {
                         uint32_t pos = 0, neg = 0;
 #pragma unroll
-                        for (int c = 0; c < 64; ++c)
-                            if ((c & (p.mpad - 1)) == j) {
-                                pos += cnt[c] >> 16;
-                                neg += cnt[c] & 0xffffu;
+                        for (int cc = 0; cc < 32; ++cc)
+                            if (((c0 + cc) & (p.mpad - 1)) == j) {
+                                pos += cnt[cc] >> 16;
+                                neg += cnt[cc] & 0xffffu;
                             }
                         if (pos) atomicAdd(&p.cpos[row * p.m + j], pos);
                         if (neg) atomicAdd(&p.cneg[row * p.m + j], neg);
                     }
                 } else {
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) {
-                        const int64_t j = jbase + c;
+                    for (int cc = 0; cc < 32; ++cc) {
+                        const int64_t j = jbase + c0 + cc;
                         if (j < p.m) {
-                            const uint32_t pos = cnt[c] >> 16, neg = cnt[c] & 0xffffu;
+                            const uint32_t pos = cnt[cc] >> 16, neg = cnt[cc] & 0xffffu;
                             if (pos) atomicAdd(&p.cpos[row * p.m + j], pos);
                             if (neg) atomicAdd(&p.cneg[row * p.m + j], neg);
                         }
@@ -494,26 +538,38 @@ struct TcPlan {
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
 
-template <int D>
+template <int D, int KIND, bool SMALL_M>
 static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
     using C = TcCfg<D>;
     static bool configured = false;
     if (!configured) {
-        SB_CUDA(cudaFuncSetAttribute(k_gemm<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
     KernelTimer kt(ctx, SB_K_GEMM);
-    k_gemm<D><<<grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
+    k_gemm<D, KIND, SMALL_M><<<grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
     SB_LAUNCH_CHECK(ctx);
 }
 
-static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp, int grid) {
-    if (D == 1)
-        launch_gemm<1>(ctx, gp, grid);
-    else if (D == 2)
-        launch_gemm<2>(ctx, gp, grid);
+template <int D>
+static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams& gp, int grid) {
+    if (kind == TCK_RAW)
+        launch_gemm<D, TCK_RAW, false>(ctx, gp, grid);
+    else if (kind == TCK_STORE)
+        small_m ? launch_gemm<D, TCK_STORE, true>(ctx, gp, grid) : launch_gemm<D, TCK_STORE, false>(ctx, gp, grid);
     else
-        launch_gemm<3>(ctx, gp, grid);
+        small_m ? launch_gemm<D, TCK_COUNT, true>(ctx, gp, grid) : launch_gemm<D, TCK_COUNT, false>(ctx, gp, grid);
+}
+
+static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp, int grid) {
+    const int kind = (gp.mode & TCM_RAW) ? TCK_RAW : (gp.mode & TCM_STORE) ? TCK_STORE : TCK_COUNT;
+    const bool small_m = gp.mpad < 64;
+    if (D == 1)
+        launch_gemm_k<1>(ctx, kind, small_m, gp, grid);
+    else if (D == 2)
+        launch_gemm_k<2>(ctx, kind, small_m, gp, grid);
+    else
+        launch_gemm_k<3>(ctx, kind, small_m, gp, grid);
 }
 
 static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
@@ -590,6 +646,19 @@ static TcPlan* build_plan(sb_enrich* e) {
         }
         pl->n_rb = static_cast<int32_t>(sb_ceil_div(n, TC_ROWS));
         pl->n_kt = static_cast<int32_t>(sb_ceil_div(n, TC_KT));
+
+        // the epilogue compares in int32 (score = hi * 256 + lo): needs n_i * 2^(8D-2) < 2^38
+        {
+            std::vector<int64_t> h_rp(n + 1);
+            SB_CUDA(cudaMemcpyAsync(h_rp.data(), e->row_ptr.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            int64_t max_nb = 0;
+            for (int64_t i = 0; i < n; ++i) max_nb = std::max(max_nb, h_rp[i + 1] - h_rp[i]);
+            if (max_nb >= 65536) {
+                pl->usable = false;  // neighborhoods of 65536+ nodes: exact SIMT engine
+                return pl;
+            }
+        }
 
         // ---- A tiles
         DevBuf<uint8_t> occ;

@@ -149,6 +149,10 @@ int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int variant /*0 = pro
                        const int8_t* a_host /*128 x 64*ktiles*/, const int8_t* b_host /*64*ktiles x ncols*/,
                        int32_t* d_host /*128 x ncols*/);
 
+/* Streaming-rate probe of the same kernel: `grid` CTAs x `slots` accumulations over `ktiles` L2-resident tile pairs;
+ * returns device milliseconds (bench / profiling only). */
+int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,7 @@ SIGNATURES = {
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
     "sb_selftest_mma_i8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "sb_selftest_mma_rate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
 }
 
 
@@ -350,3 +351,10 @@ def selftest_mma_i8(ctx, a, b, variant=0):
     d = np.empty((128, ncols), dtype=np.int32)
     _check(ctx.lib, ctx.lib.sb_selftest_mma_i8(ctx.h, ncols, k // 64, int(variant), _ptr(a), _ptr(b), _ptr(d)))
     return d
+
+
+def selftest_mma_rate(ctx, ncols=192, ktiles=32, slots=64, grid=148):
+    """Device ms for grid x slots accumulations of ktiles L2-resident k-tiles (128 x ncols x 64 int8 each)."""
+    ms = C.c_double()
+    _check(ctx.lib, ctx.lib.sb_selftest_mma_rate(ctx.h, ncols, ktiles, slots, grid, C.byref(ms)))
+    return ms.value

@@ -2,7 +2,9 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -105,6 +107,30 @@ struct KernelTimer {
         if (!e0) return;
         cudaEventRecord(e1, ctx->stream);
         ctx->timers[cls].emplace_back(e0, e1);
+    }
+};
+}  // namespace sb
+
+namespace sb {
+// SB_TRACE=1: print host-side phase timings (each phase is closed by a stream synchronize) to stderr
+struct PhaseTrace {
+    sb_ctx* ctx;
+    const char* name;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    PhaseTrace(sb_ctx* c, const char* n) : ctx(c), name(n) {
+        static const bool enabled = getenv("SB_TRACE") != nullptr;
+        on = enabled;
+        if (on) {
+            cudaStreamSynchronize(ctx->stream);
+            t0 = std::chrono::steady_clock::now();
+        }
+    }
+    ~PhaseTrace() {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "[sb_trace] %-28s %9.3f ms\n", name, ms);
     }
 };
 }  // namespace sb

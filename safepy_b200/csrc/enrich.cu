@@ -286,6 +286,7 @@ __global__ void k_sum_i32(const int32_t* __restrict__ v, int64_t n, unsigned lon
 // ------------------------------------------------------------------------------------------------ host side
 static void build_csr(sb_enrich* e) {
     sb_ctx* ctx = e->ctx;
+    PhaseTrace tr(ctx, "enrich.build_csr");
     const int64_t n = e->n;
     DevBuf<int64_t> cnt;
     cnt.reserve(n);
@@ -513,6 +514,7 @@ int sb_enrich_destroy(sb_enrich* e) {
     SB_API_BEGIN
     if (e) {
         e->ctx->bind();
+        PhaseTrace tr(e->ctx, "enrich.destroy");
         if (e->tc) tc_plan_destroy(e->tc);
         if (e->b_owned && e->b) cudaFree(const_cast<void*>(e->b));
         delete e;

@@ -151,7 +151,9 @@ int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int variant /*0 = pro
 
 /* Streaming-rate probe of the same kernel: `grid` CTAs x `slots` accumulations over `ktiles` L2-resident tile pairs;
  * returns device milliseconds (bench / profiling only). */
-int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, double* ms_out);
+int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, int dbg /*1: no MMAs, 2: no copies*/,
+                         const uint32_t* desc_override /*NULL, or 9 descriptor fields for speed-only experiments*/,
+                         double* ms_out);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ SIGNATURES = {
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
     "sb_selftest_mma_i8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
-    "sb_selftest_mma_rate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "sb_selftest_mma_rate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
 }
 
 
@@ -353,8 +353,9 @@ def selftest_mma_i8(ctx, a, b, variant=0):
     return d
 
 
-def selftest_mma_rate(ctx, ncols=192, ktiles=32, slots=64, grid=148):
+def selftest_mma_rate(ctx, ncols=192, ktiles=32, slots=64, grid=148, dbg=0, desc=None):
     """Device ms for grid x slots accumulations of ktiles L2-resident k-tiles (128 x ncols x 64 int8 each)."""
     ms = C.c_double()
-    _check(ctx.lib, ctx.lib.sb_selftest_mma_rate(ctx.h, ncols, ktiles, slots, grid, C.byref(ms)))
+    d = None if desc is None else np.ascontiguousarray(desc, dtype=np.uint32)
+    _check(ctx.lib, ctx.lib.sb_selftest_mma_rate(ctx.h, ncols, ktiles, slots, grid, dbg, _ptr(d), C.byref(ms)))
     return ms.value

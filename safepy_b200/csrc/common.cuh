@@ -88,6 +88,12 @@ struct sb_ctx {
     int64_t launches = 0;
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers[SB_K_CLASSES];
+    // grow-only scratch shared by all plans of this context (used only inside one call at a time):
+    // gathered operand tiles, fix-up list, packed count accumulators
+    sb::DevBuf<int8_t> ws_bcat;
+    sb::DevBuf<uint64_t> ws_flag_ij;
+    sb::DevBuf<uint32_t> ws_flag_p;
+    sb::DevBuf<uint32_t> ws_cpk;
     void bind() const { SB_CUDA(cudaSetDevice(device)); }
 };
 

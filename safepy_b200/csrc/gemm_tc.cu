@@ -28,10 +28,14 @@ namespace sb {
 constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
 constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
 constexpr int TC_TILE_A = TC_ROWS * TC_KT;
+constexpr int TC_STAGES = 4;            // smem ring depth; producer warp k owns stage k
+constexpr int TC_PROD_WARPS = TC_STAGES;
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = (2 + TC_EPI_WARPS) * 32;
-constexpr int TC_KT_CAP = 2048;          // k-tile ids of one row block staged in smem by the producer
-constexpr int TC_S0_BYTES = 64 * TC_ROWS * 8;
+// The SM's warp arbiter favours high warp ids: the latency-critical single-warp roles (MMA issue, copy issue)
+// therefore sit above the eight epilogue warps.
+constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
+constexpr int TC_THREADS = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;
 
 enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
 
@@ -54,32 +58,89 @@ struct GemmParams {
     unsigned int flag_cap;
     int32_t* raw_out;         // TCM_RAW: [128][64*D]
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
-    int32_t q_wrap;           // slot index is taken modulo q_wrap (rate self-test re-reads one slot)
+    int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
+    int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies, bit2 = no tcgen05 fence after the
+                              // full-barrier wait, bit3 = plain arrive instead of tcgen05.commit on `empty`,
+                              // bit4 = one polling lane per epilogue warp
+    uint32_t a_layout, b_layout;  // smem descriptor layout_type (0 = no swizzle; probe may try 2/4/6)
+    uint32_t a_kstep, b_kstep;    // descriptor start-address advance per K=32 MMA
+    uint32_t b_kmajor;            // probe only: 1 = declare B K-major in the instruction descriptor
 };
 
 template <int D>
 struct TcCfg {
     static constexpr int NCOLS = 64 * D;
     static constexpr int TILE_B = TC_KT * NCOLS;
-    static constexpr int STAGE = TC_TILE_A + TILE_B;
-    static constexpr int STAGES = D == 3 ? 7 : 8;
-    static constexpr int SMEM = STAGES * STAGE + TC_S0_BYTES + TC_KT_CAP * 4 + 256;
+    static constexpr int TILE_AB = TC_TILE_A + TILE_B;
+    static constexpr int TPS = D == 1 ? 3 : 2;  // k-tiles per pipeline stage
+    static constexpr int STAGE = TPS * TILE_AB;
+    static constexpr int STAGES = TC_STAGES;
+    static constexpr int OFF_B = STAGES * TPS * TC_TILE_A;
+    static constexpr int OFF_S0HI = STAGES * STAGE;         // int32 [64][128]
+    static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;   // uint32 [16][128], 4 columns per word
+    static constexpr int OFF_BAR = OFF_S0LO + 16 * TC_ROWS * 4;
+    static constexpr int SMEM = OFF_BAR + 256;
+};
+
+// Walks the (unit, slot q, stage fill) sequence every role of the kernel agrees on.  A "fill" is one pipeline
+// stage worth of k-tiles (up to TPS); fill number f always lands in stage f % TC_STAGES.
+struct FillWalker {
+    const GemmParams& p;
+    int tps;
+    int u, rb, cg, q, q1, t0, nk, nfills, pr;
+    bool done;
+    __device__ FillWalker(const GemmParams& pp, int tps_) : p(pp), tps(tps_), u(blockIdx.x), pr(0) {
+        done = true;
+        enter_unit();
+    }
+    __device__ void enter_unit() {
+        const int n_units = p.n_rb * p.n_cg * p.q_chunks;
+        done = u >= n_units;
+        if (done) return;
+        rb = u % p.n_rb;
+        const int rest = u / p.n_rb;
+        cg = rest % p.n_cg;
+        const int qc = rest / p.n_cg;
+        q = qc * p.q_per;
+        q1 = min(p.q_total, q + p.q_per);
+        t0 = p.tile_ptr[rb];
+        nk = p.tile_ptr[rb + 1] - t0;
+        nfills = (nk + tps - 1) / tps;
+        pr = 0;
+    }
+    __device__ bool first_of_slot() const { return pr == 0; }
+    __device__ bool last_of_slot() const { return pr == nfills - 1; }
+    __device__ int tiles_in_fill() const { return min(tps, nk - pr * tps); }
+    // advance by one fill; returns true when a slot (one accumulation) was completed
+    __device__ bool next() {
+        if (++pr < nfills) return false;
+        pr = 0;
+        if (++q >= q1) {
+            u += gridDim.x;
+            enter_unit();
+        }
+        return true;
+    }
+    __device__ void advance(int k) {
+        for (int i = 0; i < k && !done; ++i) next();
+    }
 };
 
 // kernel flavours (compile-time, so the hot epilogue carries no mode tests)
 enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
 
-// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer (+ TMEM alloc), 2..9 = epilogue.
-// Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half ((w - 2) >> 2) of every digit plane.
+// Warp roles: 0..7 = epilogue, 8..11 = bulk-copy producers (warp 8 + k fills stage k, so the per-fill barrier /
+// issue latency chains of four warps overlap), 12 = MMA issuer (+ TMEM alloc).
+// Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
 template <int D, int KIND, bool SMALL_M>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
-    uint8_t* sB = smem + C::STAGES * TC_TILE_A;
-    int2* s0s = reinterpret_cast<int2*>(smem + C::STAGES * C::STAGE);  // [64 cols][128 rows] (hi, lo) of S0
-    int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE + TC_S0_BYTES + TC_KT_CAP * 4);
+    uint8_t* sB = smem + C::OFF_B;
+    int32_t* s_hi = reinterpret_cast<int32_t*>(smem + C::OFF_S0HI);
+    uint32_t* s_lo = reinterpret_cast<uint32_t*>(smem + C::OFF_S0LO);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* full = bars;                        // [STAGES]
     uint64_t* empty = bars + C::STAGES;           // [STAGES]
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]
@@ -99,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -107,82 +168,128 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
 
     const int n_units = p.n_rb * p.n_cg * p.q_chunks;
 
-    if (warp == 0) {
-        // ------------------------------------------------------------ producer: bulk copies into the smem ring
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    if (warp >= TC_PROD_WARP0 && warp < TC_MMA_WARP) {
+        // ------------------------------------------------------------ producers: bulk copies into the smem ring
+        // Warp w fills stage w only (fills w, w + STAGES, ...), so four independent barrier / issue latency chains
+        // overlap.  Control flow is warp-uniform; one elected lane issues the copies.
+        const int stage = warp - TC_PROD_WARP0;
+        const int n_units_p = p.n_rb * p.n_cg * p.q_chunks;
+        const size_t q_stride = static_cast<size_t>(p.n_cg) * p.n_kt * C::TILE_B;  // bytes between slots of one group
+        uint8_t* const dstA = sA + stage * C::TPS * TC_TILE_A;
+        uint8_t* const dstB = sB + stage * C::TPS * C::TILE_B;
+        uint32_t round = 0;
+        int skip = stage;  // fills of the shared sequence that belong to other stages before my next one
+        for (int u = blockIdx.x; u < n_units_p; u += gridDim.x) {
             const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
             const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
             const int t0 = p.tile_ptr[rb], nk = p.tile_ptr[rb + 1] - t0;
-            __syncwarp();
-            for (int i = lane; i < min(nk, TC_KT_CAP); i += 32) s_kt[i] = p.tile_kt[t0 + i];
-            __syncwarp();
-            if (lane == 0) {
-                for (int q = q0; q < q1; ++q) {
-                    const int8_t* bslot = p.bcat + (static_cast<size_t>(q % p.q_wrap) * p.n_cg + cg) *
-                                                       static_cast<size_t>(p.n_kt) * C::TILE_B;
-                    for (int i = 0; i < nk; ++i) {
-                        const int kt = i < TC_KT_CAP ? s_kt[i] : p.tile_kt[t0 + i];
-                        mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], C::STAGE);
-                        bulk_g2s(sA + stage * TC_TILE_A, p.a_tiles + static_cast<size_t>(t0 + i) * TC_TILE_A,
-                                 TC_TILE_A, &full[stage]);
-                        bulk_g2s(sB + stage * C::TILE_B, bslot + static_cast<size_t>(kt) * C::TILE_B, C::TILE_B,
-                                 &full[stage]);
-                        if (++stage == C::STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0,
-                                                /*b MN*/ 1);
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t acc_it = 0;  // accumulations issued so far: buffer = it & 1, barrier phase = (it >> 1) & 1
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                const int rb = u % p.n_rb, qc = (u / p.n_rb) / p.n_cg;
-                const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
-                const int nk = p.tile_ptr[rb + 1] - p.tile_ptr[rb];
-                for (int q = q0; q < q1; ++q) {
-                    const uint32_t buf = acc_it & 1u, tpar = (acc_it >> 1) & 1u;
-                    mbar_wait(&tempty[buf], tpar ^ 1);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tbase + buf * 256;
-                    for (int i = 0; i < nk; ++i) {
-                        mbar_wait(&full[stage], phase);
-                        tc_fence_after();
-                        const uint32_t a0 = smem_u32(sA + stage * TC_TILE_A);
-                        const uint32_t b0 = smem_u32(sB + stage * C::TILE_B);
+            const int nfills = (nk + C::TPS - 1) / C::TPS;
+            // k-tile ids of this row block live in registers, spread over the lanes (tile i -> lane i & 31,
+            // register i >> 5); row blocks with more than 128 tiles read the tail from global memory
+            int ktr[4];
 #pragma unroll
-                        for (int ks = 0; ks < TC_KT / 32; ++ks) {
-                            // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
-                            // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
-                            const uint64_t adesc = smem_desc_noswz(a0 + ks * 2 * 2048, p.a_lbo, p.a_sbo);
-                            const uint64_t bdesc = smem_desc_noswz(b0 + ks * 4 * (C::NCOLS * 8), p.b_lbo, p.b_sbo);
-                            mma_i8_ss(d_tmem, adesc, bdesc, idesc, (i | ks) != 0);
-                        }
-                        mma_commit(&empty[stage]);
-                        if (++stage == C::STAGES) {
-                            stage = 0;
-                            phase ^= 1;
-                        }
-                    }
-                    mma_commit(&tfull[buf]);
-                    ++acc_it;
+            for (int r = 0; r < 4; ++r) ktr[r] = (r * 32 + lane < nk) ? p.tile_kt[t0 + r * 32 + lane] : 0;
+            const int8_t* const a_unit = p.a_tiles + static_cast<size_t>(t0) * TC_TILE_A;
+            const int8_t* const b_unit = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
+            int q = q0, pr = skip;
+            while (true) {
+                while (pr >= nfills) {
+                    pr -= nfills;
+                    ++q;
                 }
+                if (q >= q1) break;
+                const int i0 = pr * C::TPS;
+                const int nt = min(C::TPS, nk - i0);
+                int kts[C::TPS];
+#pragma unroll
+                for (int t = 0; t < C::TPS; ++t) {
+                    const int i = i0 + t;
+                    const int sel = (i >> 5) == 0 ? ktr[0] : ((i >> 5) == 1 ? ktr[1] : ((i >> 5) == 2 ? ktr[2] : ktr[3]));
+                    kts[t] = __shfl_sync(0xffffffffu, sel, i & 31);
+                    if (i >= 128 && i < nk) kts[t] = p.tile_kt[t0 + i];
+                }
+                const int8_t* const b_q = b_unit + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
+                if (!(p.dbg & 64)) mbar_wait(&empty[stage], (round & 1u) ^ 1u);
+                if (elect_one()) {
+                    if (p.dbg & 2) {
+                        mbar_arrive(&full[stage]);
+                    } else {
+                        mbar_expect_tx(&full[stage], nt * C::TILE_AB);
+#pragma unroll
+                        for (int t = 0; t < C::TPS; ++t)
+                            if (t < nt) {
+                                bulk_g2s(dstA + t * TC_TILE_A, a_unit + static_cast<size_t>(i0 + t) * TC_TILE_A, TC_TILE_A,
+                                         &full[stage]);
+                                bulk_g2s(dstB + t * C::TILE_B, b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B,
+                                         &full[stage]);
+                            }
+                    }
+                }
+                __syncwarp();
+                ++round;
+                pr += TC_STAGES;
             }
+            // fills left over past the end of this unit are skipped at the start of the next one
+            skip = pr + (q - q1) * nfills;   // q == q1 here unless the unit was empty
+        }
+    } else if (warp == TC_MMA_WARP) {
+        // ------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
+        // The loop is unrolled over the stage index so that every smem descriptor is a compile-time offset from the
+        // (uniform) shared-memory base.
+        const uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0,
+                                        /*b MN*/ p.b_kmajor ? 0 : 1);
+        const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+        const uint64_t a_hi = (smem_desc_noswz(0, p.a_lbo, p.a_sbo) | (static_cast<uint64_t>(p.a_layout) << 61));
+        const uint64_t b_hi = (smem_desc_noswz(0, p.b_lbo, p.b_sbo) | (static_cast<uint64_t>(p.b_layout) << 61));
+        FillWalker fw(p, C::TPS);
+        uint32_t acc_it = 0;  // accumulations issued so far: buffer = it & 1, barrier phase = (it >> 1) & 1
+        uint32_t round = 0;
+        while (!fw.done) {
+#pragma unroll
+            for (int stage = 0; stage < TC_STAGES; ++stage) {
+                if (fw.done) break;
+                const uint32_t buf = acc_it & 1u;
+                if (fw.first_of_slot()) {
+                    mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                    tc_fence_after();
+                }
+                const int nt = fw.tiles_in_fill();
+                const bool first = fw.first_of_slot(), last = fw.last_of_slot();
+                if (!(p.dbg & 32)) mbar_wait(&full[stage], round & 1u);
+                if (!(p.dbg & 4)) tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tbase + buf * 256;
+                    if (!(p.dbg & 1)) {
+#pragma unroll
+                        for (int t = 0; t < C::TPS; ++t)
+                            if (t < nt) {
+#pragma unroll
+                                for (int ks = 0; ks < TC_KT / 32; ++ks) {
+                                    // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
+                                    // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
+                                    const uint32_t a_addr = sA0 + (stage * C::TPS + t) * TC_TILE_A + ks * p.a_kstep;
+                                    const uint32_t b_addr = sB0 + (stage * C::TPS + t) * C::TILE_B + ks * p.b_kstep;
+                                    const uint64_t adesc = a_hi | static_cast<uint64_t>((a_addr >> 4) & 0x3FFF);
+                                    const uint64_t bdesc = b_hi | static_cast<uint64_t>((b_addr >> 4) & 0x3FFF);
+                                    mma_i8_ss(d_tmem, adesc, bdesc, idesc, (!first) || (t | ks) != 0);
+                                }
+                            }
+                    }
+                    if (p.dbg & 8)
+                        mbar_arrive(&empty[stage]);
+                    else
+                        mma_commit(&empty[stage]);
+                    if (last) mma_commit(&tfull[buf]);
+                }
+                __syncwarp();
+                if (fw.next()) ++acc_it;
+            }
+            ++round;
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
-        const int quarter = warp & 3;            // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;        // which 32 of the slot's 64 (permutation, attribute) columns
+        const int quarter = warp & 3;                       // TMEM lane quarter this warp may read
+        const int half = warp >> 2;                         // which 32 of the slot's 64 columns
         const int row_in_tile = quarter * 32 + lane;
         const int c0 = half * 32;
         uint32_t acc_it = 0;
@@ -197,14 +304,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             uint32_t cnt[32];
             if (KIND == TCK_COUNT) {
                 band = row_ok ? static_cast<int>(p.row_ptr[row + 1] - p.row_ptr[row]) : 0;
-#pragma unroll 4
-                for (int cc = 0; cc < 32; ++cc) {
-                    const int c = c0 + cc;
-                    const int64_t j = SMALL_M ? (c & (p.mpad - 1)) : jbase + c;
-                    if (p.inexact[j]) inexact_mask |= 1u << cc;
-                    // thread-private copy of the observed fixed-point score, split as S0 = hi * 256 + lo
-                    const long long s0 = p.s0fix[row * p.mpad + j];
-                    s0s[c * TC_ROWS + row_in_tile] = make_int2(static_cast<int>(s0 >> 8), static_cast<int>(s0 & 255));
+                // thread-private copy of the observed fixed-point scores, split as S0 = hi * 256 + lo
+#pragma unroll 2
+                for (int g = 0; g < 8; ++g) {
+                    uint32_t lo4 = 0;
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int cc = g * 4 + x, c = c0 + cc;
+                        const int64_t j = SMALL_M ? (c & (p.mpad - 1)) : jbase + c;
+                        if (p.inexact[j]) inexact_mask |= 1u << cc;
+                        const long long s0 = p.s0fix[row * p.mpad + j];
+                        s_hi[c * TC_ROWS + row_in_tile] = static_cast<int>(s0 >> 8);
+                        lo4 |= static_cast<uint32_t>(s0 & 255) << (8 * x);
+                    }
+                    s_lo[((c0 >> 2) + g) * TC_ROWS + row_in_tile] = lo4;
                 }
 #pragma unroll
                 for (int cc = 0; cc < 32; ++cc) cnt[cc] = 0;
@@ -248,10 +361,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             if (D > 1) hi += static_cast<int32_t>(acc[1][x]);
                             if (D > 2) hi += static_cast<int32_t>(acc[D - 1][x]) << 8;
                             const int lo = a0 & 255;
-                            const int2 o = s0s[c * TC_ROWS + row_in_tile];
-                            int dh = hi - o.x;
+                            const int o_hi = s_hi[c * TC_ROWS + row_in_tile];
+                            const int o_lo = (s_lo[(c >> 2) * TC_ROWS + row_in_tile] >> (8 * (c & 3))) & 255;
+                            int dh = hi - o_hi;
                             dh = max(min(dh, 1 << 22), -(1 << 22));  // keeps sign and |diff| >> band, avoids overflow
-                            const int diff = dh * 256 + (lo - o.y);
+                            const int diff = dh * 256 + (lo - o_lo);
                             uint32_t add;
                             if (all_exact) {
                                 add = (diff >= 0 ? 0x10000u : 0u) + (diff <= 0 ? 1u : 0u);
@@ -324,7 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tbase, 512);
+    if (warp == TC_MMA_WARP) tmem_dealloc(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ operand builders
@@ -536,14 +650,9 @@ struct TcPlan {
     DevBuf<int8_t> digits;
     DevBuf<uint8_t> inexact;
     DevBuf<int64_t> s0fix;
-    DevBuf<int8_t> bcat;
-    DevBuf<uint64_t> flag_ij;
-    DevBuf<uint32_t> flag_p;
     DevBuf<unsigned int> flag_count;
-    DevBuf<uint32_t> cpk;
-    int64_t cpk_perms = 0;  // permutations accumulated in cpk since the last unpack (16-bit fields)
+    int64_t cpk_perms = 0;  // permutations accumulated in the packed counters since the last unpack (16-bit fields)
     unsigned int flag_cap = 0;
-    int64_t slots_cap = 0;
 };
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
@@ -588,7 +697,7 @@ static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, in
     KernelTimer kt(ctx, SB_K_GATHER);
 #define SB_G(DD)                                                                                              \
     k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->n, pl->mpad, pl->n_kt, pl->n_cg, pl->pps, \
-                                                pl->log2_mpad, batch_perms, pl->bcat.p)
+                                                pl->log2_mpad, batch_perms, ctx->ws_bcat.p)
     if (pl->D == 1)
         SB_G(1);
     else if (pl->D == 2)
@@ -600,11 +709,12 @@ static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, in
 }
 
 static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
+    sb_ctx* ctx = e->ctx;
     GemmParams gp{};
     gp.a_tiles = pl->a_tiles.p;
     gp.tile_ptr = pl->tile_ptr.p;
     gp.tile_kt = pl->tile_kt.p;
-    gp.bcat = pl->bcat.p;
+    gp.bcat = ctx->ws_bcat.p;
     gp.n_kt = pl->n_kt;
     gp.n_rb = pl->n_rb;
     gp.n_cg = pl->n_cg;
@@ -616,17 +726,19 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.s0fix = pl->s0fix.p;
     gp.row_ptr = e->row_ptr.p;
     gp.inexact = pl->inexact.p;
-    gp.flag_ij = pl->flag_ij.p;
-    gp.flag_p = pl->flag_p.p;
+    gp.flag_ij = ctx->ws_flag_ij.p;
+    gp.flag_p = ctx->ws_flag_p.p;
     gp.flag_count = pl->flag_count.p;
     gp.flag_cap = pl->flag_cap;
-    gp.cpk = pl->cpk.p;
+    gp.cpk = ctx->ws_cpk.p;
     const uint32_t ncols = 64u * pl->D;
     gp.a_lbo = 2048;       // K-major A: stride between the two 16-byte K chunks of one MMA
     gp.a_sbo = 128;        //            stride between 8-row groups
     gp.b_lbo = ncols * 8;  // MN-major B: stride between 8-row K groups
     gp.b_sbo = 128;        //             stride between 16-column chunks
     gp.q_wrap = INT_MAX;
+    gp.a_kstep = 2 * 2048;
+    gp.b_kstep = 4 * ncols * 8;
     return gp;
 }
 
@@ -780,19 +892,17 @@ static TcPlan* build_plan(sb_enrich* e) {
         // ---- flag list (capacity >= one slot's worst case so that overflow recovery always terminates)
         const int64_t worst_slot = static_cast<int64_t>(pl->n_rb) * TC_ROWS * 64 * (pl->mpad >= 64 ? pl->n_cg : 1);
         pl->flag_cap = static_cast<unsigned int>(std::min<int64_t>(std::max<int64_t>(4ll << 20, worst_slot), 1ll << 31));
-        pl->flag_ij.reserve(pl->flag_cap);
-        pl->flag_p.reserve(pl->flag_cap);
+        ctx->ws_flag_ij.reserve(pl->flag_cap);
+        ctx->ws_flag_p.reserve(pl->flag_cap);
         pl->flag_count.reserve(1);
-        pl->cpk.reserve(static_cast<size_t>(n) * m);
-        SB_CUDA(cudaMemsetAsync(pl->cpk.p, 0, static_cast<size_t>(n) * m * sizeof(uint32_t), st));
+        ctx->ws_cpk.reserve(static_cast<size_t>(n) * m);
 
         delete tr;
         tr = new PhaseTrace(ctx, "tc.plan.s0fix");
         // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
         const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
         const int64_t slots1 = slots_for(pl, 1);
-        pl->bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
-        pl->slots_cap = slots1;
+        ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
         pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_ROWS * pl->mpad);
         launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1);
         GemmParams gp = base_params(e, pl);
@@ -842,7 +952,7 @@ static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpo
     sb_ctx* ctx = e->ctx;
     const int64_t cells = e->n * e->m;
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(cells, 256), ctx->num_sms * 16));
-    k_unpack_counts<<<blocks, 256, 0, ctx->stream>>>(pl->cpk.p, cells, cneg, cpos);
+    k_unpack_counts<<<blocks, 256, 0, ctx->stream>>>(ctx->ws_cpk.p, cells, cneg, cpos);
     SB_LAUNCH_CHECK(ctx);
     pl->cpk_perms = 0;
 }
@@ -868,17 +978,21 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
-    const size_t budget = std::min<size_t>(std::max<size_t>(free_b / 8, slot_bytes * slots_for(pl, 1)), 16ull << 30);
+    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(free_b / 8, slot_bytes * slots_for(pl, 1)), 16ull << 30),
+                                   ctx->ws_bcat.n);
     int64_t max_slots = std::max<int64_t>(slots_for(pl, 1), static_cast<int64_t>(budget / slot_bytes));
     max_slots = std::min<int64_t>(max_slots, 65535);
     int64_t pb = pl->mpad >= 64 ? max_slots / pl->n_cg : max_slots * pl->pps;
     pb = std::max<int64_t>(1, std::min<int64_t>(pb, 16384));  // 16-bit per-unit counters
     pb = std::min(pb, num_perm);
     const int64_t need_slots = slots_for(pl, pb);
-    if (need_slots > pl->slots_cap) {
-        pl->bcat.reserve(static_cast<size_t>(need_slots) * slot_bytes);
-        pl->slots_cap = need_slots;
-    }
+    ctx->ws_bcat.reserve(static_cast<size_t>(need_slots) * slot_bytes);
+    // the packed counters and the fix-up list live in context scratch: (re)claim them for this call
+    ctx->ws_flag_ij.reserve(pl->flag_cap);
+    ctx->ws_flag_p.reserve(pl->flag_cap);
+    ctx->ws_cpk.reserve(static_cast<size_t>(e->n) * e->m);
+    SB_CUDA(cudaMemsetAsync(ctx->ws_cpk.p, 0, static_cast<size_t>(e->n) * e->m * sizeof(uint32_t), st));
+    pl->cpk_perms = 0;
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
@@ -903,7 +1017,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         SB_CUDA(cudaStreamSynchronize(st));
         if (h_flags <= pl->flag_cap) {
             if (h_flags)
-                fixup_flags(e, perm, pl->flag_ij.p, pl->flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
+                fixup_flags(e, perm, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
             flagged += h_flags;
         } else {
             // The list overflowed: nothing of it is used.  Re-emit the flags slot by slot (one slot's worst case
@@ -913,7 +1027,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
                 SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
                 GemmParams gp = base_params(e, pl);
                 gp.mode = TCM_FLAG;
-                gp.bcat = pl->bcat.p + static_cast<size_t>(q) * pl->n_cg * slot_bytes;
+                gp.bcat = ctx->ws_bcat.p + static_cast<size_t>(q) * pl->n_cg * slot_bytes;
                 gp.q_total = 1;
                 gp.q_chunks = 1;
                 gp.q_per = 1;
@@ -923,7 +1037,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
                 launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms));
                 ktile_iters += tiles_per_pass;
                 const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
-                fixup_flags(e, perm_q, pl->flag_ij.p, pl->flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
+                fixup_flags(e, perm_q, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
                 unsigned int hq = 0;
                 SB_CUDA(cudaMemcpyAsync(&hq, pl->flag_count.p, sizeof hq, cudaMemcpyDeviceToHost, st));
                 SB_CUDA(cudaStreamSynchronize(st));
@@ -1008,6 +1122,8 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
     gp.b_sbo = 128;
     gp.q_wrap = INT_MAX;
+    gp.a_kstep = 2 * 2048;
+    gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
     if (variant & 1) std::swap(gp.a_lbo, gp.a_sbo);
     if (variant & 2) std::swap(gp.b_lbo, gp.b_sbo);
     launch_gemm_d(ctx, D, gp, 1);
@@ -1019,11 +1135,12 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
 
 // Streaming-rate probe: `grid` CTAs each run `slots` accumulations over the same `ktiles` L2-resident tile pairs
 // through the production pipeline (no HBM traffic after the first touch).  Returns the device time in ms.
-extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, double* ms_out) {
+extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, int dbg,
+                                    const uint32_t* desc_override /*NULL or 9 values*/, double* ms_out) {
     SB_API_BEGIN
     SB_CHECK(ctx && ms_out, "sb_selftest_mma_rate: NULL argument");
     SB_CHECK(ncols == 64 || ncols == 128 || ncols == 192, "sb_selftest_mma_rate: ncols must be 64, 128 or 192");
-    SB_CHECK(ktiles >= 1 && ktiles <= TC_KT_CAP && slots >= 1 && grid >= 1, "sb_selftest_mma_rate: bad sizes");
+    SB_CHECK(ktiles >= 1 && ktiles <= 4096 && slots >= 1 && grid >= 1, "sb_selftest_mma_rate: bad sizes");
     ctx->bind();
     const int D = ncols / 64;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
@@ -1057,6 +1174,7 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     gp.q_chunks = grid;
     gp.q_total = slots * grid;
     gp.q_wrap = 1;
+    gp.dbg = dbg;
     gp.mode = TCM_RAW;
     gp.n = TC_ROWS;
     gp.m = 64;
@@ -1068,6 +1186,19 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     gp.a_sbo = 128;
     gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
     gp.b_sbo = 128;
+    gp.a_kstep = 2 * 2048;
+    gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
+    if (desc_override) {  // speed-only experiments with other canonical layouts (results are not checked)
+        gp.a_layout = desc_override[0];
+        gp.a_lbo = desc_override[1];
+        gp.a_sbo = desc_override[2];
+        gp.a_kstep = desc_override[3];
+        gp.b_layout = desc_override[4];
+        gp.b_lbo = desc_override[5];
+        gp.b_sbo = desc_override[6];
+        gp.b_kstep = desc_override[7];
+        gp.b_kmajor = desc_override[8];
+    }
     cudaEvent_t e0, e1;
     SB_CUDA(cudaEventCreate(&e0));
     SB_CUDA(cudaEventCreate(&e1));

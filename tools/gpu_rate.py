@@ -1,5 +1,4 @@
-"""L2-hot streaming rate of the production GEMM pipeline (no HBM traffic): what one B200 sustains when every CTA
-streams k-tiles that are already L2-resident.  Separates the L2->SM / shared-memory ceiling from HBM effects."""
+"""L2-hot streaming-rate experiments on the production GEMM pipeline (speed only, see sb_selftest_mma_rate)."""
 import os
 import sys
 
@@ -8,13 +7,18 @@ sys.path.insert(0, ROOT)
 from safepy_b200 import _lib, get_context  # noqa: E402
 
 ctx = get_context()
-for grid in (1, 32, 148):
-    for ncols in (64, 128, 192):
-        ktiles, slots = 32, 64
-        ms = _lib.selftest_mma_rate(ctx, ncols, ktiles, slots, grid)
-        it = grid * slots * ktiles
-        ops = it * 2.0 * 128 * ncols * 64
-        byt = it * (8192 + 64 * ncols)
-        cyc = ms * 1e-3 * 1.965e9 / (slots * ktiles)
-        print("grid=%3d ncols=%3d: %.3f ms  %.0f int8 TOPS  %.2f TB/s smem fill  ~%.0f cycles/k-tile@1.965GHz (MMA floor %d)"
-              % (grid, ncols, ms, ops / ms / 1e9, byt / ms / 1e9, cyc, ncols), flush=True)
+
+
+def run(tag, ncols, grid, dbg=0, kt=32, slots=64):
+    ms = _lib.selftest_mma_rate(ctx, ncols, kt, slots, grid, dbg, None)
+    it = grid * slots * kt
+    ops = it * 2.0 * 128 * ncols * 64
+    cyc = ms * 1e-3 * 1.965e9
+    print("%-16s N=%3d grid=%3d ktiles=%4d slots=%4d: %.3f ms %5.0f TOPS  %6.0f cyc/slot  %5.0f cyc/k-tile"
+          % (tag, ncols, grid, kt, slots, ms, ops / ms / 1e9, cyc / slots, cyc / slots / kt), flush=True)
+
+
+for grid in (1, 148):
+    for n in (64, 128, 192):
+        for dbg, tag in ((0, "production"), (1, "copies only"), (2, "MMAs only"), (3, "barriers only")):
+            run(tag, n, grid, dbg, 32, 64)

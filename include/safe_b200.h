@@ -63,6 +63,9 @@ int sb_ctx_destroy(sb_ctx* ctx);
 /* run all subsequent work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int sb_ctx_set_stream(sb_ctx* ctx, void* cuda_stream);
 int sb_ctx_synchronize(sb_ctx* ctx);
+/* Device memory is taken from a cached, stream-ordered pool (freed blocks are kept for reuse).  This returns every
+ * cached block and the context's scratch buffers to the driver. */
+int sb_ctx_release_memory(sb_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t sb_ctx_launch_count(sb_ctx* ctx);
 /* Device-time accounting: with profiling on, launches are bracketed by CUDA events on the context's stream.

@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_ctx_destroy": (C.c_int, [_vp]),
     "sb_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "sb_ctx_synchronize": (C.c_int, [_vp]),
+    "sb_ctx_release_memory": (C.c_int, [_vp]),
     "sb_ctx_launch_count": (_i64, [_vp]),
     "sb_ctx_profile": (C.c_int, [_vp, C.c_int]),
     "sb_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(_i64)]),
@@ -122,6 +123,10 @@ class Context:
 
     def synchronize(self):
         _check(self.lib, self.lib.sb_ctx_synchronize(self.h))
+
+    def release_memory(self):
+        """Return the library's cached device memory (pool + scratch) to the driver."""
+        _check(self.lib, self.lib.sb_ctx_release_memory(self.h))
 
     @property
     def launch_count(self):

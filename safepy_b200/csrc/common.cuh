@@ -53,6 +53,14 @@ struct Error : std::runtime_error {
         return 2;                                    \
     }
 
+// Device allocations are stream-ordered and cached: cudaMallocAsync / cudaFreeAsync on the stream of the context
+// the calling thread bound last (sb_ctx::bind), from the device's default memory pool whose release threshold
+// sb_ctx_create raises to "keep everything".  A plan that is created and destroyed per call therefore costs no
+// cudaMalloc / cudaFree (both of which synchronise the device) after the first call.
+cudaStream_t& alloc_stream();  // thread-local
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+
 template <class T>
 struct DevBuf {
     T* p = nullptr;
@@ -62,15 +70,15 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) dev_free(p);
         p = nullptr;
         n = 0;
     }
-    // grow-only allocation
+    // grow-only allocation (contents are NOT preserved)
     void reserve(size_t count) {
         if (count <= n) return;
         release();
-        SB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        p = static_cast<T*>(dev_alloc(count * sizeof(T)));
         n = count;
     }
 };
@@ -94,7 +102,11 @@ struct sb_ctx {
     sb::DevBuf<uint64_t> ws_flag_ij;
     sb::DevBuf<uint32_t> ws_flag_p;
     sb::DevBuf<uint32_t> ws_cpk;
-    void bind() const { SB_CUDA(cudaSetDevice(device)); }
+    sb::DevBuf<unsigned int> ws_counter;
+    void bind() const {
+        SB_CUDA(cudaSetDevice(device));
+        sb::alloc_stream() = stream;
+    }
 };
 
 namespace sb {

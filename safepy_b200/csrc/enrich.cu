@@ -475,9 +475,8 @@ int sb_enrich_create(sb_ctx* ctx, sb_neigh* a, const void* b_host, int dtype, in
     sb_enrich* e = enrich_new(ctx, a, dtype, n, m);
     try {
         ctx->bind();
-        void* d = nullptr;
         const size_t bytes = static_cast<size_t>(n) * m * elem_size(dtype);
-        SB_CUDA(cudaMalloc(&d, bytes));
+        void* d = dev_alloc(bytes);
         e->b = d;
         e->b_owned = true;
         SB_CUDA(cudaMemcpyAsync(d, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
@@ -516,7 +515,7 @@ int sb_enrich_destroy(sb_enrich* e) {
         e->ctx->bind();
         PhaseTrace tr(e->ctx, "enrich.destroy");
         if (e->tc) tc_plan_destroy(e->tc);
-        if (e->b_owned && e->b) cudaFree(const_cast<void*>(e->b));
+        if (e->b_owned && e->b) dev_free(const_cast<void*>(e->b));
         delete e;
     }
     SB_API_END

@@ -28,28 +28,33 @@ namespace sb {
 constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
 constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
 constexpr int TC_TILE_A = TC_ROWS * TC_KT;
-constexpr int TC_STAGES = 4;            // smem ring depth; producer warp k owns stage k
-constexpr int TC_PROD_WARPS = TC_STAGES;
+constexpr int TC_STAGES = 4;             // smem ring depth
+constexpr int TC_TPS = 2;                // k-tiles per pipeline stage (tile lists are padded to a multiple of it)
 constexpr int TC_EPI_WARPS = 8;
-// The SM's warp arbiter favours high warp ids: the latency-critical single-warp roles (MMA issue, copy issue)
+// The SM's warp arbiter favours high warp ids: the latency-critical single-warp roles (copy issue, MMA issue)
 // therefore sit above the eight epilogue warps.
-constexpr int TC_PROD_WARP0 = TC_EPI_WARPS;
-constexpr int TC_MMA_WARP = TC_EPI_WARPS + TC_PROD_WARPS;
-constexpr int TC_THREADS = (TC_PROD_WARPS + 1 + TC_EPI_WARPS) * 32;
+constexpr int TC_PROD_WARP = TC_EPI_WARPS;
+constexpr int TC_MMA_WARP = TC_EPI_WARPS + 1;
+constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+constexpr int TC_SCHED = 4;              // depth of the work-unit ring (producer -> MMA / epilogue warps)
+constexpr int TC_KT_SMEM = 2048;         // k-tile ids of the current row block cached in smem (tail: global)
 
 enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
 
 struct GemmParams {
     const int8_t* a_tiles;
-    const int32_t* tile_ptr;  // [n_rb + 1]
+    const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
     const int8_t* bcat;       // [slot][kt][64 x 64*D]
     int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;
+    int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
+    unsigned int* unit_counter;  // dynamic scheduler (zeroed before the launch)
     int32_t mode;
     int64_t n, m, mpad;
     int32_t log2_mpad, pps, batch_perms;
     int64_t* s0fix;           // [n_rb * 128][mpad]
     const int64_t* row_ptr;   // band_i = row_ptr[i+1] - row_ptr[i]
+    const int32_t* node_of_row;  // internal row -> caller's node id (nullptr: identity)
     const uint8_t* inexact;   // [mpad]
     uint32_t* cpk;            // packed counts (pos << 16 | neg) per (node, attribute), one atomic per cell
     uint64_t* flag_ij;
@@ -59,12 +64,14 @@ struct GemmParams {
     int32_t* raw_out;         // TCM_RAW: [128][64*D]
     uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
     int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
-    int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies, bit2 = no tcgen05 fence after the
-                              // full-barrier wait, bit3 = plain arrive instead of tcgen05.commit on `empty`,
-                              // bit4 = one polling lane per epilogue warp
+    int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies
     uint32_t a_layout, b_layout;  // smem descriptor layout_type (0 = no swizzle; probe may try 2/4/6)
     uint32_t a_kstep, b_kstep;    // descriptor start-address advance per K=32 MMA
     uint32_t b_kmajor;            // probe only: 1 = declare B K-major in the instruction descriptor
+};
+
+struct UnitInfo {
+    int32_t rb, cg, q0, q1, t0, nfills, pad0, pad1;
 };
 
 template <int D>
@@ -72,65 +79,40 @@ struct TcCfg {
     static constexpr int NCOLS = 64 * D;
     static constexpr int TILE_B = TC_KT * NCOLS;
     static constexpr int TILE_AB = TC_TILE_A + TILE_B;
-    static constexpr int TPS = D == 1 ? 3 : 2;  // k-tiles per pipeline stage
+    static constexpr int TPS = TC_TPS;
     static constexpr int STAGE = TPS * TILE_AB;
     static constexpr int STAGES = TC_STAGES;
     static constexpr int OFF_B = STAGES * TPS * TC_TILE_A;
-    static constexpr int OFF_S0HI = STAGES * STAGE;         // int32 [64][128]
-    static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;   // uint32 [16][128], 4 columns per word
-    static constexpr int OFF_BAR = OFF_S0LO + 16 * TC_ROWS * 4;
+    static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
+    static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;    // uint32 [16][128], 4 columns per word
+    static constexpr int OFF_KT = OFF_S0LO + 16 * TC_ROWS * 4;      // int32 [TC_KT_SMEM]
+    static constexpr int OFF_UNIT = OFF_KT + TC_KT_SMEM * 4;        // UnitInfo [TC_SCHED]
+    static constexpr int OFF_BAR = OFF_UNIT + TC_SCHED * 32;
     static constexpr int SMEM = OFF_BAR + 256;
 };
 
-// Walks the (unit, slot q, stage fill) sequence every role of the kernel agrees on.  A "fill" is one pipeline
-// stage worth of k-tiles (up to TPS); fill number f always lands in stage f % TC_STAGES.
-struct FillWalker {
-    const GemmParams& p;
-    int tps;
-    int u, rb, cg, q, q1, t0, nk, nfills, pr;
-    bool done;
-    __device__ FillWalker(const GemmParams& pp, int tps_) : p(pp), tps(tps_), u(blockIdx.x), pr(0) {
-        done = true;
-        enter_unit();
-    }
-    __device__ void enter_unit() {
-        const int n_units = p.n_rb * p.n_cg * p.q_chunks;
-        done = u >= n_units;
-        if (done) return;
-        rb = u % p.n_rb;
-        const int rest = u / p.n_rb;
-        cg = rest % p.n_cg;
-        const int qc = rest / p.n_cg;
-        q = qc * p.q_per;
-        q1 = min(p.q_total, q + p.q_per);
-        t0 = p.tile_ptr[rb];
-        nk = p.tile_ptr[rb + 1] - t0;
-        nfills = (nk + tps - 1) / tps;
-        pr = 0;
-    }
-    __device__ bool first_of_slot() const { return pr == 0; }
-    __device__ bool last_of_slot() const { return pr == nfills - 1; }
-    __device__ int tiles_in_fill() const { return min(tps, nk - pr * tps); }
-    // advance by one fill; returns true when a slot (one accumulation) was completed
-    __device__ bool next() {
-        if (++pr < nfills) return false;
-        pr = 0;
-        if (++q >= q1) {
-            u += gridDim.x;
-            enter_unit();
-        }
-        return true;
-    }
-    __device__ void advance(int k) {
-        for (int i = 0; i < k && !done; ++i) next();
-    }
-};
+// Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
+// tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTAs that
+// fetch neighbouring unit numbers read the same gathered operand slab (q chunk, column group).
+__device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb, int& cg, int& q0, int& q1) {
+    const int per_full = p.band_rb * p.n_cg * p.q_chunks;
+    const int b = min(u / per_full, p.n_bands - 1);
+    const int r = u - b * per_full;
+    const int rows = min(p.band_rb, p.n_rb - b * p.band_rb);
+    rb = b * p.band_rb + r % rows;
+    const int rest = r / rows;
+    cg = rest % p.n_cg;
+    const int qc = rest / p.n_cg;
+    q0 = qc * p.q_per;
+    q1 = min(p.q_total, q0 + p.q_per);
+}
 
 // kernel flavours (compile-time, so the hot epilogue carries no mode tests)
 enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
 
-// Warp roles: 0..7 = epilogue, 8..11 = bulk-copy producers (warp 8 + k fills stage k, so the per-fill barrier /
-// issue latency chains of four warps overlap), 12 = MMA issuer (+ TMEM alloc).
+// Warp roles: 0..7 = epilogue, 8 = scheduler + bulk-copy producer, 9 = MMA issuer (+ TMEM alloc).
+// The producer warp draws work units from a global counter and publishes them through a small smem ring, so all
+// roles walk the same unit sequence.  Issue loops are warp-uniform with one elected lane issuing.
 // Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
 template <int D, int KIND, bool SMALL_M>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
@@ -140,12 +122,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     uint8_t* sB = smem + C::OFF_B;
     int32_t* s_hi = reinterpret_cast<int32_t*>(smem + C::OFF_S0HI);
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(smem + C::OFF_S0LO);
+    int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::OFF_KT);
+    UnitInfo* s_unit = reinterpret_cast<UnitInfo*>(smem + C::OFF_UNIT);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* full = bars;                        // [STAGES]
     uint64_t* empty = bars + C::STAGES;           // [STAGES]
     uint64_t* tfull = bars + 2 * C::STAGES;       // [2]
     uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * C::STAGES + 4);
+    uint64_t* sfull = bars + 2 * C::STAGES + 4;   // [TC_SCHED]
+    uint64_t* sempty = sfull + TC_SCHED;          // [TC_SCHED]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + TC_SCHED);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -158,6 +144,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             mbar_init(&tfull[b], 1);
             mbar_init(&tempty[b], TC_EPI_WARPS);
         }
+        for (int s = 0; s < TC_SCHED; ++s) {
+            mbar_init(&sfull[s], 1);
+            mbar_init(&sempty[s], TC_EPI_WARPS + 1);
+        }
         mbar_fence_init();
     }
     if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, 512);
@@ -168,123 +158,127 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
 
     const int n_units = p.n_rb * p.n_cg * p.q_chunks;
 
-    if (warp >= TC_PROD_WARP0 && warp < TC_MMA_WARP) {
-        // ------------------------------------------------------------ producers: bulk copies into the smem ring
-        // Warp w fills stage w only (fills w, w + STAGES, ...), so four independent barrier / issue latency chains
-        // overlap.  Control flow is warp-uniform; one elected lane issues the copies.
-        const int stage = warp - TC_PROD_WARP0;
-        const int n_units_p = p.n_rb * p.n_cg * p.q_chunks;
+    if (warp == TC_PROD_WARP) {
+        // ------------------------------------------------------------ scheduler + producer
         const size_t q_stride = static_cast<size_t>(p.n_cg) * p.n_kt * C::TILE_B;  // bytes between slots of one group
-        uint8_t* const dstA = sA + stage * C::TPS * TC_TILE_A;
-        uint8_t* const dstB = sB + stage * C::TPS * C::TILE_B;
-        uint32_t round = 0;
-        int skip = stage;  // fills of the shared sequence that belong to other stages before my next one
-        for (int u = blockIdx.x; u < n_units_p; u += gridDim.x) {
-            const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
-            const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
+        uint32_t stage = 0, phase = 0, uit = 0;
+        unsigned int next_u = 0;
+        if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);
+        next_u = __shfl_sync(0xffffffffu, next_u, 0);
+        while (true) {
+            const int u = static_cast<int>(next_u);
+            const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+            mbar_wait(&sempty[sl], spar ^ 1u);
+            if (u >= n_units || static_cast<int>(next_u) < 0) {
+                if (lane == 0) {
+                    s_unit[sl].rb = -1;
+                    mbar_arrive(&sfull[sl]);
+                }
+                break;
+            }
+            if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);  // consumed at the top of the next iteration
+            int rb, cg, q0, q1;
+            decode_unit(p, u, rb, cg, q0, q1);
             const int t0 = p.tile_ptr[rb], nk = p.tile_ptr[rb + 1] - t0;
-            const int nfills = (nk + C::TPS - 1) / C::TPS;
-            // k-tile ids of this row block live in registers, spread over the lanes (tile i -> lane i & 31,
-            // register i >> 5); row blocks with more than 128 tiles read the tail from global memory
-            int ktr[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) ktr[r] = (r * 32 + lane < nk) ? p.tile_kt[t0 + r * 32 + lane] : 0;
+            const int nfills = nk / C::TPS;
+            if (lane == 0) {
+                UnitInfo inf;
+                inf.rb = rb; inf.cg = cg; inf.q0 = q0; inf.q1 = q1; inf.t0 = t0; inf.nfills = nfills;
+                inf.pad0 = inf.pad1 = 0;
+                s_unit[sl] = inf;
+                mbar_arrive(&sfull[sl]);
+            }
+            for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
+            __syncwarp();
             const int8_t* const a_unit = p.a_tiles + static_cast<size_t>(t0) * TC_TILE_A;
-            const int8_t* const b_unit = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
-            int q = q0, pr = skip;
-            while (true) {
-                while (pr >= nfills) {
-                    pr -= nfills;
-                    ++q;
-                }
-                if (q >= q1) break;
-                const int i0 = pr * C::TPS;
-                const int nt = min(C::TPS, nk - i0);
-                int kts[C::TPS];
+            const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
+            for (int q = q0; q < q1; ++q) {
+                const int8_t* const b_q = b_cg + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
+                for (int f = 0; f < nfills; ++f) {
+                    int kts[C::TPS];
 #pragma unroll
-                for (int t = 0; t < C::TPS; ++t) {
-                    const int i = i0 + t;
-                    const int sel = (i >> 5) == 0 ? ktr[0] : ((i >> 5) == 1 ? ktr[1] : ((i >> 5) == 2 ? ktr[2] : ktr[3]));
-                    kts[t] = __shfl_sync(0xffffffffu, sel, i & 31);
-                    if (i >= 128 && i < nk) kts[t] = p.tile_kt[t0 + i];
-                }
-                const int8_t* const b_q = b_unit + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
-                if (!(p.dbg & 64)) mbar_wait(&empty[stage], (round & 1u) ^ 1u);
-                if (elect_one()) {
-                    if (p.dbg & 2) {
-                        mbar_arrive(&full[stage]);
-                    } else {
-                        mbar_expect_tx(&full[stage], nt * C::TILE_AB);
+                    for (int t = 0; t < C::TPS; ++t) {
+                        const int i = f * C::TPS + t;
+                        kts[t] = i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i];
+                    }
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    if (elect_one()) {
+                        if (p.dbg & 2) {
+                            mbar_arrive(&full[stage]);
+                        } else {
+                            mbar_expect_tx(&full[stage], C::TPS * C::TILE_AB);
+                            bulk_g2s(sA + stage * C::TPS * TC_TILE_A,
+                                     a_unit + static_cast<size_t>(f) * C::TPS * TC_TILE_A, C::TPS * TC_TILE_A,
+                                     &full[stage]);
 #pragma unroll
-                        for (int t = 0; t < C::TPS; ++t)
-                            if (t < nt) {
-                                bulk_g2s(dstA + t * TC_TILE_A, a_unit + static_cast<size_t>(i0 + t) * TC_TILE_A, TC_TILE_A,
-                                         &full[stage]);
-                                bulk_g2s(dstB + t * C::TILE_B, b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B,
-                                         &full[stage]);
-                            }
+                            for (int t = 0; t < C::TPS; ++t)
+                                bulk_g2s(sB + (stage * C::TPS + t) * C::TILE_B,
+                                         b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B, &full[stage]);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
                 }
-                __syncwarp();
-                ++round;
-                pr += TC_STAGES;
             }
-            // fills left over past the end of this unit are skipped at the start of the next one
-            skip = pr + (q - q1) * nfills;   // q == q1 here unless the unit was empty
+            next_u = __shfl_sync(0xffffffffu, next_u, 0);
+            ++uit;
         }
     } else if (warp == TC_MMA_WARP) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-        // The loop is unrolled over the stage index so that every smem descriptor is a compile-time offset from the
-        // (uniform) shared-memory base.
         const uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0,
                                         /*b MN*/ p.b_kmajor ? 0 : 1);
-        const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
-        const uint64_t a_hi = (smem_desc_noswz(0, p.a_lbo, p.a_sbo) | (static_cast<uint64_t>(p.a_layout) << 61));
-        const uint64_t b_hi = (smem_desc_noswz(0, p.b_lbo, p.b_sbo) | (static_cast<uint64_t>(p.b_layout) << 61));
-        FillWalker fw(p, C::TPS);
-        uint32_t acc_it = 0;  // accumulations issued so far: buffer = it & 1, barrier phase = (it >> 1) & 1
-        uint32_t round = 0;
-        while (!fw.done) {
-#pragma unroll
-            for (int stage = 0; stage < TC_STAGES; ++stage) {
-                if (fw.done) break;
+        const uint64_t a_desc0 = smem_desc_noswz(smem_u32(sA), p.a_lbo, p.a_sbo) |
+                                 (static_cast<uint64_t>(p.a_layout) << 61);
+        const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo) |
+                                 (static_cast<uint64_t>(p.b_layout) << 61);
+        const uint32_t a_ks = p.a_kstep >> 4, b_ks = p.b_kstep >> 4;
+        uint32_t stage = 0, phase = 0, acc_it = 0, uit = 0;
+        while (true) {
+            const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+            mbar_wait(&sfull[sl], spar);
+            const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, nfills = s_unit[sl].nfills;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sl]);
+            if (rb < 0) break;
+            for (int q = q0; q < q1; ++q) {
+                // accumulations issued so far: buffer = acc_it & 1, barrier phase = (acc_it >> 1) & 1
                 const uint32_t buf = acc_it & 1u;
-                if (fw.first_of_slot()) {
-                    mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tbase + buf * 256;
+                for (int f = 0; f < nfills; ++f) {
+                    mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                }
-                const int nt = fw.tiles_in_fill();
-                const bool first = fw.first_of_slot(), last = fw.last_of_slot();
-                if (!(p.dbg & 32)) mbar_wait(&full[stage], round & 1u);
-                if (!(p.dbg & 4)) tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t d_tmem = tbase + buf * 256;
-                    if (!(p.dbg & 1)) {
+                    if (elect_one()) {
+                        if (!(p.dbg & 1)) {
+                            // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
+                            // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
+                            const uint64_t a_st = a_desc0 + stage * (C::TPS * TC_TILE_A >> 4);
+                            const uint64_t b_st = b_desc0 + stage * (C::TPS * C::TILE_B >> 4);
 #pragma unroll
-                        for (int t = 0; t < C::TPS; ++t)
-                            if (t < nt) {
+                            for (int t = 0; t < C::TPS; ++t) {
 #pragma unroll
-                                for (int ks = 0; ks < TC_KT / 32; ++ks) {
-                                    // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
-                                    // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
-                                    const uint32_t a_addr = sA0 + (stage * C::TPS + t) * TC_TILE_A + ks * p.a_kstep;
-                                    const uint32_t b_addr = sB0 + (stage * C::TPS + t) * C::TILE_B + ks * p.b_kstep;
-                                    const uint64_t adesc = a_hi | static_cast<uint64_t>((a_addr >> 4) & 0x3FFF);
-                                    const uint64_t bdesc = b_hi | static_cast<uint64_t>((b_addr >> 4) & 0x3FFF);
-                                    mma_i8_ss(d_tmem, adesc, bdesc, idesc, (!first) || (t | ks) != 0);
-                                }
+                                for (int ks = 0; ks < TC_KT / 32; ++ks)
+                                    mma_i8_ss(d_tmem, a_st + (t * (TC_TILE_A >> 4) + ks * a_ks),
+                                              b_st + (t * (C::TILE_B >> 4) + ks * b_ks), idesc,
+                                              (f | t | ks) != 0);
                             }
-                    }
-                    if (p.dbg & 8)
-                        mbar_arrive(&empty[stage]);
-                    else
+                        }
                         mma_commit(&empty[stage]);
-                    if (last) mma_commit(&tfull[buf]);
+                        if (f == nfills - 1) mma_commit(&tfull[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
                 }
-                __syncwarp();
-                if (fw.next()) ++acc_it;
+                ++acc_it;
             }
-            ++round;
+            ++uit;
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
@@ -292,18 +286,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         const int half = warp >> 2;                         // which 32 of the slot's 64 columns
         const int row_in_tile = quarter * 32 + lane;
         const int c0 = half * 32;
-        uint32_t acc_it = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int rb = u % p.n_rb, rest = u / p.n_rb, cg = rest % p.n_cg, qc = rest / p.n_cg;
-            const int q0 = qc * p.q_per, q1 = min(p.q_total, q0 + p.q_per);
+        uint32_t acc_it = 0, uit = 0;
+        while (true) {
+            const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+            mbar_wait(&sfull[sl], spar);
+            const int rb = s_unit[sl].rb, cg = s_unit[sl].cg, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sl]);
+            ++uit;
+            if (rb < 0) break;
             const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + row_in_tile;
             const bool row_ok = row < p.n;
+            // counts, bands and fix-ups are addressed by the caller's node id
+            const int64_t node = (row_ok && p.node_of_row) ? p.node_of_row[row] : row;
             const int64_t jbase = SMALL_M ? 0 : static_cast<int64_t>(cg) * 64;
             int band = 0;
             uint32_t inexact_mask = 0;
             uint32_t cnt[32];
             if (KIND == TCK_COUNT) {
-                band = row_ok ? static_cast<int>(p.row_ptr[row + 1] - p.row_ptr[row]) : 0;
+                band = row_ok ? static_cast<int>(p.row_ptr[node + 1] - p.row_ptr[node]) : 0;
                 // thread-private copy of the observed fixed-point scores, split as S0 = hi * 256 + lo
 #pragma unroll 2
                 for (int g = 0; g < 8; ++g) {
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             if (j < p.m) {
                                 const unsigned int k = atomicAdd(p.flag_count, 1u);
                                 if (k < p.flag_cap) {
-                                    p.flag_ij[k] = (static_cast<uint64_t>(row) << 32) | static_cast<uint64_t>(j);
+                                    p.flag_ij[k] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(j);
                                     p.flag_p[k] = static_cast<uint32_t>(pl);
                                 }
                             }
@@ -424,13 +425,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
 #pragma unroll
                         for (int cc = 0; cc < 32; ++cc)
                             if (((c0 + cc) & (p.mpad - 1)) == j) v += cnt[cc];
-                        if (v) atomicAdd(&p.cpk[row * p.m + j], v);
+                        if (v) atomicAdd(&p.cpk[node * p.m + j], v);
                     }
                 } else {
 #pragma unroll
                     for (int cc = 0; cc < 32; ++cc) {
                         const int64_t j = jbase + c0 + cc;
-                        if (j < p.m && cnt[cc]) atomicAdd(&p.cpk[row * p.m + j], cnt[cc]);
+                        if (j < p.m && cnt[cc]) atomicAdd(&p.cpk[node * p.m + j], cnt[cc]);
                     }
                 }
             }
@@ -472,17 +473,21 @@ __global__ void __launch_bounds__(256) k_tile_occ(const uint32_t* __restrict__ w
     }
 }
 
-// tile_kt / tile_rb lists from the occupancy flags; one block per row block (serial chunks + block scan)
+// tile_kt / tile_rb lists from the occupancy flags; one block per row block (serial chunks + block scan).
+// Row blocks are padded to a multiple of TC_TPS tiles: padding entries get tile_rb = -1 (expanded as all-zero A
+// tiles, so they contribute nothing) and repeat the last valid k-tile id.
 __global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ occ, int32_t n_kt,
                                                    const int32_t* __restrict__ tile_ptr, int32_t* __restrict__ tile_kt,
                                                    int32_t* __restrict__ tile_rb) {
     const int rb = blockIdx.x;
     __shared__ int part[256];
+    __shared__ int s_last;
     const int chunk = (n_kt + 255) / 256;
     const int b = threadIdx.x * chunk, e = min(n_kt, b + chunk);
     int c = 0;
     for (int kt = b; kt < e; ++kt) c += occ[static_cast<size_t>(rb) * n_kt + kt];
     part[threadIdx.x] = c;
+    if (threadIdx.x == 0) s_last = 0;
     __syncthreads();
     for (int o = 1; o < 256; o <<= 1) {
         int v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
@@ -490,13 +495,23 @@ __global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ o
         part[threadIdx.x] += v;
         __syncthreads();
     }
-    int at = tile_ptr[rb] + (threadIdx.x ? part[threadIdx.x - 1] : 0);
+    const int t0 = tile_ptr[rb];
+    int at = t0 + (threadIdx.x ? part[threadIdx.x - 1] : 0);
+    int last = -1;
     for (int kt = b; kt < e; ++kt)
         if (occ[static_cast<size_t>(rb) * n_kt + kt]) {
             tile_kt[at] = kt;
             tile_rb[at] = rb;
             ++at;
+            last = kt;
         }
+    if (last >= 0) atomicMax(&s_last, last);
+    __syncthreads();
+    const int real = part[255], padded = tile_ptr[rb + 1] - t0;
+    for (int i = real + threadIdx.x; i < padded; i += blockDim.x) {
+        tile_kt[t0 + i] = s_last;
+        tile_rb[t0 + i] = -1;
+    }
 }
 
 // expand one 128 x 64 bit tile into int8 {0,1} in K-major core-matrix order:
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(256) k_expand_tiles(const uint32_t* __restrict
         const int kc = it >> 7, r = it & 127;
         const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + r;
         uint32_t bits = 0;
-        if (row < n) bits = (words[row * ld + 2 * kt + (kc >> 1)] >> ((kc & 1) * 16)) & 0xffffu;
+        if (rb >= 0 && row < n) bits = (words[row * ld + 2 * kt + (kc >> 1)] >> ((kc & 1) * 16)) & 0xffffu;
         uint32_t w[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -643,7 +658,8 @@ struct TcPlan {
     int D = 0;
     int64_t n = 0, m = 0, mpad = 0;
     int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
-    int64_t n_tiles = 0;
+    int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
+    int64_t n_tiles_real = 0;  // non-empty tiles
     bool usable = true;  // false: data contains +-inf -> SIMT engine
     DevBuf<int8_t> a_tiles;
     DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
@@ -680,7 +696,15 @@ static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams&
         small_m ? launch_gemm<D, TCK_COUNT, true>(ctx, gp, grid) : launch_gemm<D, TCK_COUNT, false>(ctx, gp, grid);
 }
 
-static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp, int grid) {
+static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid) {
+    GemmParams gp = gp_in;
+    if (gp.band_rb <= 0) {
+        gp.band_rb = gp.n_rb;
+        gp.n_bands = 1;
+    }
+    ctx->ws_counter.reserve(1);
+    gp.unit_counter = ctx->ws_counter.p;
+    SB_CUDA(cudaMemsetAsync(gp.unit_counter, 0, sizeof(unsigned int), ctx->stream));
     const int kind = (gp.mode & TCM_RAW) ? TCK_RAW : (gp.mode & TCM_STORE) ? TCK_STORE : TCK_COUNT;
     const bool small_m = gp.mpad < 64;
     if (D == 1)
@@ -796,11 +820,13 @@ static TcPlan* build_plan(sb_enrich* e) {
         std::vector<int32_t> h_cnt(pl->n_rb), h_ptr(pl->n_rb + 1);
         SB_CUDA(cudaMemcpyAsync(h_cnt.data(), rb_count.p, pl->n_rb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
-        int64_t run = 0;
+        int64_t run = 0, real = 0;
         for (int i = 0; i < pl->n_rb; ++i) {
             h_ptr[i] = static_cast<int32_t>(run);
-            run += h_cnt[i];
+            real += h_cnt[i];
+            run += sb_ceil_div(h_cnt[i], TC_TPS) * TC_TPS;
         }
+        pl->n_tiles_real = real;
         SB_CHECK(run < (1ll << 31), "too many non-empty neighborhood tiles (%lld)", (long long)run);
         h_ptr[pl->n_rb] = static_cast<int32_t>(run);
         pl->n_tiles = run;
@@ -929,23 +955,30 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
     gp.mode = mode;
     gp.q_total = q_total;
     gp.batch_perms = batch_perms;
+    // L2 blocking (see decode_unit).  A band of row blocks keeps its A tiles (<= ~32 MB) resident; the gathered
+    // operand slab that the band touches for one (q chunk, column group) is kept to <= ~16 MB, so the two or three
+    // slabs that the dynamically scheduled CTAs work on at any time stay in the 126 MB L2 together with the band.
+    const double tile_b = static_cast<double>(TC_KT) * 64 * pl->D;
+    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_TILE_A / pl->n_rb;
+    int band = static_cast<int>(std::max(1.0, (32 << 20) / a_per_rb));
+    band = std::max(band, std::min(pl->n_rb, ctx->num_sms));
+    band = std::min(band, static_cast<int>(pl->n_rb));
+    gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, band));
+    gp.band_rb = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.n_bands));
+    gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.band_rb));
+    const double touched = std::min(1.0, 3.0 * gp.band_rb * TC_ROWS / static_cast<double>(pl->n));
+    const double slab = pl->n_kt * tile_b * touched;
+    int q_per = static_cast<int>(std::max(1.0, std::min(16.0, (16 << 20) / slab)));
+    // enough units to keep every SM busy with a few units each
     const int base_units = pl->n_rb * pl->n_cg;
-    int q_chunks = 1;
-    if (base_units < 2 * ctx->num_sms) q_chunks = std::min<int>(q_total, sb_ceil_div(2 * ctx->num_sms, base_units));
-    int q_per = static_cast<int>(sb_ceil_div(q_total, q_chunks));
-    // L2 locality: the CTAs of one wave work on the same (column group, q range) for neighbouring row blocks, so
-    // the gathered operand slab of that range (n_kt tiles per slot, of which a wave touches the part near its
-    // rows) must stay L2-resident while the wave drifts through it.
-    {
-        const double slab = static_cast<double>(pl->n_kt) * TC_KT * 64 * pl->D;
-        const double touched = std::min(1.0, 3.0 * ctx->num_sms * TC_ROWS / static_cast<double>(pl->n));
-        const int q_l2 = std::max(1, static_cast<int>((48 << 20) / (slab * touched)));
-        q_per = std::min(q_per, q_l2);
-    }
+    const int want_chunks = static_cast<int>(sb_ceil_div(4 * ctx->num_sms, base_units));
+    q_per = std::min<int>(q_per, std::max<int>(1, q_total / std::max(1, want_chunks)));
+    q_per = std::max(1, std::min(q_per, q_total));
     gp.q_per = q_per;
     gp.q_chunks = static_cast<int32_t>(sb_ceil_div(q_total, gp.q_per));
-    const int units = base_units * gp.q_chunks;
-    launch_gemm_d(ctx, pl->D, gp, std::min(units, ctx->num_sms));
+    const int64_t units = static_cast<int64_t>(base_units) * gp.q_chunks;
+    SB_CHECK(units < (1ll << 31), "too many work units in one batch (%lld)", (long long)units);
+    launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms)));
 }
 
 static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpos) {
@@ -996,7 +1029,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
-    int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;
+    int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;  // includes padding tiles
     for (int64_t p0 = 0; p0 < num_perm; p0 += pb) {
         const int64_t np = std::min(pb, num_perm - p0);
         const int32_t* perm = perm_dev + p0 * e->n;
@@ -1049,7 +1082,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     flush_counts(e, pl, cneg, cpos);
     e->stats[0] = e->n * e->m * num_perm - flagged;
     e->stats[1] = flagged;
-    e->stats[2] = pl->n_tiles;
+    e->stats[2] = pl->n_tiles_real;
     e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
     e->stats[4] = pl->D;
     e->stats[5] = ktile_iters;
@@ -1072,7 +1105,8 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     const int K = ktiles * TC_KT;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
     // host-side tiling into the production layouts
-    std::vector<int8_t> at(static_cast<size_t>(ktiles) * TC_TILE_A), bt(static_cast<size_t>(ktiles) * tile_b);
+    const int kt_pad = static_cast<int>(sb_ceil_div(ktiles, TC_TPS) * TC_TPS);  // padding tiles of A are all zero
+    std::vector<int8_t> at(static_cast<size_t>(kt_pad) * TC_TILE_A, 0), bt(static_cast<size_t>(ktiles) * tile_b);
     for (int kt = 0; kt < ktiles; ++kt)
         for (int r = 0; r < TC_ROWS; ++r)
             for (int k = 0; k < TC_KT; ++k)
@@ -1084,20 +1118,20 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
             for (int c = 0; c < ncols; ++c)
                 bt[static_cast<size_t>(kt) * tile_b + (k >> 3) * (nc16 * 128) + (c >> 4) * 128 + (k & 7) * 16 + (c & 15)] =
                     b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
-    std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
-    for (int i = 0; i < ktiles; ++i) kts[i] = i;
+    std::vector<int32_t> ptr = {0, kt_pad}, kts(kt_pad);
+    for (int i = 0; i < kt_pad; ++i) kts[i] = std::min(i, ktiles - 1);
     DevBuf<int8_t> d_a, d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
     d_a.reserve(at.size());
     d_b.reserve(bt.size());
     d_ptr.reserve(2);
-    d_kt.reserve(ktiles);
+    d_kt.reserve(kt_pad);
     d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
     cudaStream_t st = ctx->stream;
     SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_b.p, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), ktiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), kt_pad * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemsetAsync(d_out.p, 0xff, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t), st));
     GemmParams gp{};
     gp.a_tiles = d_a.p;
@@ -1141,6 +1175,7 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     SB_CHECK(ctx && ms_out, "sb_selftest_mma_rate: NULL argument");
     SB_CHECK(ncols == 64 || ncols == 128 || ncols == 192, "sb_selftest_mma_rate: ncols must be 64, 128 or 192");
     SB_CHECK(ktiles >= 1 && ktiles <= 4096 && slots >= 1 && grid >= 1, "sb_selftest_mma_rate: bad sizes");
+    ktiles = static_cast<int>(sb_ceil_div(ktiles, TC_TPS) * TC_TPS);
     ctx->bind();
     const int D = ncols / 64;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;

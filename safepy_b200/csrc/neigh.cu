@@ -27,6 +27,22 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
     last_error() = buf;
 }
+cudaStream_t& alloc_stream() {
+    thread_local cudaStream_t s = nullptr;
+    return s;
+}
+void* dev_alloc(size_t bytes) {
+    void* p = nullptr;
+    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, alloc_stream());
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        fail("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return p;
+}
+void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, alloc_stream());
+}
 void fail(const char* fmt, ...) {
     char buf[1024];
     va_list ap;
@@ -245,6 +261,13 @@ int sb_ctx_create(int device, sb_ctx** out) {
     SB_CHECK(prop.major == 10, "sb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
              device, prop.major, prop.minor);
     SB_CUDA(cudaSetDevice(device));
+    {
+        // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        SB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     sb_ctx* c = new sb_ctx;
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
@@ -255,7 +278,28 @@ int sb_ctx_create(int device, sb_ctx** out) {
 
 int sb_ctx_destroy(sb_ctx* ctx) {
     SB_API_BEGIN
-    delete ctx;
+    if (ctx) {
+        ctx->bind();
+        cudaStreamSynchronize(ctx->stream);
+        delete ctx;
+    }
+    SB_API_END
+}
+
+int sb_ctx_release_memory(sb_ctx* ctx) {
+    SB_API_BEGIN
+    SB_CHECK(ctx, "sb_ctx_release_memory: ctx is NULL");
+    ctx->bind();
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->ws_bcat.release();
+    ctx->ws_flag_ij.release();
+    ctx->ws_flag_p.release();
+    ctx->ws_cpk.release();
+    ctx->ws_counter.release();
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaMemPool_t pool;
+    SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+    SB_CUDA(cudaMemPoolTrimTo(pool, 0));
     SB_API_END
 }
 
@@ -329,10 +373,11 @@ int sb_neigh_create(sb_ctx* ctx, int64_t n, sb_neigh** out) {
     a->ld = sb_ld_words(n);
     a->owned = true;
     size_t bytes = static_cast<size_t>(n) * a->ld * sizeof(uint32_t);
-    cudaError_t e = cudaMalloc(&a->words, bytes);
-    if (e != cudaSuccess) {
+    try {
+        a->words = static_cast<uint32_t*>(dev_alloc(bytes));
+    } catch (...) {
         delete a;
-        fail("sb_neigh_create: cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        throw;
     }
     SB_CUDA(cudaMemsetAsync(a->words, 0, bytes, ctx->stream));
     *out = a;
@@ -359,7 +404,7 @@ int sb_neigh_destroy(sb_neigh* a) {
     if (a) {
         if (a->owned && a->words) {
             a->ctx->bind();
-            cudaFree(a->words);
+            dev_free(a->words);
         }
         delete a;
     }

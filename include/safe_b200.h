@@ -149,13 +149,13 @@ int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev);
  * Runs one 128 x N x K int8 tcgen05 GEMM from host operands through the production tile layouts and returns the
  * int32 accumulators; used to pin descriptor / layout encodings against a CPU product. */
 int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int variant /*0 = production descriptors*/,
-                       const int8_t* a_host /*128 x 64*ktiles*/, const int8_t* b_host /*64*ktiles x ncols*/,
+                       const int8_t* a_host /*128 x 64*ktiles, 0/1*/, const int8_t* b_host /*64*ktiles x ncols*/,
                        int32_t* d_host /*128 x ncols*/);
 
 /* Streaming-rate probe of the same kernel: `grid` CTAs x `slots` accumulations over `ktiles` L2-resident tile pairs;
  * returns device milliseconds (bench / profiling only). */
 int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, int dbg /*1: no MMAs, 2: no copies*/,
-                         const uint32_t* desc_override /*NULL, or 9 descriptor fields for speed-only experiments*/,
+                         const uint32_t* desc_override /*NULL, or {b_lbo, b_sbo, b_kstep} for speed-only experiments*/,
                          double* ms_out);
 
 #ifdef __cplusplus

@@ -27,22 +27,32 @@ namespace sb {
 
 constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
 constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
-constexpr int TC_TILE_A = TC_ROWS * TC_KT;
-constexpr int TC_STAGES = 4;             // smem ring depth
-constexpr int TC_TPS = 2;                // k-tiles per pipeline stage (tile lists are padded to a multiple of it)
+constexpr int TC_STAGES = 3;             // smem ring depth (gathered-operand tiles), TC_TPS tiles per stage
+constexpr int TC_ASLOTS = 2;             // TMEM ring depth (expanded A tiles), TC_TPS tiles per slot
+constexpr int TC_TPS = 4;                // k-tiles per pipeline fill (tile lists are padded to a multiple of it):
+                                         // one fill = 8 MMAs = 768 tensor cycles at D = 3, which covers the
+                                         // ~550 cycles of barrier / issue latency every role spends per fill
 constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EXP_WARPS = 4;          // one per TMEM lane quarter
 // The SM's warp arbiter favours high warp ids: the latency-critical single-warp roles (copy issue, MMA issue)
-// therefore sit above the eight epilogue warps.
-constexpr int TC_PROD_WARP = TC_EPI_WARPS;
-constexpr int TC_MMA_WARP = TC_EPI_WARPS + 1;
-constexpr int TC_THREADS = (TC_EPI_WARPS + 2) * 32;
+// therefore sit above the epilogue and expander warps.
+constexpr int TC_EXP_WARP0 = TC_EPI_WARPS;
+constexpr int TC_PROD_WARP = TC_EPI_WARPS + TC_EXP_WARPS;
+constexpr int TC_MMA_WARP = TC_PROD_WARP + 1;
+constexpr int TC_THREADS = (TC_EPI_WARPS + TC_EXP_WARPS + 2) * 32;
+// TMEM columns: accumulator buffer b at [256 b, 256 b + 64 D); A slot s (TC_TPS tiles x 16 columns) in the gap
+// [256 s + 192, 256 s + 256)
+__host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return s * 256u + 192u; }
+static_assert(TC_TPS * 16 <= 64 && TC_ASLOTS == 2, "A slots must fit the two 64-column gaps of TMEM");
 constexpr int TC_SCHED = 4;              // depth of the work-unit ring (producer -> MMA / epilogue warps)
 constexpr int TC_KT_SMEM = 2048;         // k-tile ids of the current row block cached in smem (tail: global)
 
 enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
+// kernel flavours (compile-time, so the hot epilogue carries no mode tests)
+enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
 
 struct GemmParams {
-    const int8_t* a_tiles;
+    const uint64_t* a_bits;   // [n_tiles][128]: bit k of word r = A[row block row r][64 kt + k]
     const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
     const int8_t* bcat;       // [slot][kt][64 x 64*D]
@@ -62,13 +72,24 @@ struct GemmParams {
     unsigned int* flag_count;
     unsigned int flag_cap;
     int32_t* raw_out;         // TCM_RAW: [128][64*D]
-    uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+    uint32_t b_lbo, b_sbo;
     int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
     int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies
-    uint32_t a_layout, b_layout;  // smem descriptor layout_type (0 = no swizzle; probe may try 2/4/6)
-    uint32_t a_kstep, b_kstep;    // descriptor start-address advance per K=32 MMA
-    uint32_t b_kmajor;            // probe only: 1 = declare B K-major in the instruction descriptor
+    uint32_t b_kstep;         // descriptor start-address advance per K=32 MMA
+    long long* prof;          // per-role cycle counters [16] (see print_prof), or nullptr
 };
+
+// cycle accounting per role, enabled by a non-null GemmParams::prof (SB_TRACE runs and the rate probe)
+#define TC_TIMED(KINDV, acc, stmt)            \
+    do {                                      \
+        if (p.prof) {                         \
+            const long long _t0 = clock64();  \
+            stmt;                             \
+            (acc) += clock64() - _t0;         \
+        } else {                              \
+            stmt;                             \
+        }                                     \
+    } while (0)
 
 struct UnitInfo {
     int32_t rb, cg, q0, q1, t0, nfills, pad0, pad1;
@@ -78,18 +99,26 @@ template <int D>
 struct TcCfg {
     static constexpr int NCOLS = 64 * D;
     static constexpr int TILE_B = TC_KT * NCOLS;
-    static constexpr int TILE_AB = TC_TILE_A + TILE_B;
     static constexpr int TPS = TC_TPS;
-    static constexpr int STAGE = TPS * TILE_AB;
+    static constexpr int STAGE = TPS * TILE_B;
     static constexpr int STAGES = TC_STAGES;
-    static constexpr int OFF_B = STAGES * TPS * TC_TILE_A;
     static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
     static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;    // uint32 [16][128], 4 columns per word
     static constexpr int OFF_KT = OFF_S0LO + 16 * TC_ROWS * 4;      // int32 [TC_KT_SMEM]
     static constexpr int OFF_UNIT = OFF_KT + TC_KT_SMEM * 4;        // UnitInfo [TC_SCHED]
     static constexpr int OFF_BAR = OFF_UNIT + TC_SCHED * 32;
-    static constexpr int SMEM = OFF_BAR + 256;
+    static constexpr int SMEM = OFF_BAR + 512;  // 32 mbarriers + the TMEM base address
 };
+
+// 64 membership bits -> 16 TMEM words of four 0/1 bytes (K elements 4c .. 4c+3 of a row sit in 32-bit column c)
+__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t (&r)[16]) {
+    const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        r[c] = (((lo >> (4 * c)) & 0xfu) * 0x00204081u) & 0x01010101u;
+        r[8 + c] = (((hi >> (4 * c)) & 0xfu) * 0x00204081u) & 0x01010101u;
+    }
+}
 
 // Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
 // tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTAs that
@@ -107,19 +136,18 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb,
     q1 = min(p.q_total, q0 + p.q_per);
 }
 
-// kernel flavours (compile-time, so the hot epilogue carries no mode tests)
-enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
-
-// Warp roles: 0..7 = epilogue, 8 = scheduler + bulk-copy producer, 9 = MMA issuer (+ TMEM alloc).
-// The producer warp draws work units from a global counter and publishes them through a small smem ring, so all
-// roles walk the same unit sequence.  Issue loops are warp-uniform with one elected lane issuing.
+// Warp roles: 0..7 = epilogue, 8..11 = A expanders, 12 = scheduler + bulk-copy producer, 13 = MMA issuer (+ TMEM
+// alloc).  The producer warp draws work units from a global counter and publishes them through a small smem ring,
+// so all roles walk the same unit sequence.  Issue loops are warp-uniform with one elected lane issuing.
+// A never touches shared memory: expander warp w holds rows 32 w .. 32 w + 31 of the row block, reads the 64
+// membership bits of its row for a k-tile (8 bytes), expands them to int8 0/1 in registers and stores them into a
+// TMEM slot, from where tcgen05.mma takes its A operand.  Only the gathered operand travels through smem.
 // Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
 template <int D, int KIND, bool SMALL_M>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + C::OFF_B;
+    uint8_t* sB = smem;
     int32_t* s_hi = reinterpret_cast<int32_t*>(smem + C::OFF_S0HI);
     uint32_t* s_lo = reinterpret_cast<uint32_t*>(smem + C::OFF_S0LO);
     int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::OFF_KT);
@@ -131,7 +159,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]
     uint64_t* sfull = bars + 2 * C::STAGES + 4;   // [TC_SCHED]
     uint64_t* sempty = sfull + TC_SCHED;          // [TC_SCHED]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + TC_SCHED);
+    uint64_t* afull = sempty + TC_SCHED;          // [TC_ASLOTS]
+    uint64_t* aempty = afull + TC_ASLOTS;         // [TC_ASLOTS]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + TC_ASLOTS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -146,7 +176,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         }
         for (int s = 0; s < TC_SCHED; ++s) {
             mbar_init(&sfull[s], 1);
-            mbar_init(&sempty[s], TC_EPI_WARPS + 1);
+            mbar_init(&sempty[s], TC_EPI_WARPS + TC_EXP_WARPS + 1);
+        }
+        for (int s = 0; s < TC_ASLOTS; ++s) {
+            mbar_init(&afull[s], TC_EXP_WARPS);
+            mbar_init(&aempty[s], 1);
         }
         mbar_fence_init();
     }
@@ -162,6 +196,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         // ------------------------------------------------------------ scheduler + producer
         const size_t q_stride = static_cast<size_t>(p.n_cg) * p.n_kt * C::TILE_B;  // bytes between slots of one group
         uint32_t stage = 0, phase = 0, uit = 0;
+        long long pt_wait = 0, pt_fills = 0;
+        const long long pt_start = clock64();
         unsigned int next_u = 0;
         if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);
         next_u = __shfl_sync(0xffffffffu, next_u, 0);
@@ -190,7 +226,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             }
             for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
             __syncwarp();
-            const int8_t* const a_unit = p.a_tiles + static_cast<size_t>(t0) * TC_TILE_A;
             const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
             for (int q = q0; q < q1; ++q) {
                 const int8_t* const b_q = b_cg + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
@@ -201,15 +236,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                         const int i = f * C::TPS + t;
                         kts[t] = i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i];
                     }
-                    mbar_wait(&empty[stage], phase ^ 1u);
+                    TC_TIMED(KIND, pt_wait, mbar_wait(&empty[stage], phase ^ 1u));
+                    ++pt_fills;
                     if (elect_one()) {
                         if (p.dbg & 2) {
                             mbar_arrive(&full[stage]);
                         } else {
-                            mbar_expect_tx(&full[stage], C::TPS * C::TILE_AB);
-                            bulk_g2s(sA + stage * C::TPS * TC_TILE_A,
-                                     a_unit + static_cast<size_t>(f) * C::TPS * TC_TILE_A, C::TPS * TC_TILE_A,
-                                     &full[stage]);
+                            mbar_expect_tx(&full[stage], C::STAGE);
 #pragma unroll
                             for (int t = 0; t < C::TPS; ++t)
                                 bulk_g2s(sB + (stage * C::TPS + t) * C::TILE_B,
@@ -226,16 +259,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             next_u = __shfl_sync(0xffffffffu, next_u, 0);
             ++uit;
         }
+        if (p.prof && lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 0), clock64() - pt_start);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 1), pt_wait);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), pt_fills);
+        }
+    } else if (warp >= TC_EXP_WARP0 && warp < TC_PROD_WARP) {
+        // ------------------------------------------------------------ A expanders: bits -> int8 0/1 in TMEM
+        const int quarter = warp - TC_EXP_WARP0;
+        const int r = quarter * 32 + lane;
+        const uint32_t t_lane = tbase + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t aslot = 0, aphase = 0, uit = 0;
+        long long xt_wait = 0, xt_st = 0;
+        const long long xt_start = clock64();
+        while (true) {
+            const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+            mbar_wait(&sfull[sl], spar);
+            const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, t0 = s_unit[sl].t0,
+                      nfills = s_unit[sl].nfills;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sempty[sl]);
+            ++uit;
+            if (rb < 0) break;
+            const uint64_t* const abase = p.a_bits + static_cast<size_t>(t0) * TC_ROWS + r;
+            // the same tile list is expanded once per slot; the bits of the next fill are loaded one fill ahead
+            uint64_t w[C::TPS];
+#pragma unroll
+            for (int t = 0; t < C::TPS; ++t) w[t] = abase[t * TC_ROWS];
+            for (int q = q0; q < q1; ++q) {
+                for (int f = 0; f < nfills; ++f) {
+                    const int fn = (f + 1 == nfills) ? 0 : f + 1;
+                    uint64_t nx[C::TPS];
+#pragma unroll
+                    for (int t = 0; t < C::TPS; ++t)
+                        nx[t] = abase[(static_cast<size_t>(fn) * C::TPS + t) * TC_ROWS];
+                    TC_TIMED(KIND, xt_wait, mbar_wait(&aempty[aslot], aphase ^ 1u));
+                    tc_fence_after();
+                    const uint32_t ta = t_lane + tc_acol(aslot);
+                    const long long st0 = p.prof ? clock64() : 0;
+#pragma unroll
+                    for (int t = 0; t < C::TPS; ++t) {
+                        uint32_t e[16];
+                        expand_bits(w[t], e);
+                        tmem_st16(ta + t * 16, e);
+                    }
+                    tmem_st_wait();
+                    if (p.prof) xt_st += clock64() - st0;
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&afull[aslot]);
+                    if (++aslot == TC_ASLOTS) {
+                        aslot = 0;
+                        aphase ^= 1u;
+                    }
+#pragma unroll
+                    for (int t = 0; t < C::TPS; ++t) w[t] = nx[t];
+                }
+            }
+        }
+        if (p.prof && warp == TC_EXP_WARP0 && lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 2), clock64() - xt_start);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 3), xt_wait);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 11), xt_st);
+        }
     } else if (warp == TC_MMA_WARP) {
         // ------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-        const uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0,
-                                        /*b MN*/ p.b_kmajor ? 0 : 1);
-        const uint64_t a_desc0 = smem_desc_noswz(smem_u32(sA), p.a_lbo, p.a_sbo) |
-                                 (static_cast<uint64_t>(p.a_layout) << 61);
-        const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo) |
-                                 (static_cast<uint64_t>(p.b_layout) << 61);
-        const uint32_t a_ks = p.a_kstep >> 4, b_ks = p.b_kstep >> 4;
-        uint32_t stage = 0, phase = 0, acc_it = 0, uit = 0;
+        const uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0, /*b MN*/ 1);
+        const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo);
+        const uint32_t b_ks = p.b_kstep >> 4;
+        uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc_it = 0, uit = 0;
+        long long mt_wa = 0, mt_wb = 0, mt_wt = 0;
+        const long long mt_start = clock64();
         while (true) {
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
             mbar_wait(&sfull[sl], spar);
@@ -246,28 +340,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             for (int q = q0; q < q1; ++q) {
                 // accumulations issued so far: buffer = acc_it & 1, barrier phase = (acc_it >> 1) & 1
                 const uint32_t buf = acc_it & 1u;
-                mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u);
-                tc_fence_after();
+                TC_TIMED(KIND, mt_wt, mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u));
                 const uint32_t d_tmem = tbase + buf * 256;
                 for (int f = 0; f < nfills; ++f) {
-                    mbar_wait(&full[stage], phase);
+                    TC_TIMED(KIND, mt_wa, mbar_wait(&afull[aslot], aphase));
+                    TC_TIMED(KIND, mt_wb, mbar_wait(&full[stage], phase));
                     tc_fence_after();
                     if (elect_one()) {
                         if (!(p.dbg & 1)) {
-                            // A: K-major, two 16-byte K chunks per MMA (chunk stride 2048 B)
-                            // B: MN-major, four 8-row K groups per MMA (group stride NCOLS*8 B)
-                            const uint64_t a_st = a_desc0 + stage * (C::TPS * TC_TILE_A >> 4);
-                            const uint64_t b_st = b_desc0 + stage * (C::TPS * C::TILE_B >> 4);
+                            // A: TMEM slot, 8 columns per K=32 MMA.  B: MN-major smem, four 8-row K groups per MMA
+                            const uint32_t a_t = tbase + tc_acol(aslot);
+                            const uint64_t b_st = b_desc0 + stage * (C::STAGE >> 4);
 #pragma unroll
                             for (int t = 0; t < C::TPS; ++t) {
 #pragma unroll
                                 for (int ks = 0; ks < TC_KT / 32; ++ks)
-                                    mma_i8_ss(d_tmem, a_st + (t * (TC_TILE_A >> 4) + ks * a_ks),
-                                              b_st + (t * (C::TILE_B >> 4) + ks * b_ks), idesc,
-                                              (f | t | ks) != 0);
+                                    mma_i8_ts(d_tmem, a_t + t * 16 + ks * 8,
+                                              b_st + (t * (C::TILE_B >> 4) + ks * b_ks), idesc, (f | t | ks) != 0);
                             }
                         }
                         mma_commit(&empty[stage]);
+                        mma_commit(&aempty[aslot]);
                         if (f == nfills - 1) mma_commit(&tfull[buf]);
                     }
                     __syncwarp();
@@ -275,10 +368,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                         stage = 0;
                         phase ^= 1u;
                     }
+                    if (++aslot == TC_ASLOTS) {
+                        aslot = 0;
+                        aphase ^= 1u;
+                    }
                 }
                 ++acc_it;
             }
             ++uit;
+        }
+        if (p.prof && lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 4), clock64() - mt_start);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 5), mt_wa);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 6), mt_wb);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 7), mt_wt);
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
@@ -287,6 +390,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         const int row_in_tile = quarter * 32 + lane;
         const int c0 = half * 32;
         uint32_t acc_it = 0, uit = 0;
+        long long et_wait = 0;
+        const long long et_start = clock64();
         while (true) {
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
             mbar_wait(&sfull[sl], spar);
@@ -300,11 +405,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             // counts, bands and fix-ups are addressed by the caller's node id
             const int64_t node = (row_ok && p.node_of_row) ? p.node_of_row[row] : row;
             const int64_t jbase = SMALL_M ? 0 : static_cast<int64_t>(cg) * 64;
-            int band = 0;
+            int band = 0, bh = 1;
             uint32_t inexact_mask = 0;
             uint32_t cnt[32];
             if (KIND == TCK_COUNT) {
                 band = row_ok ? static_cast<int>(p.row_ptr[node + 1] - p.row_ptr[node]) : 0;
+                bh = (band + 255) / 256 + 1;
                 // thread-private copy of the observed fixed-point scores, split as S0 = hi * 256 + lo
 #pragma unroll 2
                 for (int g = 0; g < 8; ++g) {
@@ -329,19 +435,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
 
             for (int q = q0; q < q1; ++q) {
                 const uint32_t buf = acc_it & 1u, tpar = (acc_it >> 1) & 1u;
-                mbar_wait(&tfull[buf], tpar);
+                TC_TIMED(KIND, et_wait, mbar_wait(&tfull[buf], tpar));
                 tc_fence_after();
                 const uint32_t t_addr = tbase + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + c0;
                 uint32_t flagmask = 0;
+                constexpr int CW = 8;  // columns per TMEM load: keeps the live accumulator set at 8 D registers
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t acc[D][16];
+                for (int ch = 0; ch < 32 / CW; ++ch) {
+                    uint32_t acc[D][CW];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) tmem_ld16(t_addr + d * 64 + ch * 16, acc[d]);
+                    for (int d = 0; d < D; ++d) tmem_ld8(t_addr + d * 64 + ch * CW, acc[d]);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) {
-                        const int cc = ch * 16 + x;   // column inside this warp's half
+                    for (int x = 0; x < CW; ++x) {
+                        const int cc = ch * CW + x;   // column inside this warp's half
                         const int c = c0 + cc;        // column inside the slot
                         if (KIND == TCK_RAW) {
                             if (q == q1 - 1) {  // rate probe: only the last accumulation of a unit is stored
@@ -355,37 +462,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][x])) << 16;
                             const bool col_ok = SMALL_M ? (c < p.mpad) : true;
                             if (col_ok) p.s0fix[row * p.mpad + jbase + c] = S;
-                        } else {
-                            // S = hi * 256 + lo with lo in [0, 256); all int32 (|S| < 2^38 is checked on the host)
+                        }
+                    }
+                    if (KIND == TCK_COUNT) {
+                        // Fast pass on the high part only.  S = hi * 256 + lo with lo in [0, 256) (all int32, |S| < 2^38
+                        // is checked on the host), so S - S0 = dh * 256 + dl with |dl| <= 255 and
+                        //   dh >= bh  =>  S - S0 >  band,      dh <= -bh  =>  S - S0 < -band,     bh = (band + 255) / 256 + 1
+                        // (band = 0 for exactly representable columns).  The few comparisons in between are redone
+                        // with the low parts in the slow pass below.
+                        uint32_t undmask = 0;
+#pragma unroll
+                        for (int x = 0; x < CW; ++x) {
+                            const int cc = ch * CW + x;
+                            const int c = c0 + cc;
                             const int a0 = static_cast<int32_t>(acc[0][x]);
                             int hi = a0 >> 8;
                             if (D > 1) hi += static_cast<int32_t>(acc[1][x]);
                             if (D > 2) hi += static_cast<int32_t>(acc[D - 1][x]) << 8;
-                            const int lo = a0 & 255;
-                            const int o_hi = s_hi[c * TC_ROWS + row_in_tile];
-                            const int o_lo = (s_lo[(c >> 2) * TC_ROWS + row_in_tile] >> (8 * (c & 3))) & 255;
-                            int dh = hi - o_hi;
-                            dh = max(min(dh, 1 << 22), -(1 << 22));  // keeps sign and |diff| >> band, avoids overflow
-                            const int diff = dh * 256 + (lo - o_lo);
-                            uint32_t add;
-                            if (all_exact) {
-                                add = (diff >= 0 ? 0x10000u : 0u) + (diff <= 0 ? 1u : 0u);
-                            } else {
-                                const int b = (all_inexact || ((inexact_mask >> cc) & 1u)) ? band : 0;
-                                const bool gt = diff > b, lt = diff < -b;
-                                const bool und = !(gt | lt);
-                                const bool tie = und && b == 0;
-                                add = ((gt | tie) ? 0x10000u : 0u) + ((lt | tie) ? 1u : 0u);
-                                if (und && b != 0) flagmask |= 1u << cc;
-                            }
+                            const int dh = hi - s_hi[c * TC_ROWS + row_in_tile];
+                            const int bhc = all_exact ? 1 : ((all_inexact || ((inexact_mask >> cc) & 1u)) ? bh : 1);
+                            bool gt = dh >= bhc, lt = dh <= -bhc;
+                            bool und = !(gt | lt);
                             if (SMALL_M) {
-                                const int pl = q * p.pps + (c >> p.log2_mpad);
-                                if (pl >= p.batch_perms) {
-                                    add = 0;
-                                    flagmask &= ~(1u << cc);
-                                }
+                                const bool live = q * p.pps + (c >> p.log2_mpad) < p.batch_perms;
+                                gt &= live;
+                                lt &= live;
+                                und &= live;
                             }
-                            cnt[cc] += add;
+                            cnt[cc] += (gt ? 0x10000u : 0u) + (lt ? 1u : 0u);
+                            if (und) undmask |= 1u << x;
+                        }
+                        if (__any_sync(0xffffffffu, undmask != 0)) {
+#pragma unroll
+                            for (int x = 0; x < CW; ++x) {
+                                if (!((undmask >> x) & 1u)) continue;
+                                const int cc = ch * CW + x;
+                                const int c = c0 + cc;
+                                const int a0 = static_cast<int32_t>(acc[0][x]);
+                                int hi = a0 >> 8;
+                                if (D > 1) hi += static_cast<int32_t>(acc[1][x]);
+                                if (D > 2) hi += static_cast<int32_t>(acc[D - 1][x]) << 8;
+                                const int lo = a0 & 255;
+                                const int o_hi = s_hi[c * TC_ROWS + row_in_tile];
+                                const int o_lo = (s_lo[(c >> 2) * TC_ROWS + row_in_tile] >> (8 * (c & 3))) & 255;
+                                const int diff = (hi - o_hi) * 256 + (lo - o_lo);  // |hi - o_hi| < bh here: no overflow
+                                const int b = (!all_exact && (all_inexact || ((inexact_mask >> cc) & 1u))) ? band : 0;
+                                const bool gt = diff > b, lt = diff < -b;
+                                const bool tie = !(gt | lt) && b == 0;
+                                cnt[cc] += ((gt | tie) ? 0x10000u : 0u) + ((lt | tie) ? 1u : 0u);
+                                if (!(gt | lt) && b != 0) flagmask |= 1u << cc;
+                            }
                         }
                     }
                 }
@@ -435,6 +561,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                     }
                 }
             }
+        }
+        if (p.prof && warp == 0 && lane == 0) {
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 8), clock64() - et_start);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 9), et_wait);
         }
     }
     tc_fence_before();
@@ -514,27 +644,25 @@ __global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ o
     }
 }
 
-// expand one 128 x 64 bit tile into int8 {0,1} in K-major core-matrix order:
-//   byte offset = kc * 2048 + row * 16 + (k & 15),  kc = k >> 4
-__global__ void __launch_bounds__(256) k_expand_tiles(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
-                                                      const int32_t* __restrict__ tile_kt,
-                                                      const int32_t* __restrict__ tile_rb, int8_t* __restrict__ out) {
-    const int tile = blockIdx.x;
+// the 128 x 64 bit block of every stored tile as one 64-bit word per row (padding tiles and rows are zero)
+__global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
+                                                    const int32_t* __restrict__ tile_kt,
+                                                    const int32_t* __restrict__ tile_rb, int64_t n_tiles,
+                                                    uint64_t* __restrict__ out) {
+    const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (idx >= n_tiles * TC_ROWS) return;
+    const int64_t tile = idx / TC_ROWS;
+    const int r = static_cast<int>(idx % TC_ROWS);
     const int kt = tile_kt[tile], rb = tile_rb[tile];
-    uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(tile) * TC_TILE_A);
-    for (int it = threadIdx.x; it < 512; it += blockDim.x) {
-        const int kc = it >> 7, r = it & 127;
+    uint64_t w = 0;
+    if (rb >= 0) {
         const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + r;
-        uint32_t bits = 0;
-        if (rb >= 0 && row < n) bits = (words[row * ld + 2 * kt + (kc >> 1)] >> ((kc & 1) * 16)) & 0xffffu;
-        uint32_t w[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const uint32_t nib = (bits >> (4 * q)) & 0xfu;
-            w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        if (row < n) {
+            const uint2 v = *reinterpret_cast<const uint2*>(words + row * ld + 2 * kt);
+            w = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
         }
-        dst[it] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    out[idx] = w;
 }
 
 // per-column exponent range of nan0(B): kmax = exponent of the largest magnitude, lmin = exponent of the lowest
@@ -661,7 +789,7 @@ struct TcPlan {
     int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
     int64_t n_tiles_real = 0;  // non-empty tiles
     bool usable = true;  // false: data contains +-inf -> SIMT engine
-    DevBuf<int8_t> a_tiles;
+    DevBuf<uint64_t> a_bits;
     DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
     DevBuf<int8_t> digits;
     DevBuf<uint8_t> inexact;
@@ -672,6 +800,19 @@ struct TcPlan {
 };
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
+
+static void print_prof(sb_ctx* ctx, const long long* d_prof, const char* what) {
+    long long h[16];
+    SB_CUDA(cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const double fills = std::max<double>(1.0, static_cast<double>(h[10]));
+    fprintf(stderr,
+            "[sb_trace] %s: cycles per fill (%d k-tiles): producer %.0f (wait empty %.0f) | expander %.0f (wait aempty "
+            "%.0f, tmem st %.0f) | mma %.0f (wait A %.0f, wait B %.0f, wait tempty %.0f) | epilogue %.0f (wait "
+            "tfull %.0f)\n",
+            what, TC_TPS, h[0] / fills, h[1] / fills, h[2] / fills, h[3] / fills, h[11] / fills, h[4] / fills,
+            h[5] / fills, h[6] / fills, h[7] / fills, h[8] / fills, h[9] / fills);
+}
 
 template <int D, int KIND, bool SMALL_M>
 static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
@@ -735,7 +876,7 @@ static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, in
 static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     sb_ctx* ctx = e->ctx;
     GemmParams gp{};
-    gp.a_tiles = pl->a_tiles.p;
+    gp.a_bits = pl->a_bits.p;
     gp.tile_ptr = pl->tile_ptr.p;
     gp.tile_kt = pl->tile_kt.p;
     gp.bcat = ctx->ws_bcat.p;
@@ -756,12 +897,9 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.flag_cap = pl->flag_cap;
     gp.cpk = ctx->ws_cpk.p;
     const uint32_t ncols = 64u * pl->D;
-    gp.a_lbo = 2048;       // K-major A: stride between the two 16-byte K chunks of one MMA
-    gp.a_sbo = 128;        //            stride between 8-row groups
     gp.b_lbo = ncols * 8;  // MN-major B: stride between 8-row K groups
     gp.b_sbo = 128;        //             stride between 16-column chunks
     gp.q_wrap = INT_MAX;
-    gp.a_kstep = 2 * 2048;
     gp.b_kstep = 4 * ncols * 8;
     return gp;
 }
@@ -833,13 +971,13 @@ static TcPlan* build_plan(sb_enrich* e) {
         pl->tile_ptr.reserve(pl->n_rb + 1);
         pl->tile_kt.reserve(run);
         pl->tile_rb.reserve(run);
-        pl->a_tiles.reserve(static_cast<size_t>(run) * TC_TILE_A);
+        pl->a_bits.reserve(static_cast<size_t>(run) * TC_ROWS);
         SB_CUDA(cudaMemcpyAsync(pl->tile_ptr.p, h_ptr.data(), (pl->n_rb + 1) * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, st));
         k_tile_list<<<pl->n_rb, 256, 0, st>>>(occ.p, pl->n_kt, pl->tile_ptr.p, pl->tile_kt.p, pl->tile_rb.p);
         SB_LAUNCH_CHECK(ctx);
-        k_expand_tiles<<<static_cast<unsigned>(run), 256, 0, st>>>(e->a->words, n, e->a->ld, pl->tile_kt.p,
-                                                                  pl->tile_rb.p, pl->a_tiles.p);
+        k_pack_tiles<<<static_cast<unsigned>(sb_ceil_div(run * TC_ROWS, 256)), 256, 0, st>>>(
+            e->a->words, n, e->a->ld, pl->tile_kt.p, pl->tile_rb.p, run, pl->a_bits.p);
         SB_LAUNCH_CHECK(ctx);
 
         delete tr;
@@ -959,7 +1097,7 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
     // operand slab that the band touches for one (q chunk, column group) is kept to <= ~16 MB, so the two or three
     // slabs that the dynamically scheduled CTAs work on at any time stay in the 126 MB L2 together with the band.
     const double tile_b = static_cast<double>(TC_KT) * 64 * pl->D;
-    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_TILE_A / pl->n_rb;
+    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_ROWS * 8 / pl->n_rb;
     int band = static_cast<int>(std::max(1.0, (32 << 20) / a_per_rb));
     band = std::max(band, std::min(pl->n_rb, ctx->num_sms));
     band = std::min(band, static_cast<int>(pl->n_rb));
@@ -978,7 +1116,17 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
     gp.q_chunks = static_cast<int32_t>(sb_ceil_div(q_total, gp.q_per));
     const int64_t units = static_cast<int64_t>(base_units) * gp.q_chunks;
     SB_CHECK(units < (1ll << 31), "too many work units in one batch (%lld)", (long long)units);
+    static const bool trace = getenv("SB_TRACE") != nullptr;
+    DevBuf<long long> d_prof;
+    if (trace) {
+        d_prof.reserve(16);
+        SB_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(long long), ctx->stream));
+        gp.prof = d_prof.p;
+        fprintf(stderr, "[sb_trace] gemm schedule: n_rb %d n_cg %d q_total %d q_per %d band_rb %d n_bands %d units %lld\n",
+                pl->n_rb, pl->n_cg, q_total, gp.q_per, gp.band_rb, gp.n_bands, (long long)units);
+    }
     launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms)));
+    if (trace) print_prof(ctx, d_prof.p, "batch gemm");
 }
 
 static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpos) {
@@ -1104,14 +1252,17 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     const int D = ncols / 64;
     const int K = ktiles * TC_KT;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
-    // host-side tiling into the production layouts
+    // host-side tiling into the production layouts; A is a 0/1 matrix (any non-zero entry counts as 1)
     const int kt_pad = static_cast<int>(sb_ceil_div(ktiles, TC_TPS) * TC_TPS);  // padding tiles of A are all zero
-    std::vector<int8_t> at(static_cast<size_t>(kt_pad) * TC_TILE_A, 0), bt(static_cast<size_t>(ktiles) * tile_b);
+    std::vector<uint64_t> at(static_cast<size_t>(kt_pad) * TC_ROWS, 0);
+    std::vector<int8_t> bt(static_cast<size_t>(ktiles) * tile_b);
     for (int kt = 0; kt < ktiles; ++kt)
-        for (int r = 0; r < TC_ROWS; ++r)
+        for (int r = 0; r < TC_ROWS; ++r) {
+            uint64_t w = 0;
             for (int k = 0; k < TC_KT; ++k)
-                at[static_cast<size_t>(kt) * TC_TILE_A + (k >> 4) * 2048 + r * 16 + (k & 15)] =
-                    a_host[static_cast<size_t>(r) * K + kt * TC_KT + k];
+                if (a_host[static_cast<size_t>(r) * K + kt * TC_KT + k]) w |= 1ull << k;
+            at[static_cast<size_t>(kt) * TC_ROWS + r] = w;
+        }
     const int nc16 = ncols / 16;
     for (int kt = 0; kt < ktiles; ++kt)
         for (int k = 0; k < TC_KT; ++k)
@@ -1120,7 +1271,8 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
                     b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
     std::vector<int32_t> ptr = {0, kt_pad}, kts(kt_pad);
     for (int i = 0; i < kt_pad; ++i) kts[i] = std::min(i, ktiles - 1);
-    DevBuf<int8_t> d_a, d_b;
+    DevBuf<uint64_t> d_a;
+    DevBuf<int8_t> d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
     d_a.reserve(at.size());
     d_b.reserve(bt.size());
@@ -1128,13 +1280,13 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     d_kt.reserve(kt_pad);
     d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
     cudaStream_t st = ctx->stream;
-    SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_b.p, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), kt_pad * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemsetAsync(d_out.p, 0xff, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t), st));
     GemmParams gp{};
-    gp.a_tiles = d_a.p;
+    gp.a_bits = d_a.p;
     gp.tile_ptr = d_ptr.p;
     gp.tile_kt = d_kt.p;
     gp.bcat = d_b.p;
@@ -1151,15 +1303,11 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     gp.pps = 1;
     gp.batch_perms = 1;
     gp.raw_out = d_out.p;
-    gp.a_lbo = 2048;
-    gp.a_sbo = 128;
     gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
     gp.b_sbo = 128;
     gp.q_wrap = INT_MAX;
-    gp.a_kstep = 2 * 2048;
     gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
-    if (variant & 1) std::swap(gp.a_lbo, gp.a_sbo);
-    if (variant & 2) std::swap(gp.b_lbo, gp.b_sbo);
+    if (variant & 2) std::swap(gp.b_lbo, gp.b_sbo);  // deliberately wrong descriptor (negative control)
     launch_gemm_d(ctx, D, gp, 1);
     SB_CUDA(cudaMemcpyAsync(d_host, d_out.p, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t),
                             cudaMemcpyDeviceToHost, st));
@@ -1167,10 +1315,11 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     SB_API_END
 }
 
-// Streaming-rate probe: `grid` CTAs each run `slots` accumulations over the same `ktiles` L2-resident tile pairs
+// Streaming-rate probe: `grid` CTAs each run `slots` accumulations over the same `ktiles` L2-resident tiles
 // through the production pipeline (no HBM traffic after the first touch).  Returns the device time in ms.
 extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slots, int grid, int dbg,
-                                    const uint32_t* desc_override /*NULL or 9 values*/, double* ms_out) {
+                                    const uint32_t* desc_override /*NULL, or {b_lbo, b_sbo, b_kstep}*/,
+                                    double* ms_out) {
     SB_API_BEGIN
     SB_CHECK(ctx && ms_out, "sb_selftest_mma_rate: NULL argument");
     SB_CHECK(ncols == 64 || ncols == 128 || ncols == 192, "sb_selftest_mma_rate: ncols must be 64, 128 or 192");
@@ -1179,26 +1328,24 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     ctx->bind();
     const int D = ncols / 64;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
-    DevBuf<int8_t> d_a, d_b;
+    DevBuf<uint64_t> d_a;
+    DevBuf<int8_t> d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
-    d_a.reserve(static_cast<size_t>(ktiles) * TC_TILE_A);
+    d_a.reserve(static_cast<size_t>(ktiles) * TC_ROWS);
     d_b.reserve(static_cast<size_t>(ktiles) * tile_b);
-    d_ptr.reserve(grid + 1);
+    d_ptr.reserve(2);
     d_kt.reserve(ktiles);
     d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
     cudaStream_t st = ctx->stream;
-    SB_CUDA(cudaMemsetAsync(d_a.p, 1, static_cast<size_t>(ktiles) * TC_TILE_A, st));
+    SB_CUDA(cudaMemsetAsync(d_a.p, 0x55, static_cast<size_t>(ktiles) * TC_ROWS * sizeof(uint64_t), st));
     SB_CUDA(cudaMemsetAsync(d_b.p, 1, static_cast<size_t>(ktiles) * tile_b, st));
-    std::vector<int32_t> ptr(grid + 1), kts(ktiles);
-    for (int i = 0; i <= grid; ++i) ptr[i] = i == 0 ? 0 : ktiles;  // every row block uses the same tile range
-    ptr[0] = 0;
+    std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
     for (int i = 0; i < ktiles; ++i) kts[i] = i;
-    // all units share tiles [0, ktiles): tile_ptr[rb] = 0 and tile_ptr[rb + 1] = ktiles cannot both hold for a
-    // prefix array, so the probe uses n_rb = 1 and spreads the CTAs over the q chunks instead
+    // all units share tiles [0, ktiles): one row block, the CTAs are spread over the q chunks
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), ktiles * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     GemmParams gp{};
-    gp.a_tiles = d_a.p;
+    gp.a_bits = d_a.p;
     gp.tile_ptr = d_ptr.p;
     gp.tile_kt = d_kt.p;
     gp.bcat = d_b.p;
@@ -1217,31 +1364,27 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     gp.pps = 1;
     gp.batch_perms = 1;
     gp.raw_out = d_out.p;
-    gp.a_lbo = 2048;
-    gp.a_sbo = 128;
     gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
     gp.b_sbo = 128;
-    gp.a_kstep = 2 * 2048;
     gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
-    if (desc_override) {  // speed-only experiments with other canonical layouts (results are not checked)
-        gp.a_layout = desc_override[0];
-        gp.a_lbo = desc_override[1];
-        gp.a_sbo = desc_override[2];
-        gp.a_kstep = desc_override[3];
-        gp.b_layout = desc_override[4];
-        gp.b_lbo = desc_override[5];
-        gp.b_sbo = desc_override[6];
-        gp.b_kstep = desc_override[7];
-        gp.b_kmajor = desc_override[8];
+    if (desc_override) {  // speed-only experiments with other descriptor fields (results are not checked)
+        gp.b_lbo = desc_override[0];
+        gp.b_sbo = desc_override[1];
+        gp.b_kstep = desc_override[2];
     }
     cudaEvent_t e0, e1;
     SB_CUDA(cudaEventCreate(&e0));
     SB_CUDA(cudaEventCreate(&e1));
+    DevBuf<long long> d_prof;
+    d_prof.reserve(16);
+    gp.prof = d_prof.p;
     launch_gemm_d(ctx, D, gp, grid);  // warm-up (also pulls the tiles into L2)
+    SB_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(long long), st));
     SB_CUDA(cudaEventRecord(e0, st));
     launch_gemm_d(ctx, D, gp, grid);
     SB_CUDA(cudaEventRecord(e1, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    if (getenv("SB_TRACE")) print_prof(ctx, d_prof.p, "rate probe");
     float ms = 0.f;
     SB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);

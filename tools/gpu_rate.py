@@ -1,4 +1,5 @@
-"""L2-hot streaming-rate experiments on the production GEMM pipeline (speed only, see sb_selftest_mma_rate)."""
+"""L2-hot streaming-rate experiments on the production GEMM pipeline (speed only, see sb_selftest_mma_rate).
+With SB_TRACE=1 the library also prints the per-role cycle accounting of every run."""
 import os
 import sys
 
@@ -13,12 +14,12 @@ def run(tag, ncols, grid, dbg=0, kt=32, slots=64):
     ms = _lib.selftest_mma_rate(ctx, ncols, kt, slots, grid, dbg, None)
     it = grid * slots * kt
     ops = it * 2.0 * 128 * ncols * 64
-    cyc = ms * 1e-3 * 1.965e9
-    print("%-16s N=%3d grid=%3d ktiles=%4d slots=%4d: %.3f ms %5.0f TOPS  %6.0f cyc/slot  %5.0f cyc/k-tile"
-          % (tag, ncols, grid, kt, slots, ms, ops / ms / 1e9, cyc / slots, cyc / slots / kt), flush=True)
+    print("%-16s N=%3d grid=%3d ktiles=%4d slots=%4d: %.3f ms %5.0f TOPS  %.2f us/k-tile/CTA"
+          % (tag, ncols, grid, kt, slots, ms, ops / ms / 1e9, ms * 1e3 / slots / kt), flush=True)
 
 
+slots = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 for grid in (1, 148):
-    for n in (64, 128, 192):
+    for n in (64, 192):
         for dbg, tag in ((0, "production"), (1, "copies only"), (2, "MMAs only"), (3, "barriers only")):
-            run(tag, n, grid, dbg, 32, 64)
+            run(tag, n, grid, dbg, 32, slots)

@@ -28,7 +28,8 @@ namespace sb {
 constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
 constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
 constexpr int TC_STAGES = 3;             // smem ring depth (gathered-operand tiles), TC_TPS tiles per stage
-constexpr int TC_ASLOTS = 2;             // TMEM ring depth (expanded A tiles), TC_TPS tiles per slot
+constexpr int TC_ASLOTS = 4;             // TMEM ring depth (expanded A tiles), TC_APS tiles per slot
+constexpr int TC_APS = 2;                // k-tiles per A slot (half a fill: the MMA warp frees A slots twice per fill)
 constexpr int TC_TPS = 4;                // k-tiles per pipeline fill (tile lists are padded to a multiple of it):
                                          // one fill = 8 MMAs = 768 tensor cycles at D = 3, which covers the
                                          // ~550 cycles of barrier / issue latency every role spends per fill
@@ -40,12 +41,13 @@ constexpr int TC_EXP_WARP0 = TC_EPI_WARPS;
 constexpr int TC_PROD_WARP = TC_EPI_WARPS + TC_EXP_WARPS;
 constexpr int TC_MMA_WARP = TC_PROD_WARP + 1;
 constexpr int TC_THREADS = (TC_EPI_WARPS + TC_EXP_WARPS + 2) * 32;
-// TMEM columns: accumulator buffer b at [256 b, 256 b + 64 D); A slot s (TC_TPS tiles x 16 columns) in the gap
-// [256 s + 192, 256 s + 256)
-__host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return s * 256u + 192u; }
-static_assert(TC_TPS * 16 <= 64 && TC_ASLOTS == 2, "A slots must fit the two 64-column gaps of TMEM");
+// TMEM columns: accumulator buffer b at [256 b, 256 b + 64 D); A slot s (TC_APS tiles x 16 columns) in the gaps
+// [192, 256) and [448, 512)
+__host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return (s >> 1) * 256u + 192u + (s & 1u) * 32u; }
+static_assert(TC_APS * 16 == 32 && TC_ASLOTS == 4 && TC_TPS == 2 * TC_APS, "A slots must tile the TMEM gaps");
+constexpr int TC_LUT_REP = 8;            // replicas of the byte -> 8 x int8 expansion table (bank spreading)
 constexpr int TC_SCHED = 4;              // depth of the work-unit ring (producer -> MMA / epilogue warps)
-constexpr int TC_KT_SMEM = 2048;         // k-tile ids of the current row block cached in smem (tail: global)
+constexpr int TC_KT_SMEM = 1024;         // k-tile ids of the current row block cached in smem (tail: global)
 
 enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
 // kernel flavours (compile-time, so the hot epilogue carries no mode tests)
@@ -74,7 +76,7 @@ struct GemmParams {
     int32_t* raw_out;         // TCM_RAW: [128][64*D]
     uint32_t b_lbo, b_sbo;
     int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
-    int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies
+    int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies, bit2 = MMA warp does not wait for operands
     uint32_t b_kstep;         // descriptor start-address advance per K=32 MMA
     long long* prof;          // per-role cycle counters [16] (see print_prof), or nullptr
 };
@@ -100,25 +102,41 @@ struct TcCfg {
     static constexpr int NCOLS = 64 * D;
     static constexpr int TILE_B = TC_KT * NCOLS;
     static constexpr int TPS = TC_TPS;
-    static constexpr int STAGE = TPS * TILE_B;
+    static constexpr int STAGE_B = TPS * TILE_B;                    // gathered-operand tiles of one fill
+    static constexpr int STAGE_A = TPS * TC_ROWS * 8;               // their A bit tiles (one 64-bit mask per row)
+    static constexpr int STAGE = STAGE_B + STAGE_A;
     static constexpr int STAGES = TC_STAGES;
     static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
     static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;    // uint32 [16][128], 4 columns per word
     static constexpr int OFF_KT = OFF_S0LO + 16 * TC_ROWS * 4;      // int32 [TC_KT_SMEM]
-    static constexpr int OFF_UNIT = OFF_KT + TC_KT_SMEM * 4;        // UnitInfo [TC_SCHED]
+    static constexpr int OFF_LUT = OFF_KT + TC_KT_SMEM * 4;         // uint64 [256][TC_LUT_REP]
+    static constexpr int OFF_UNIT = OFF_LUT + 256 * TC_LUT_REP * 8; // UnitInfo [TC_SCHED]
     static constexpr int OFF_BAR = OFF_UNIT + TC_SCHED * 32;
     static constexpr int SMEM = OFF_BAR + 512;  // 32 mbarriers + the TMEM base address
 };
 
-// 64 membership bits -> 16 TMEM words of four 0/1 bytes (K elements 4c .. 4c+3 of a row sit in 32-bit column c)
-__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t (&r)[16]) {
+// 64 membership bits -> 16 TMEM words of four 0/1 bytes (K elements 4c .. 4c+3 of a row sit in 32-bit column c).
+// One table lookup per byte of the mask: entry b of the table holds the eight 0/1 bytes of b.  The table is
+// replicated TC_LUT_REP times (lane l reads replica l % TC_LUT_REP) so that a warp's 32 random lookups spread over
+// the shared-memory banks.
+__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t lut_addr, uint32_t (&r)[16]) {
     const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
+    constexpr uint32_t SH = 6;  // log2(TC_LUT_REP * 8) bytes per table entry
+    constexpr uint32_t MASK = 0xffu << SH;
+    uint32_t idx[8];
+    idx[0] = (lo << SH) & MASK;
+    idx[1] = (lo >> (8 - SH)) & MASK;
+    idx[2] = (lo >> (16 - SH)) & MASK;
+    idx[3] = (lo >> (24 - SH)) & MASK;
+    idx[4] = (hi << SH) & MASK;
+    idx[5] = (hi >> (8 - SH)) & MASK;
+    idx[6] = (hi >> (16 - SH)) & MASK;
+    idx[7] = (hi >> (24 - SH)) & MASK;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        r[c] = (((lo >> (4 * c)) & 0xfu) * 0x00204081u) & 0x01010101u;
-        r[8 + c] = (((hi >> (4 * c)) & 0xfu) * 0x00204081u) & 0x01010101u;
-    }
+    for (int b = 0; b < 8; ++b)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2 * b]), "=r"(r[2 * b + 1]) : "r"(lut_addr + idx[b]));
 }
+static_assert(TC_LUT_REP * 8 == 64, "expand_bits assumes 64-byte table entries");
 
 // Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
 // tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTAs that
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], 1 + TC_EXP_WARPS);  // MMA commit + the expander warps (done reading the bit tiles)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
@@ -183,6 +201,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             mbar_init(&aempty[s], 1);
         }
         mbar_fence_init();
+    }
+    {
+        uint64_t* lut = reinterpret_cast<uint64_t*>(smem + C::OFF_LUT);
+        for (int i = threadIdx.x; i < 256 * TC_LUT_REP; i += blockDim.x) {
+            const uint32_t b = static_cast<uint32_t>(i) / TC_LUT_REP;
+            uint64_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v |= static_cast<uint64_t>((b >> j) & 1u) << (8 * j);
+            lut[i] = v;
+        }
     }
     if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
@@ -227,7 +255,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
             __syncwarp();
             const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
-            for (int q = q0; q < q1; ++q) {
+            const uint64_t* const a_unit = p.a_bits + static_cast<size_t>(t0) * TC_ROWS;
+            for (int q = q0; q < q1 && !(p.dbg & 4); ++q) {
                 const int8_t* const b_q = b_cg + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
                 for (int f = 0; f < nfills; ++f) {
                     int kts[C::TPS];
@@ -243,10 +272,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             mbar_arrive(&full[stage]);
                         } else {
                             mbar_expect_tx(&full[stage], C::STAGE);
+                            uint8_t* const st = sB + stage * C::STAGE;
 #pragma unroll
                             for (int t = 0; t < C::TPS; ++t)
-                                bulk_g2s(sB + (stage * C::TPS + t) * C::TILE_B,
-                                         b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B, &full[stage]);
+                                bulk_g2s(st + t * C::TILE_B, b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B,
+                                         &full[stage]);
+                            bulk_g2s(st + C::STAGE_B, a_unit + static_cast<size_t>(f) * (C::TPS * TC_ROWS), C::STAGE_A,
+                                     &full[stage]);
                         }
                     }
                     __syncwarp();
@@ -263,13 +295,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 0), clock64() - pt_start);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 1), pt_wait);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), pt_fills);
+            if (p.dbg & 4) p.prof[10] = static_cast<long long>(p.q_total) * (p.tile_ptr[1] / C::TPS);  // probe: n_rb = 1
         }
     } else if (warp >= TC_EXP_WARP0 && warp < TC_PROD_WARP) {
         // ------------------------------------------------------------ A expanders: bits -> int8 0/1 in TMEM
         const int quarter = warp - TC_EXP_WARP0;
         const int r = quarter * 32 + lane;
         const uint32_t t_lane = tbase + (static_cast<uint32_t>(quarter * 32) << 16);
-        uint32_t aslot = 0, aphase = 0, uit = 0;
+        uint32_t aslot = 0, aphase = 0, stage = 0, phase = 0, uit = 0;
         long long xt_wait = 0, xt_st = 0;
         const long long xt_start = clock64();
         while (true) {
@@ -281,39 +314,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             if (lane == 0) mbar_arrive(&sempty[sl]);
             ++uit;
             if (rb < 0) break;
-            const uint64_t* const abase = p.a_bits + static_cast<size_t>(t0) * TC_ROWS + r;
-            // the same tile list is expanded once per slot; the bits of the next fill are loaded one fill ahead
-            uint64_t w[C::TPS];
-#pragma unroll
-            for (int t = 0; t < C::TPS; ++t) w[t] = abase[t * TC_ROWS];
-            for (int q = q0; q < q1; ++q) {
+            const uint32_t lut_addr = smem_u32(smem + C::OFF_LUT) + (lane % TC_LUT_REP) * 8;
+            (void)t0;
+            for (int q = q0; q < q1 && !(p.dbg & 4); ++q) {
                 for (int f = 0; f < nfills; ++f) {
-                    const int fn = (f + 1 == nfills) ? 0 : f + 1;
-                    uint64_t nx[C::TPS];
+                    // the bit tiles of this fill arrive in the smem stage together with the gathered operand
+                    mbar_wait(&full[stage], phase);
+                    const uint64_t* const sbits =
+                        reinterpret_cast<const uint64_t*>(sB + stage * C::STAGE + C::STAGE_B) + r;
+                    uint64_t w[C::TPS];
 #pragma unroll
-                    for (int t = 0; t < C::TPS; ++t)
-                        nx[t] = abase[(static_cast<size_t>(fn) * C::TPS + t) * TC_ROWS];
-                    TC_TIMED(KIND, xt_wait, mbar_wait(&aempty[aslot], aphase ^ 1u));
-                    tc_fence_after();
-                    const uint32_t ta = t_lane + tc_acol(aslot);
-                    const long long st0 = p.prof ? clock64() : 0;
-#pragma unroll
-                    for (int t = 0; t < C::TPS; ++t) {
-                        uint32_t e[16];
-                        expand_bits(w[t], e);
-                        tmem_st16(ta + t * 16, e);
-                    }
-                    tmem_st_wait();
-                    if (p.prof) xt_st += clock64() - st0;
-                    tc_fence_before();
+                    for (int t = 0; t < C::TPS; ++t) w[t] = sbits[t * TC_ROWS];
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&afull[aslot]);
-                    if (++aslot == TC_ASLOTS) {
-                        aslot = 0;
-                        aphase ^= 1u;
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
                     }
 #pragma unroll
-                    for (int t = 0; t < C::TPS; ++t) w[t] = nx[t];
+                    for (int h = 0; h < C::TPS / TC_APS; ++h) {
+                        uint32_t e[TC_APS][16];
+#pragma unroll
+                        for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], lut_addr, e[t]);
+                        TC_TIMED(KIND, xt_wait, mbar_wait(&aempty[aslot], aphase ^ 1u));
+                        tc_fence_after();
+                        const uint32_t ta = t_lane + tc_acol(aslot);
+                        const long long st0 = p.prof ? clock64() : 0;
+#pragma unroll
+                        for (int t = 0; t < TC_APS; ++t) tmem_st16(ta + t * 16, e[t]);
+                        tmem_st_wait();
+                        if (p.prof) xt_st += clock64() - st0;
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&afull[aslot]);
+                        if (++aslot == TC_ASLOTS) {
+                            aslot = 0;
+                            aphase ^= 1u;
+                        }
+                    }
                 }
             }
         }
@@ -343,34 +381,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                 TC_TIMED(KIND, mt_wt, mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u));
                 const uint32_t d_tmem = tbase + buf * 256;
                 for (int f = 0; f < nfills; ++f) {
-                    TC_TIMED(KIND, mt_wa, mbar_wait(&afull[aslot], aphase));
-                    TC_TIMED(KIND, mt_wb, mbar_wait(&full[stage], phase));
-                    tc_fence_after();
-                    if (elect_one()) {
-                        if (!(p.dbg & 1)) {
-                            // A: TMEM slot, 8 columns per K=32 MMA.  B: MN-major smem, four 8-row K groups per MMA
-                            const uint32_t a_t = tbase + tc_acol(aslot);
-                            const uint64_t b_st = b_desc0 + stage * (C::STAGE >> 4);
+                    // no wait on full[stage]: the expanders pass it before they publish the first A slot of the fill
+                    const uint64_t b_st = b_desc0 + stage * (C::STAGE >> 4);
 #pragma unroll
-                            for (int t = 0; t < C::TPS; ++t) {
+                    for (int h = 0; h < C::TPS / TC_APS; ++h) {
+                        if (!(p.dbg & 4)) TC_TIMED(KIND, mt_wa, mbar_wait(&afull[aslot], aphase));
+                        tc_fence_after();
+                        if (elect_one()) {
+                            if (!(p.dbg & 1)) {
+                                // A: TMEM slot, 8 columns per K=32 MMA.  B: MN-major smem, four 8-row K groups per MMA
+                                const uint32_t a_t = tbase + tc_acol(aslot);
 #pragma unroll
-                                for (int ks = 0; ks < TC_KT / 32; ++ks)
-                                    mma_i8_ts(d_tmem, a_t + t * 16 + ks * 8,
-                                              b_st + (t * (C::TILE_B >> 4) + ks * b_ks), idesc, (f | t | ks) != 0);
+                                for (int t = 0; t < TC_APS; ++t) {
+#pragma unroll
+                                    for (int ks = 0; ks < TC_KT / 32; ++ks)
+                                        mma_i8_ts(d_tmem, a_t + t * 16 + ks * 8,
+                                                  b_st + ((h * TC_APS + t) * (C::TILE_B >> 4) + ks * b_ks), idesc,
+                                                  (f | h | t | ks) != 0);
+                                }
+                            }
+                            if (!(p.dbg & 4)) mma_commit(&aempty[aslot]);
+                            if (h == C::TPS / TC_APS - 1) {
+                                if (!(p.dbg & 4)) mma_commit(&empty[stage]);
+                                if (f == nfills - 1) mma_commit(&tfull[buf]);
                             }
                         }
-                        mma_commit(&empty[stage]);
-                        mma_commit(&aempty[aslot]);
-                        if (f == nfills - 1) mma_commit(&tfull[buf]);
+                        __syncwarp();
+                        if (++aslot == TC_ASLOTS) {
+                            aslot = 0;
+                            aphase ^= 1u;
+                        }
                     }
-                    __syncwarp();
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1u;
-                    }
-                    if (++aslot == TC_ASLOTS) {
-                        aslot = 0;
-                        aphase ^= 1u;
                     }
                 }
                 ++acc_it;

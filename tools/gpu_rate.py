@@ -20,6 +20,7 @@ def run(tag, ncols, grid, dbg=0, kt=32, slots=64):
 
 slots = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 for grid in (1, 148):
-    for n in (64, 192):
-        for dbg, tag in ((0, "production"), (1, "copies only"), (2, "MMAs only"), (3, "barriers only")):
+    for n in (64, 128, 192):
+        for dbg, tag in ((0, "production"), (1, "copies only"), (2, "MMAs only"), (3, "barriers only"),
+                         (6, "MMA issue only"), (7, "issue loop only")):
             run(tag, n, grid, dbg, 32, slots)

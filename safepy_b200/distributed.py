@@ -1,0 +1,43 @@
+"""Multi-GPU plumbing for the permutation null: one process per GPU, permutations sharded, ONE sum all-reduce.
+
+The randomization null is embarrassingly parallel over permutations once the host has generated the (inherently
+sequential) index stream: rank r scores permutations [lo, hi) against the full neighborhood matrix and the counts
+add up (safepy/safe.py:518-519 does the same reduction with np.sum over its worker results).  This module holds the
+backend-independent part so that it can be exercised with gloo on CPU; bench.py uses it with NCCL on device buffers.
+"""
+import numpy as np
+
+from .permutations import make_perm_rows, shard_bounds
+
+
+def local_perm_rows(node2attribute, num_permutations, random_seed, world_size, rank):
+    """Gather rows of this rank's shard.  Every rank replays the whole RNG stream (cumulative shuffles cannot be
+    skipped ahead) and keeps its slice; returns (rows[lo:hi], lo, hi)."""
+    rows = make_perm_rows(node2attribute, num_permutations, random_seed)
+    lo, hi = shard_bounds(num_permutations, world_size, rank)
+    return np.ascontiguousarray(rows[lo:hi]), lo, hi
+
+
+def sharded_perm_counts(count_fn, node2attribute, num_permutations, random_seed, dist=None, device=None):
+    """counts_neg, counts_pos over all permutations.
+
+    count_fn(rows) -> (counts_neg, counts_pos) for a block of gather rows (e.g. Enrichment.perm_counts);
+    dist: an initialised torch.distributed module (or None for a single process)."""
+    world = dist.get_world_size() if dist is not None else 1
+    rank = dist.get_rank() if dist is not None else 0
+    rows, lo, hi = local_perm_rows(node2attribute, num_permutations, random_seed, world, rank)
+    n, m = node2attribute.shape
+    if hi > lo:
+        cneg, cpos = count_fn(rows)
+    else:
+        cneg = np.zeros((n, m), dtype=np.int64)
+        cpos = np.zeros((n, m), dtype=np.int64)
+    if dist is None or world == 1:
+        return np.asarray(cneg), np.asarray(cpos)
+    import torch
+    both = torch.from_numpy(np.stack([np.asarray(cneg, dtype=np.int64), np.asarray(cpos, dtype=np.int64)]))
+    if device is not None:
+        both = both.to(device)
+    dist.all_reduce(both)  # the single collective of stage 2
+    both = both.cpu().numpy()
+    return both[0], both[1]

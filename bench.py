@@ -332,12 +332,12 @@ def run_ours(args):
         sec_per_step = ms_total / 1e3 / args.steps
         value = scores_per_step / sec_per_step
         gemm_ms, gemm_launches = kern["gemm"]
-        # algorithmic FLOPs of the score GEMM: 2 * (cells of non-empty A tiles) * M per permutation,
+        # algorithmic FLOPs of the score GEMM: 2 * (cells of non-empty 256 x 64 A tiles) * M per permutation,
         # digit passes and padding are implementation factors and are NOT counted
         tiles = stats["a_tiles"]
-        flops_total = 2.0 * tiles * 128 * 64 * m * (hi - lo) * args.steps
+        flops_total = 2.0 * tiles * 256 * 64 * m * (hi - lo) * args.steps
         achieved_tf = flops_total / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
-        int8_ops = 2.0 * stats["ktile_iters"] * 128 * 64 * 64 * stats["digits"] * args.steps
+        int8_ops = 2.0 * stats["ktile_iters"] * 256 * 64 * 64 * stats["digits"] * args.steps
         out = {
             "metric": "enrichment node-attr-perm scores/s", "value": value, "unit": "scores/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,

@@ -4,18 +4,18 @@
 //
 // Arithmetic.  A is {0,1}.  Every attribute column j of nan0(B) is turned into a fixed-point integer
 // q = rint(v * 2^s_j) and written as D balanced base-256 digits (int8).  S_fix = A @ q is then computed EXACTLY by
-// tcgen05.mma.kind::i8 (int32 accumulators in TMEM, one accumulator per digit plane, recombined in int64 in the
-// epilogue).  If a column is exactly representable (binary / integer / dyadic data) S_fix comparisons ARE the
-// reference's comparisons.  Otherwise |S_fix - 2^s * S_true| <= n_i / 2, so |S_fix(p) - S_fix(0)| > n_i decides the
-// comparison rigorously and the rare remainder is appended to a list that enrich.cu re-evaluates in fp64.
+// tcgen05.mma.kind::i8 (int32 accumulators in TMEM, one accumulator per digit plane, recombined in the epilogue).
+// If a column is exactly representable (binary / integer / dyadic data) S_fix comparisons ARE the reference's
+// comparisons.  Otherwise |S_fix - 2^s * S_true| <= n_i / 2, so |S_fix(p) - S_fix(0)| > n_i decides the comparison
+// rigorously and the rare remainder is appended to a list that enrich.cu re-evaluates in fp64.
 //
-// Data movement.  A lives as a list of non-empty 128 x 64 int8 tiles per 128-row block (empty tiles are skipped:
-// with spatially ordered nodes most of them are).  The permuted operand of a batch of permutations is gathered
-// once into "Bcat" tiles (64 x 64*D int8).  Both tile kinds are stored in HBM in the tensor core's canonical
-// no-swizzle core-matrix order, so one 1-D bulk async copy (TMA engine, UBLKCP) per tile lands them in shared
-// memory ready for the MMA.  Per CTA: warp 0 = copy producer, warp 1 = MMA issuer, warps 2-5 = epilogue;
-// smem ring of STAGES (A,B) tile pairs; two TMEM accumulator buffers so the epilogue of slot q overlaps the MMAs
-// of slot q+1.
+// Data movement.  The kernel runs on CTA PAIRS (cluster of two SMs, tcgen05 cta_group::2, M = 256): a pair owns a
+// block of 256 rows of A (128 per CTA) and multiplies it with a gathered-operand tile whose 64*D columns are split
+// between the two CTAs' shared memories, so every byte of the gathered operand that leaves L2 feeds 256 rows.
+// A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row.  The masks ride along with the
+// gathered tiles through the smem ring, expander warps turn them into int8 0/1 in TMEM, and the MMA takes its A
+// operand from TMEM.  Gathered tiles are stored in HBM in the tensor core's canonical no-swizzle MN-major
+// core-matrix order, one half per CTA, so one 1-D bulk async copy (TMA engine, UBLKCP) lands a half tile MMA-ready.
 #include <algorithm>
 #include <climits>
 #include <vector>
@@ -25,9 +25,10 @@
 
 namespace sb {
 
-constexpr int TC_ROWS = 128;             // rows of A per CTA tile (= TMEM lanes)
-constexpr int TC_KT = 64;                // K extent of one smem tile (2 MMAs of K=32)
-constexpr int TC_STAGES = 3;             // smem ring depth (gathered-operand tiles), TC_TPS tiles per stage
+constexpr int TC_ROWS = 128;             // rows of A per CTA (= TMEM lanes)
+constexpr int TC_PROWS = 2 * TC_ROWS;    // rows per CTA pair = rows of one work unit's row block
+constexpr int TC_KT = 64;                // K extent of one tile (2 MMAs of K=32)
+constexpr int TC_STAGES = 5;             // smem ring depth, TC_TPS tiles per stage
 constexpr int TC_ASLOTS = 4;             // TMEM ring depth (expanded A tiles), TC_APS tiles per slot
 constexpr int TC_APS = 2;                // k-tiles per A slot (half a fill: the MMA warp frees A slots twice per fill)
 constexpr int TC_TPS = 4;                // k-tiles per pipeline fill (tile lists are padded to a multiple of it):
@@ -46,7 +47,7 @@ constexpr int TC_THREADS = (TC_EPI_WARPS + TC_EXP_WARPS + 2) * 32;
 __host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return (s >> 1) * 256u + 192u + (s & 1u) * 32u; }
 static_assert(TC_APS * 16 == 32 && TC_ASLOTS == 4 && TC_TPS == 2 * TC_APS, "A slots must tile the TMEM gaps");
 constexpr int TC_LUT_REP = 8;            // replicas of the byte -> 8 x int8 expansion table (bank spreading)
-constexpr int TC_SCHED = 4;              // depth of the work-unit ring (producer -> MMA / epilogue warps)
+constexpr int TC_SCHED = 4;              // depth of the work-unit ring (scheduler -> all other roles of the pair)
 constexpr int TC_KT_SMEM = 1024;         // k-tile ids of the current row block cached in smem (tail: global)
 
 enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
@@ -54,17 +55,17 @@ enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
 enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
 
 struct GemmParams {
-    const uint64_t* a_bits;   // [n_tiles][128]: bit k of word r = A[row block row r][64 kt + k]
+    const uint64_t* a_bits;   // [n_tiles / TPS][2 (CTA rank)][TPS][128]: bit k of a word = A[row][64 kt + k]
     const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
-    const int8_t* bcat;       // [slot][kt][64 x 64*D]
-    int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;
+    const int8_t* bcat;       // [slot][kt][2 (CTA rank)][64 x 32*D]
+    int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;  // n_rb: blocks of TC_PROWS rows
     int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
     unsigned int* unit_counter;  // dynamic scheduler (zeroed before the launch)
     int32_t mode;
     int64_t n, m, mpad;
     int32_t log2_mpad, pps, batch_perms;
-    int64_t* s0fix;           // [n_rb * 128][mpad]
+    int64_t* s0fix;           // [n_rb * 256][mpad]
     const int64_t* row_ptr;   // band_i = row_ptr[i+1] - row_ptr[i]
     const int32_t* node_of_row;  // internal row -> caller's node id (nullptr: identity)
     const uint8_t* inexact;   // [mpad]
@@ -73,7 +74,7 @@ struct GemmParams {
     uint32_t* flag_p;
     unsigned int* flag_count;
     unsigned int flag_cap;
-    int32_t* raw_out;         // TCM_RAW: [128][64*D]
+    int32_t* raw_out;         // TCM_RAW: [256][64*D]
     uint32_t b_lbo, b_sbo;
     int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
     int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies, bit2 = MMA warp does not wait for operands
@@ -84,7 +85,7 @@ struct GemmParams {
 // cycle accounting per role, enabled by a non-null GemmParams::prof (SB_TRACE runs and the rate probe)
 #define TC_TIMED(KINDV, acc, stmt)            \
     do {                                      \
-        if (p.prof) {                         \
+        if (PROF) {                           \
             const long long _t0 = clock64();  \
             stmt;                             \
             (acc) += clock64() - _t0;         \
@@ -100,10 +101,10 @@ struct UnitInfo {
 template <int D>
 struct TcCfg {
     static constexpr int NCOLS = 64 * D;
-    static constexpr int TILE_B = TC_KT * NCOLS;
+    static constexpr int HALF_B = TC_KT * NCOLS / 2;                // this CTA's half of a gathered tile
     static constexpr int TPS = TC_TPS;
-    static constexpr int STAGE_B = TPS * TILE_B;                    // gathered-operand tiles of one fill
-    static constexpr int STAGE_A = TPS * TC_ROWS * 8;               // their A bit tiles (one 64-bit mask per row)
+    static constexpr int STAGE_B = TPS * HALF_B;                    // gathered-operand half tiles of one fill
+    static constexpr int STAGE_A = TPS * TC_ROWS * 8;               // this CTA's A bit tiles (one 64-bit mask per row)
     static constexpr int STAGE = STAGE_B + STAGE_A;
     static constexpr int STAGES = TC_STAGES;
     static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
@@ -112,35 +113,29 @@ struct TcCfg {
     static constexpr int OFF_LUT = OFF_KT + TC_KT_SMEM * 4;         // uint64 [256][TC_LUT_REP]
     static constexpr int OFF_UNIT = OFF_LUT + 256 * TC_LUT_REP * 8; // UnitInfo [TC_SCHED]
     static constexpr int OFF_BAR = OFF_UNIT + TC_SCHED * 32;
-    static constexpr int SMEM = OFF_BAR + 512;  // 32 mbarriers + the TMEM base address
+    static constexpr int SMEM = OFF_BAR + 512;  // 34 mbarriers + the TMEM base address
 };
 
 // 64 membership bits -> 16 TMEM words of four 0/1 bytes (K elements 4c .. 4c+3 of a row sit in 32-bit column c).
 // One table lookup per byte of the mask: entry b of the table holds the eight 0/1 bytes of b.  The table is
 // replicated TC_LUT_REP times (lane l reads replica l % TC_LUT_REP) so that a warp's 32 random lookups spread over
 // the shared-memory banks.
-__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t lut_addr, uint32_t (&r)[16]) {
+__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t lane_lut, uint32_t (&r)[16]) {
     const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
-    constexpr uint32_t SH = 6;  // log2(TC_LUT_REP * 8) bytes per table entry
-    constexpr uint32_t MASK = 0xffu << SH;
-    uint32_t idx[8];
-    idx[0] = (lo << SH) & MASK;
-    idx[1] = (lo >> (8 - SH)) & MASK;
-    idx[2] = (lo >> (16 - SH)) & MASK;
-    idx[3] = (lo >> (24 - SH)) & MASK;
-    idx[4] = (hi << SH) & MASK;
-    idx[5] = (hi >> (8 - SH)) & MASK;
-    idx[6] = (hi >> (16 - SH)) & MASK;
-    idx[7] = (hi >> (24 - SH)) & MASK;
+    // two instructions per lookup address: PRMT isolates byte b, one multiply-add scales it by the 64-byte entry
+    // stride and adds this lane's table address (replica included)
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2 * b]), "=r"(r[2 * b + 1]) : "r"(lut_addr + idx[b]));
+    for (int b = 0; b < 8; ++b) {
+        const uint32_t byte = __byte_perm(b < 4 ? lo : hi, 0u, 0x4440u + (b & 3));
+        const uint32_t addr = byte * 64u + lane_lut;
+        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2 * b]), "=r"(r[2 * b + 1]) : "r"(addr));
+    }
 }
 static_assert(TC_LUT_REP * 8 == 64, "expand_bits assumes 64-byte table entries");
 
 // Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
-// tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTAs that
-// fetch neighbouring unit numbers read the same gathered operand slab (q chunk, column group).
+// tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTA pairs
+// that fetch neighbouring unit numbers read the same gathered operand slab (q chunk, column group).
 __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb, int& cg, int& q0, int& q1) {
     const int per_full = p.band_rb * p.n_cg * p.q_chunks;
     const int b = min(u / per_full, p.n_bands - 1);
@@ -154,15 +149,18 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb,
     q1 = min(p.q_total, q0 + p.q_per);
 }
 
-// Warp roles: 0..7 = epilogue, 8..11 = A expanders, 12 = scheduler + bulk-copy producer, 13 = MMA issuer (+ TMEM
-// alloc).  The producer warp draws work units from a global counter and publishes them through a small smem ring,
-// so all roles walk the same unit sequence.  Issue loops are warp-uniform with one elected lane issuing.
-// A never touches shared memory: expander warp w holds rows 32 w .. 32 w + 31 of the row block, reads the 64
-// membership bits of its row for a k-tile (8 bytes), expands them to int8 0/1 in registers and stores them into a
-// TMEM slot, from where tcgen05.mma takes its A operand.  Only the gathered operand travels through smem.
+// One cluster = one CTA pair (ranks 0 = leader, 1 = peer); 448 threads per CTA.
+// Warp roles in BOTH CTAs: 0..7 = epilogue (own 128 rows), 8..11 = A expanders (own rows, own TMEM), 12 = bulk-copy
+// producer (own half of the gathered tiles + own bit tiles), 13 = TMEM alloc; in the leader warp 12 is also the
+// scheduler and warp 13 the MMA issuer for the pair.
+// Scheduler: draws work units from a global counter and publishes them into the unit rings of both CTAs, so all
+// roles of the pair walk the same unit sequence.  Issue loops are warp-uniform with one elected lane issuing.
+// Cross-CTA signalling: peer expanders / epilogue warps / ring consumers arrive on the leader's afull / tempty /
+// sempty barriers through shared::cluster; the leader's tcgen05.commit multicasts to the aempty / empty / tfull
+// barriers of both CTAs.
 // Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
-template <int D, int KIND, bool SMALL_M>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
+template <int D, int KIND, bool SMALL_M, bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sB = smem;
@@ -171,33 +169,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
     int32_t* s_kt = reinterpret_cast<int32_t*>(smem + C::OFF_KT);
     UnitInfo* s_unit = reinterpret_cast<UnitInfo*>(smem + C::OFF_UNIT);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
-    uint64_t* full = bars;                        // [STAGES]
-    uint64_t* empty = bars + C::STAGES;           // [STAGES]
-    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]
-    uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]
-    uint64_t* sfull = bars + 2 * C::STAGES + 4;   // [TC_SCHED]
-    uint64_t* sempty = sfull + TC_SCHED;          // [TC_SCHED]
-    uint64_t* afull = sempty + TC_SCHED;          // [TC_ASLOTS]
-    uint64_t* aempty = afull + TC_ASLOTS;         // [TC_ASLOTS]
+    uint64_t* full = bars;                        // [STAGES]  local: this CTA's copies landed
+    uint64_t* empty = bars + C::STAGES;           // [STAGES]  local: MMA commit (multicast) + own expanders
+    uint64_t* tfull = bars + 2 * C::STAGES;       // [2]       local: MMA commit (multicast)
+    uint64_t* tempty = bars + 2 * C::STAGES + 2;  // [2]       leader's is used: epilogue warps of both CTAs
+    uint64_t* sfull = bars + 2 * C::STAGES + 4;   // [TC_SCHED] local: written by the leader's scheduler
+    uint64_t* sempty = sfull + TC_SCHED;          // [TC_SCHED] leader's is used: ring consumers of both CTAs
+    uint64_t* afull = sempty + TC_SCHED;          // [TC_ASLOTS] leader's is used: expanders of both CTAs
+    uint64_t* aempty = afull + TC_ASLOTS;         // [TC_ASLOTS] local: MMA commit (multicast)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + TC_ASLOTS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1 + TC_EXP_WARPS);  // MMA commit + the expander warps (done reading the bit tiles)
+            mbar_init(&empty[s], 1 + TC_EXP_WARPS);  // MMA commit + own expander warps (done reading the bit tiles)
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tfull[b], 1);
-            mbar_init(&tempty[b], TC_EPI_WARPS);
+            mbar_init(&tempty[b], 2 * TC_EPI_WARPS);
         }
         for (int s = 0; s < TC_SCHED; ++s) {
             mbar_init(&sfull[s], 1);
-            mbar_init(&sempty[s], TC_EPI_WARPS + TC_EXP_WARPS + 1);
+            // consumers: leader MMA + peer producer + epilogue and expander warps of both CTAs
+            mbar_init(&sempty[s], 2 * (TC_EPI_WARPS + TC_EXP_WARPS) + 2);
         }
         for (int s = 0; s < TC_ASLOTS; ++s) {
-            mbar_init(&afull[s], TC_EXP_WARPS);
+            mbar_init(&afull[s], 2 * TC_EXP_WARPS);
             mbar_init(&aempty[s], 1);
         }
         mbar_fence_init();
@@ -212,50 +213,78 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
             lut[i] = v;
         }
     }
-    if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, 512);
+    if (warp == TC_MMA_WARP) tmem_alloc2(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();  // barrier inits of both CTAs are visible before any remote arrive
     tc_fence_after();
     const uint32_t tbase = *tmem_slot;
 
     const int n_units = p.n_rb * p.n_cg * p.q_chunks;
+    // leader-side addresses (shared::cluster) of the barriers the peer signals remotely
+    const uint32_t ld_sempty = mapa_u32(smem_u32(sempty), 0);
+    const uint32_t ld_afull = mapa_u32(smem_u32(afull), 0);
+    const uint32_t ld_tempty = mapa_u32(smem_u32(tempty), 0);
 
     if (warp == TC_PROD_WARP) {
-        // ------------------------------------------------------------ scheduler + producer
-        const size_t q_stride = static_cast<size_t>(p.n_cg) * p.n_kt * C::TILE_B;  // bytes between slots of one group
+        // ------------------------------------------------------------ scheduler (leader) + producer (both CTAs)
+        const size_t q_stride = static_cast<size_t>(p.n_cg) * p.n_kt * (2 * C::HALF_B);  // bytes between slots
         uint32_t stage = 0, phase = 0, uit = 0;
         long long pt_wait = 0, pt_fills = 0;
-        const long long pt_start = clock64();
+        const long long pt_start = PROF ? clock64() : 0;
         unsigned int next_u = 0;
-        if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);
-        next_u = __shfl_sync(0xffffffffu, next_u, 0);
+        if (leader) {
+            if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);
+            next_u = __shfl_sync(0xffffffffu, next_u, 0);
+        }
+        const uint32_t peer_unit = mapa_u32(smem_u32(s_unit), 1), peer_sfull = mapa_u32(smem_u32(sfull), 1);
         while (true) {
-            const int u = static_cast<int>(next_u);
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
-            mbar_wait(&sempty[sl], spar ^ 1u);
-            if (u >= n_units || static_cast<int>(next_u) < 0) {
-                if (lane == 0) {
-                    s_unit[sl].rb = -1;
-                    mbar_arrive(&sfull[sl]);
+            int rb, cg, q0, q1, t0, nfills;
+            if (leader) {
+                const int u = static_cast<int>(next_u);
+                mbar_wait_cluster(&sempty[sl], spar ^ 1u);
+                const bool stop = u >= n_units || u < 0;
+                if (!stop) {
+                    if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);  // consumed at the top of the next iteration
+                    decode_unit(p, u, rb, cg, q0, q1);
+                    t0 = p.tile_ptr[rb];
+                    nfills = (p.tile_ptr[rb + 1] - t0) / C::TPS;
+                } else {
+                    rb = -1;
+                    cg = q0 = q1 = t0 = nfills = 0;
                 }
-                break;
+                if (lane == 0) {
+                    UnitInfo inf;
+                    inf.rb = rb; inf.cg = cg; inf.q0 = q0; inf.q1 = q1; inf.t0 = t0; inf.nfills = nfills;
+                    inf.pad0 = inf.pad1 = 0;
+                    s_unit[sl] = inf;
+                    const uint32_t pu = peer_unit + sl * static_cast<uint32_t>(sizeof(UnitInfo));
+                    st_cluster_u32(pu + 0, static_cast<uint32_t>(rb));
+                    st_cluster_u32(pu + 4, static_cast<uint32_t>(cg));
+                    st_cluster_u32(pu + 8, static_cast<uint32_t>(q0));
+                    st_cluster_u32(pu + 12, static_cast<uint32_t>(q1));
+                    st_cluster_u32(pu + 16, static_cast<uint32_t>(t0));
+                    st_cluster_u32(pu + 20, static_cast<uint32_t>(nfills));
+                    mbar_arrive(&sfull[sl]);
+                    mbar_arrive_cluster(peer_sfull + sl * 8);
+                }
+                if (stop) break;
+            } else {
+                mbar_wait_cluster(&sfull[sl], spar);
+                rb = s_unit[sl].rb; cg = s_unit[sl].cg; q0 = s_unit[sl].q0; q1 = s_unit[sl].q1;
+                t0 = s_unit[sl].t0; nfills = s_unit[sl].nfills;
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(ld_sempty + sl * 8);
+                if (rb < 0) break;
             }
-            if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);  // consumed at the top of the next iteration
-            int rb, cg, q0, q1;
-            decode_unit(p, u, rb, cg, q0, q1);
-            const int t0 = p.tile_ptr[rb], nk = p.tile_ptr[rb + 1] - t0;
-            const int nfills = nk / C::TPS;
-            if (lane == 0) {
-                UnitInfo inf;
-                inf.rb = rb; inf.cg = cg; inf.q0 = q0; inf.q1 = q1; inf.t0 = t0; inf.nfills = nfills;
-                inf.pad0 = inf.pad1 = 0;
-                s_unit[sl] = inf;
-                mbar_arrive(&sfull[sl]);
-            }
+            const int nk = nfills * C::TPS;
             for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
             __syncwarp();
-            const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * C::TILE_B;
-            const uint64_t* const a_unit = p.a_bits + static_cast<size_t>(t0) * TC_ROWS;
+            // this CTA's half of every gathered tile and its own rows of the A bit tiles
+            const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * (2 * C::HALF_B) + rank * C::HALF_B;
+            const uint64_t* const a_unit =
+                p.a_bits + (static_cast<size_t>(t0 / C::TPS) * 2 + rank) * (C::TPS * TC_ROWS);
             for (int q = q0; q < q1 && !(p.dbg & 4); ++q) {
                 const int8_t* const b_q = b_cg + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
                 for (int f = 0; f < nfills; ++f) {
@@ -266,7 +295,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                         kts[t] = i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i];
                     }
                     TC_TIMED(KIND, pt_wait, mbar_wait(&empty[stage], phase ^ 1u));
-                    ++pt_fills;
+                    if (PROF) ++pt_fills;
                     if (elect_one()) {
                         if (p.dbg & 2) {
                             mbar_arrive(&full[stage]);
@@ -275,10 +304,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             uint8_t* const st = sB + stage * C::STAGE;
 #pragma unroll
                             for (int t = 0; t < C::TPS; ++t)
-                                bulk_g2s(st + t * C::TILE_B, b_q + static_cast<size_t>(kts[t]) * C::TILE_B, C::TILE_B,
-                                         &full[stage]);
-                            bulk_g2s(st + C::STAGE_B, a_unit + static_cast<size_t>(f) * (C::TPS * TC_ROWS), C::STAGE_A,
-                                     &full[stage]);
+                                bulk_g2s(st + t * C::HALF_B, b_q + static_cast<size_t>(kts[t]) * (2 * C::HALF_B),
+                                         C::HALF_B, &full[stage]);
+                            bulk_g2s(st + C::STAGE_B, a_unit + static_cast<size_t>(f) * (2 * C::TPS * TC_ROWS),
+                                     C::STAGE_A, &full[stage]);
                         }
                     }
                     __syncwarp();
@@ -288,10 +317,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                     }
                 }
             }
-            next_u = __shfl_sync(0xffffffffu, next_u, 0);
+            if (leader) next_u = __shfl_sync(0xffffffffu, next_u, 0);
             ++uit;
         }
-        if (p.prof && lane == 0) {
+        if (PROF && leader && lane == 0) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 0), clock64() - pt_start);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 1), pt_wait);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), pt_fills);
@@ -302,24 +331,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         const int quarter = warp - TC_EXP_WARP0;
         const int r = quarter * 32 + lane;
         const uint32_t t_lane = tbase + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t lane_lut = smem_u32(smem + C::OFF_LUT) + (lane % TC_LUT_REP) * 8;
         uint32_t aslot = 0, aphase = 0, stage = 0, phase = 0, uit = 0;
-        long long xt_wait = 0, xt_st = 0;
-        const long long xt_start = clock64();
+        long long xt_wait = 0, xt_st = 0, xt_full = 0;
+        const long long xt_start = PROF ? clock64() : 0;
         while (true) {
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
-            mbar_wait(&sfull[sl], spar);
-            const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, t0 = s_unit[sl].t0,
-                      nfills = s_unit[sl].nfills;
+            mbar_wait_cluster(&sfull[sl], spar);
+            const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, nfills = s_unit[sl].nfills;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[sl]);
+            if (lane == 0) {
+                if (leader)
+                    mbar_arrive(&sempty[sl]);
+                else
+                    mbar_arrive_cluster(ld_sempty + sl * 8);
+            }
             ++uit;
             if (rb < 0) break;
-            const uint32_t lut_addr = smem_u32(smem + C::OFF_LUT) + (lane % TC_LUT_REP) * 8;
-            (void)t0;
+            // Software pipeline over half fills: the TMEM store of half h is in flight while half h+1 is expanded
+            // (table lookups), so neither the tcgen05.st latency nor the lookups sit on the critical path alone.
+            auto publish = [&](uint32_t slot) {   // the store into `slot` was issued earlier
+                tmem_st_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader)
+                        mbar_arrive(&afull[slot]);
+                    else
+                        mbar_arrive_cluster_relaxed(ld_afull + slot * 8);
+                }
+            };
+            bool pending = false;
+            uint32_t pending_slot = 0;
             for (int q = q0; q < q1 && !(p.dbg & 4); ++q) {
                 for (int f = 0; f < nfills; ++f) {
                     // the bit tiles of this fill arrive in the smem stage together with the gathered operand
-                    mbar_wait(&full[stage], phase);
+                    TC_TIMED(KIND, xt_full, mbar_wait(&full[stage], phase));
                     const uint64_t* const sbits =
                         reinterpret_cast<const uint64_t*>(sB + stage * C::STAGE + C::STAGE_B) + r;
                     uint64_t w[C::TPS];
@@ -335,18 +382,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                     for (int h = 0; h < C::TPS / TC_APS; ++h) {
                         uint32_t e[TC_APS][16];
 #pragma unroll
-                        for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], lut_addr, e[t]);
+                        for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], lane_lut, e[t]);
+                        if (pending) publish(pending_slot);
                         TC_TIMED(KIND, xt_wait, mbar_wait(&aempty[aslot], aphase ^ 1u));
                         tc_fence_after();
                         const uint32_t ta = t_lane + tc_acol(aslot);
-                        const long long st0 = p.prof ? clock64() : 0;
 #pragma unroll
                         for (int t = 0; t < TC_APS; ++t) tmem_st16(ta + t * 16, e[t]);
-                        tmem_st_wait();
-                        if (p.prof) xt_st += clock64() - st0;
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&afull[aslot]);
+                        pending = true;
+                        pending_slot = aslot;
                         if (++aslot == TC_ASLOTS) {
                             aslot = 0;
                             aphase ^= 1u;
@@ -354,78 +398,80 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                     }
                 }
             }
+            if (pending) publish(pending_slot);  // nothing follows in this unit: do not hold the MMA warp back
         }
-        if (p.prof && warp == TC_EXP_WARP0 && lane == 0) {
+        if (PROF && leader && warp == TC_EXP_WARP0 && lane == 0) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 2), clock64() - xt_start);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 3), xt_wait);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 11), xt_st);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 12), xt_full);
         }
     } else if (warp == TC_MMA_WARP) {
-        // ------------------------------------------------------------ MMA issuer (warp-uniform, one elected lane)
-        const uint32_t idesc = idesc_i8(TC_ROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0, /*b MN*/ 1);
-        const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo);
-        const uint32_t b_ks = p.b_kstep >> 4;
-        uint32_t stage = 0, phase = 0, aslot = 0, aphase = 0, acc_it = 0, uit = 0;
-        long long mt_wa = 0, mt_wb = 0, mt_wt = 0;
-        const long long mt_start = clock64();
-        while (true) {
-            const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
-            mbar_wait(&sfull[sl], spar);
-            const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, nfills = s_unit[sl].nfills;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[sl]);
-            if (rb < 0) break;
-            for (int q = q0; q < q1; ++q) {
-                // accumulations issued so far: buffer = acc_it & 1, barrier phase = (acc_it >> 1) & 1
-                const uint32_t buf = acc_it & 1u;
-                TC_TIMED(KIND, mt_wt, mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u));
-                const uint32_t d_tmem = tbase + buf * 256;
-                for (int f = 0; f < nfills; ++f) {
-                    // no wait on full[stage]: the expanders pass it before they publish the first A slot of the fill
-                    const uint64_t b_st = b_desc0 + stage * (C::STAGE >> 4);
+        // ------------------------------------------------------------ MMA issuer (leader only; one elected lane)
+        if (leader) {
+            const uint32_t idesc = idesc_i8(TC_PROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0, /*b MN*/ 1);
+            const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo);
+            const uint32_t b_ks = p.b_kstep >> 4;
+            uint32_t stage = 0, aslot = 0, aphase = 0, acc_it = 0, uit = 0;
+            long long mt_wa = 0, mt_wt = 0;
+            const long long mt_start = PROF ? clock64() : 0;
+            while (true) {
+                const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+                mbar_wait(&sfull[sl], spar);
+                const int rb = s_unit[sl].rb, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1, nfills = s_unit[sl].nfills;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sempty[sl]);
+                if (rb < 0) break;
+                for (int q = q0; q < q1; ++q) {
+                    // accumulations issued so far: buffer = acc_it & 1, barrier phase = (acc_it >> 1) & 1
+                    const uint32_t buf = acc_it & 1u;
+                    TC_TIMED(KIND, mt_wt, mbar_wait(&tempty[buf], ((acc_it >> 1) & 1u) ^ 1u));
+                    const uint32_t d_tmem = tbase + buf * 256;
+                    for (int f = 0; f < nfills; ++f) {
+                        // no wait on full[stage]: the expanders of both CTAs pass their full[stage] before they
+                        // publish the first A slot of the fill
+                        const uint64_t b_st = b_desc0 + stage * (C::STAGE >> 4);
 #pragma unroll
-                    for (int h = 0; h < C::TPS / TC_APS; ++h) {
-                        if (!(p.dbg & 4)) TC_TIMED(KIND, mt_wa, mbar_wait(&afull[aslot], aphase));
-                        tc_fence_after();
-                        if (elect_one()) {
-                            if (!(p.dbg & 1)) {
-                                // A: TMEM slot, 8 columns per K=32 MMA.  B: MN-major smem, four 8-row K groups per MMA
-                                const uint32_t a_t = tbase + tc_acol(aslot);
+                        for (int h = 0; h < C::TPS / TC_APS; ++h) {
+                            if (!(p.dbg & 4)) TC_TIMED(KIND, mt_wa, mbar_wait(&afull[aslot], aphase));
+                            tc_fence_after();
+                            if (elect_one()) {
+                                if (!(p.dbg & 1)) {
+                                    // A: TMEM slot (same address in both CTAs), 8 columns per K=32 MMA.
+                                    // B: MN-major smem half tiles, four 8-row K groups per MMA
+                                    const uint32_t a_t = tbase + tc_acol(aslot);
 #pragma unroll
-                                for (int t = 0; t < TC_APS; ++t) {
+                                    for (int t = 0; t < TC_APS; ++t) {
 #pragma unroll
-                                    for (int ks = 0; ks < TC_KT / 32; ++ks)
-                                        mma_i8_ts(d_tmem, a_t + t * 16 + ks * 8,
-                                                  b_st + ((h * TC_APS + t) * (C::TILE_B >> 4) + ks * b_ks), idesc,
-                                                  (f | h | t | ks) != 0);
+                                        for (int ks = 0; ks < TC_KT / 32; ++ks)
+                                            mma_i8_ts2(d_tmem, a_t + t * 16 + ks * 8,
+                                                       b_st + ((h * TC_APS + t) * (C::HALF_B >> 4) + ks * b_ks), idesc,
+                                                       (f | h | t | ks) != 0);
+                                    }
+                                }
+                                if (!(p.dbg & 4)) mma_commit2(&aempty[aslot]);
+                                if (h == C::TPS / TC_APS - 1) {
+                                    if (!(p.dbg & 4)) mma_commit2(&empty[stage]);
+                                    if (f == nfills - 1) mma_commit2(&tfull[buf]);
                                 }
                             }
-                            if (!(p.dbg & 4)) mma_commit(&aempty[aslot]);
-                            if (h == C::TPS / TC_APS - 1) {
-                                if (!(p.dbg & 4)) mma_commit(&empty[stage]);
-                                if (f == nfills - 1) mma_commit(&tfull[buf]);
+                            __syncwarp();
+                            if (++aslot == TC_ASLOTS) {
+                                aslot = 0;
+                                aphase ^= 1u;
                             }
                         }
-                        __syncwarp();
-                        if (++aslot == TC_ASLOTS) {
-                            aslot = 0;
-                            aphase ^= 1u;
-                        }
+                        if (++stage == C::STAGES) stage = 0;
                     }
-                    if (++stage == C::STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    ++acc_it;
                 }
-                ++acc_it;
+                ++uit;
             }
-            ++uit;
-        }
-        if (p.prof && lane == 0) {
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 4), clock64() - mt_start);
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 5), mt_wa);
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 6), mt_wb);
-            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 7), mt_wt);
+            if (PROF && lane == 0) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 4), clock64() - mt_start);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 5), mt_wa);
+                atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 7), mt_wt);
+            }
         }
     } else {
         // ------------------------------------------------------------ epilogue: TMEM -> compare -> counts
@@ -435,16 +481,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
         const int c0 = half * 32;
         uint32_t acc_it = 0, uit = 0;
         long long et_wait = 0;
-        const long long et_start = clock64();
+        const long long et_start = PROF ? clock64() : 0;
         while (true) {
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
-            mbar_wait(&sfull[sl], spar);
+            mbar_wait_cluster(&sfull[sl], spar);
             const int rb = s_unit[sl].rb, cg = s_unit[sl].cg, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1;
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sempty[sl]);
+            if (lane == 0) {
+                if (leader)
+                    mbar_arrive(&sempty[sl]);
+                else
+                    mbar_arrive_cluster(ld_sempty + sl * 8);
+            }
             ++uit;
             if (rb < 0) break;
-            const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + row_in_tile;
+            const int64_t row = static_cast<int64_t>(rb) * TC_PROWS + rank * TC_ROWS + row_in_tile;
             const bool row_ok = row < p.n;
             // counts, bands and fix-ups are addressed by the caller's node id
             const int64_t node = (row_ok && p.node_of_row) ? p.node_of_row[row] : row;
@@ -498,7 +549,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                             if (q == q1 - 1) {  // rate probe: only the last accumulation of a unit is stored
 #pragma unroll
                                 for (int d = 0; d < D; ++d)
-                                    p.raw_out[row_in_tile * C::NCOLS + d * 64 + c] = static_cast<int32_t>(acc[d][x]);
+                                    p.raw_out[(rank * TC_ROWS + row_in_tile) * C::NCOLS + d * 64 + c] =
+                                        static_cast<int32_t>(acc[d][x]);
                             }
                         } else if (KIND == TCK_STORE) {
                             long long S = static_cast<int32_t>(acc[0][x]);
@@ -561,7 +613,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[buf]);
+                if (lane == 0) {
+                    if (leader)
+                        mbar_arrive(&tempty[buf]);
+                    else
+                        mbar_arrive_cluster_relaxed(ld_tempty + buf * 8);
+                }
                 ++acc_it;
                 if (KIND == TCK_COUNT) {
                     if (!(p.mode & TCM_COUNT)) {
@@ -606,23 +663,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
                 }
             }
         }
-        if (p.prof && warp == 0 && lane == 0) {
+        if (PROF && leader && warp == 0 && lane == 0) {
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 8), clock64() - et_start);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 9), et_wait);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_MMA_WARP) tmem_dealloc(tbase, 512);
+    cluster_sync_all();  // no remote arrive or multicast commit may target a CTA that has already exited
+    if (warp == TC_MMA_WARP) tmem_dealloc2(tbase, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ operand builders
-// occupancy of 128 x 64 tiles of the packed matrix; one block per row block
+// occupancy of 256 x 64 tiles of the packed matrix; one block per row block (= rows of one CTA pair)
 __global__ void __launch_bounds__(256) k_tile_occ(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
                                                   int32_t n_kt, uint8_t* __restrict__ occ,
                                                   int32_t* __restrict__ rb_count) {
     const int rb = blockIdx.x;
-    const int64_t r0 = static_cast<int64_t>(rb) * TC_ROWS, r1 = min(n, r0 + TC_ROWS);
+    const int64_t r0 = static_cast<int64_t>(rb) * TC_PROWS, r1 = min(n, r0 + TC_PROWS);
     __shared__ int s_total;
     if (threadIdx.x == 0) s_total = 0;
     __syncthreads();
@@ -688,25 +746,29 @@ __global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ o
     }
 }
 
-// the 128 x 64 bit block of every stored tile as one 64-bit word per row (padding tiles and rows are zero)
+// the 256 x 64 bit block of every stored tile as one 64-bit word per row (padding tiles and rows are zero), laid
+// out so that the 128 rows one CTA needs for one fill (TC_TPS consecutive tiles) are contiguous:
+//   out[((tile / TPS) * 2 + rank) * TPS + tile % TPS][r],  rank = row / 128, r = row % 128
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
                                                     const int32_t* __restrict__ tile_kt,
                                                     const int32_t* __restrict__ tile_rb, int64_t n_tiles,
                                                     uint64_t* __restrict__ out) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    if (idx >= n_tiles * TC_ROWS) return;
-    const int64_t tile = idx / TC_ROWS;
-    const int r = static_cast<int>(idx % TC_ROWS);
+    if (idx >= n_tiles * TC_PROWS) return;
+    const int64_t tile = idx / TC_PROWS;
+    const int r256 = static_cast<int>(idx % TC_PROWS);
     const int kt = tile_kt[tile], rb = tile_rb[tile];
     uint64_t w = 0;
     if (rb >= 0) {
-        const int64_t row = static_cast<int64_t>(rb) * TC_ROWS + r;
+        const int64_t row = static_cast<int64_t>(rb) * TC_PROWS + r256;
         if (row < n) {
             const uint2 v = *reinterpret_cast<const uint2*>(words + row * ld + 2 * kt);
             w = static_cast<uint64_t>(v.x) | (static_cast<uint64_t>(v.y) << 32);
         }
     }
-    out[idx] = w;
+    const int64_t g = tile / TC_TPS, t = tile % TC_TPS;
+    const int rank = r256 / TC_ROWS, r = r256 % TC_ROWS;
+    out[(((g * 2 + rank) * TC_TPS) + t) * TC_ROWS + r] = w;
 }
 
 // per-column exponent range of nan0(B): kmax = exponent of the largest magnitude, lmin = exponent of the lowest
@@ -767,8 +829,9 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
     }
 }
 
-// Bcat tiles for a batch: tile (slot, kt) = 64 K-rows x 64*D columns in MN-major core-matrix order:
-//   16-byte chunk index ch = kg * (NC16*8) + nc * 8 + r   (k = kg*8 + r, columns nc*16 .. nc*16+15)
+// Bcat tiles for a batch: tile (slot, kt) = 64 K-rows x 64*D columns, stored as two halves of 32*D columns (one per
+// CTA of a pair), each in MN-major core-matrix order.  With k = kg*8 + r and 16-column chunk nc (columns nc*16 ..):
+//   half = nc / (NC16/2),   16-byte chunk index inside the half = kg * (NC16/2 * 8) + (nc % (NC16/2)) * 8 + r
 // column nc*16+x of the tile = digit plane (nc / 4), attribute/permutation column c = (nc & 3) * 16 + x.
 template <int D>
 __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digits, const int32_t* __restrict__ perm,
@@ -807,7 +870,8 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digit
                 v = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        dst[ch] = v;
+        constexpr int HC = NC16 / 2;  // 16-column chunks per half
+        dst[(nc / HC) * (TC_KT * HC) + kg * (HC * 8) + (nc % HC) * 8 + r] = v;
     }
 }
 
@@ -851,34 +915,38 @@ static void print_prof(sb_ctx* ctx, const long long* d_prof, const char* what) {
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     const double fills = std::max<double>(1.0, static_cast<double>(h[10]));
     fprintf(stderr,
-            "[sb_trace] %s: cycles per fill (%d k-tiles): producer %.0f (wait empty %.0f) | expander %.0f (wait aempty "
-            "%.0f, tmem st %.0f) | mma %.0f (wait A %.0f, wait B %.0f, wait tempty %.0f) | epilogue %.0f (wait "
+            "[sb_trace] %s: cycles per fill (%d k-tiles): producer %.0f (wait empty %.0f) | expander %.0f (wait full "
+            "%.0f, wait aempty %.0f, tmem st %.0f) | mma %.0f (wait A %.0f, wait tempty %.0f) | epilogue %.0f (wait "
             "tfull %.0f)\n",
-            what, TC_TPS, h[0] / fills, h[1] / fills, h[2] / fills, h[3] / fills, h[11] / fills, h[4] / fills,
-            h[5] / fills, h[6] / fills, h[7] / fills, h[8] / fills, h[9] / fills);
+            what, TC_TPS, h[0] / fills, h[1] / fills, h[2] / fills, h[12] / fills, h[3] / fills, h[11] / fills,
+            h[4] / fills, h[5] / fills, h[7] / fills, h[8] / fills, h[9] / fills);
 }
 
-template <int D, int KIND, bool SMALL_M>
+template <int D, int KIND, bool SMALL_M, bool PROF>
 static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
     using C = TcCfg<D>;
     static bool configured = false;
     if (!configured) {
-        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM));
         configured = true;
     }
     KernelTimer kt(ctx, SB_K_GEMM);
-    k_gemm<D, KIND, SMALL_M><<<grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
+    // `grid` counts CTA pairs; the kernel carries __cluster_dims__(2, 1, 1)
+    k_gemm<D, KIND, SMALL_M, PROF><<<2 * grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
     SB_LAUNCH_CHECK(ctx);
 }
 
-template <int D>
+template <int D, bool PROF>
 static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams& gp, int grid) {
     if (kind == TCK_RAW)
-        launch_gemm<D, TCK_RAW, false>(ctx, gp, grid);
+        launch_gemm<D, TCK_RAW, false, PROF>(ctx, gp, grid);
     else if (kind == TCK_STORE)
-        small_m ? launch_gemm<D, TCK_STORE, true>(ctx, gp, grid) : launch_gemm<D, TCK_STORE, false>(ctx, gp, grid);
+        small_m ? launch_gemm<D, TCK_STORE, true, false>(ctx, gp, grid)
+                : launch_gemm<D, TCK_STORE, false, false>(ctx, gp, grid);
     else
-        small_m ? launch_gemm<D, TCK_COUNT, true>(ctx, gp, grid) : launch_gemm<D, TCK_COUNT, false>(ctx, gp, grid);
+        small_m ? launch_gemm<D, TCK_COUNT, true, PROF>(ctx, gp, grid)
+                : launch_gemm<D, TCK_COUNT, false, PROF>(ctx, gp, grid);
 }
 
 static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid) {
@@ -892,12 +960,21 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
     SB_CUDA(cudaMemsetAsync(gp.unit_counter, 0, sizeof(unsigned int), ctx->stream));
     const int kind = (gp.mode & TCM_RAW) ? TCK_RAW : (gp.mode & TCM_STORE) ? TCK_STORE : TCK_COUNT;
     const bool small_m = gp.mpad < 64;
+    if (gp.prof) {  // cycle accounting compiled in (SB_TRACE / rate probe)
+        if (D == 1)
+            launch_gemm_k<1, true>(ctx, kind, small_m, gp, grid);
+        else if (D == 2)
+            launch_gemm_k<2, true>(ctx, kind, small_m, gp, grid);
+        else
+            launch_gemm_k<3, true>(ctx, kind, small_m, gp, grid);
+        return;
+    }
     if (D == 1)
-        launch_gemm_k<1>(ctx, kind, small_m, gp, grid);
+        launch_gemm_k<1, false>(ctx, kind, small_m, gp, grid);
     else if (D == 2)
-        launch_gemm_k<2>(ctx, kind, small_m, gp, grid);
+        launch_gemm_k<2, false>(ctx, kind, small_m, gp, grid);
     else
-        launch_gemm_k<3>(ctx, kind, small_m, gp, grid);
+        launch_gemm_k<3, false>(ctx, kind, small_m, gp, grid);
 }
 
 static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
@@ -941,10 +1018,10 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.flag_cap = pl->flag_cap;
     gp.cpk = ctx->ws_cpk.p;
     const uint32_t ncols = 64u * pl->D;
-    gp.b_lbo = ncols * 8;  // MN-major B: stride between 8-row K groups
+    gp.b_lbo = ncols / 2 * 8;  // MN-major B half tile: stride between 8-row K groups
     gp.b_sbo = 128;        //             stride between 16-column chunks
     gp.q_wrap = INT_MAX;
-    gp.b_kstep = 4 * ncols * 8;
+    gp.b_kstep = 4 * (ncols / 2) * 8;
     return gp;
 }
 
@@ -975,7 +1052,7 @@ static TcPlan* build_plan(sb_enrich* e) {
             pl->n_cg = 1;
             pl->pps = static_cast<int32_t>(64 / pl->mpad);
         }
-        pl->n_rb = static_cast<int32_t>(sb_ceil_div(n, TC_ROWS));
+        pl->n_rb = static_cast<int32_t>(sb_ceil_div(n, TC_PROWS));
         pl->n_kt = static_cast<int32_t>(sb_ceil_div(n, TC_KT));
 
         // the epilogue compares in int32 (score = hi * 256 + lo): needs n_i * 2^(8D-2) < 2^38
@@ -1015,12 +1092,12 @@ static TcPlan* build_plan(sb_enrich* e) {
         pl->tile_ptr.reserve(pl->n_rb + 1);
         pl->tile_kt.reserve(run);
         pl->tile_rb.reserve(run);
-        pl->a_bits.reserve(static_cast<size_t>(run) * TC_ROWS);
+        pl->a_bits.reserve(static_cast<size_t>(run) * TC_PROWS);
         SB_CUDA(cudaMemcpyAsync(pl->tile_ptr.p, h_ptr.data(), (pl->n_rb + 1) * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, st));
         k_tile_list<<<pl->n_rb, 256, 0, st>>>(occ.p, pl->n_kt, pl->tile_ptr.p, pl->tile_kt.p, pl->tile_rb.p);
         SB_LAUNCH_CHECK(ctx);
-        k_pack_tiles<<<static_cast<unsigned>(sb_ceil_div(run * TC_ROWS, 256)), 256, 0, st>>>(
+        k_pack_tiles<<<static_cast<unsigned>(sb_ceil_div(run * TC_PROWS, 256)), 256, 0, st>>>(
             e->a->words, n, e->a->ld, pl->tile_kt.p, pl->tile_rb.p, run, pl->a_bits.p);
         SB_LAUNCH_CHECK(ctx);
 
@@ -1098,7 +1175,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         delete tr;
         tr = new PhaseTrace(ctx, "tc.plan.alloc_flags");
         // ---- flag list (capacity >= one slot's worst case so that overflow recovery always terminates)
-        const int64_t worst_slot = static_cast<int64_t>(pl->n_rb) * TC_ROWS * 64 * (pl->mpad >= 64 ? pl->n_cg : 1);
+        const int64_t worst_slot = static_cast<int64_t>(pl->n_rb) * TC_PROWS * 64 * (pl->mpad >= 64 ? pl->n_cg : 1);
         pl->flag_cap = static_cast<unsigned int>(std::min<int64_t>(std::max<int64_t>(4ll << 20, worst_slot), 1ll << 31));
         ctx->ws_flag_ij.reserve(pl->flag_cap);
         ctx->ws_flag_p.reserve(pl->flag_cap);
@@ -1111,7 +1188,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
         const int64_t slots1 = slots_for(pl, 1);
         ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
-        pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_ROWS * pl->mpad);
+        pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_PROWS * pl->mpad);
         launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1);
         GemmParams gp = base_params(e, pl);
         gp.mode = TCM_STORE;
@@ -1120,7 +1197,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         gp.q_per = 1;
         gp.batch_perms = 1;
         const int units = pl->n_rb * pl->n_cg;
-        launch_gemm_d(ctx, D, gp, std::min(units, ctx->num_sms));
+        launch_gemm_d(ctx, D, gp, std::min(units, ctx->num_sms / 2));
         SB_CUDA(cudaStreamSynchronize(st));
         delete tr;
     } catch (...) {
@@ -1141,19 +1218,19 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
     // operand slab that the band touches for one (q chunk, column group) is kept to <= ~16 MB, so the two or three
     // slabs that the dynamically scheduled CTAs work on at any time stay in the 126 MB L2 together with the band.
     const double tile_b = static_cast<double>(TC_KT) * 64 * pl->D;
-    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_ROWS * 8 / pl->n_rb;
+    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_PROWS * 8 / pl->n_rb;
     int band = static_cast<int>(std::max(1.0, (32 << 20) / a_per_rb));
-    band = std::max(band, std::min(pl->n_rb, ctx->num_sms));
+    band = std::max(band, std::min(pl->n_rb, ctx->num_sms / 2));
     band = std::min(band, static_cast<int>(pl->n_rb));
     gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, band));
     gp.band_rb = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.n_bands));
     gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.band_rb));
-    const double touched = std::min(1.0, 3.0 * gp.band_rb * TC_ROWS / static_cast<double>(pl->n));
+    const double touched = std::min(1.0, 3.0 * gp.band_rb * TC_PROWS / static_cast<double>(pl->n));
     const double slab = pl->n_kt * tile_b * touched;
     int q_per = static_cast<int>(std::max(1.0, std::min(16.0, (16 << 20) / slab)));
     // enough units to keep every SM busy with a few units each
     const int base_units = pl->n_rb * pl->n_cg;
-    const int want_chunks = static_cast<int>(sb_ceil_div(4 * ctx->num_sms, base_units));
+    const int want_chunks = static_cast<int>(sb_ceil_div(4 * (ctx->num_sms / 2), base_units));
     q_per = std::min<int>(q_per, std::max<int>(1, q_total / std::max(1, want_chunks)));
     q_per = std::max(1, std::min(q_per, q_total));
     gp.q_per = q_per;
@@ -1169,7 +1246,7 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
         fprintf(stderr, "[sb_trace] gemm schedule: n_rb %d n_cg %d q_total %d q_per %d band_rb %d n_bands %d units %lld\n",
                 pl->n_rb, pl->n_cg, q_total, gp.q_per, gp.band_rb, gp.n_bands, (long long)units);
     }
-    launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms)));
+    launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms / 2)));
     if (trace) print_prof(ctx, d_prof.p, "batch gemm");
 }
 
@@ -1259,7 +1336,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
                 // batch-local permutation index of column block q is recovered by offsetting perm instead
                 gp.batch_perms = static_cast<int32_t>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
                 if (pl->mpad >= 64) gp.batch_perms = 1;
-                launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms));
+                launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms / 2));
                 ktile_iters += tiles_per_pass;
                 const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
                 fixup_flags(e, perm_q, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
@@ -1296,23 +1373,27 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     const int D = ncols / 64;
     const int K = ktiles * TC_KT;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
-    // host-side tiling into the production layouts; A is a 0/1 matrix (any non-zero entry counts as 1)
+    // host-side tiling into the production layouts; A is a 0/1 matrix (any non-zero entry counts as 1) and is given
+    // to BOTH CTAs of the pair (rows 0..127 and 128..255 of the unit), which must produce the same product
     const int kt_pad = static_cast<int>(sb_ceil_div(ktiles, TC_TPS) * TC_TPS);  // padding tiles of A are all zero
-    std::vector<uint64_t> at(static_cast<size_t>(kt_pad) * TC_ROWS, 0);
+    std::vector<uint64_t> at(static_cast<size_t>(kt_pad) * TC_PROWS, 0);
     std::vector<int8_t> bt(static_cast<size_t>(ktiles) * tile_b);
     for (int kt = 0; kt < ktiles; ++kt)
         for (int r = 0; r < TC_ROWS; ++r) {
             uint64_t w = 0;
             for (int k = 0; k < TC_KT; ++k)
                 if (a_host[static_cast<size_t>(r) * K + kt * TC_KT + k]) w |= 1ull << k;
-            at[static_cast<size_t>(kt) * TC_ROWS + r] = w;
+            for (int rank = 0; rank < 2; ++rank)
+                at[((static_cast<size_t>(kt / TC_TPS) * 2 + rank) * TC_TPS + kt % TC_TPS) * TC_ROWS + r] = w;
         }
-    const int nc16 = ncols / 16;
+    const int hc = ncols / 32;  // 16-column chunks per half tile
     for (int kt = 0; kt < ktiles; ++kt)
         for (int k = 0; k < TC_KT; ++k)
-            for (int c = 0; c < ncols; ++c)
-                bt[static_cast<size_t>(kt) * tile_b + (k >> 3) * (nc16 * 128) + (c >> 4) * 128 + (k & 7) * 16 + (c & 15)] =
-                    b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
+            for (int c = 0; c < ncols; ++c) {
+                const int nc = c >> 4;
+                bt[static_cast<size_t>(kt) * tile_b + (nc / hc) * (tile_b / 2) + (k >> 3) * (hc * 128) + (nc % hc) * 128 +
+                   (k & 7) * 16 + (c & 15)] = b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
+            }
     std::vector<int32_t> ptr = {0, kt_pad}, kts(kt_pad);
     for (int i = 0; i < kt_pad; ++i) kts[i] = std::min(i, ktiles - 1);
     DevBuf<uint64_t> d_a;
@@ -1322,13 +1403,13 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     d_b.reserve(bt.size());
     d_ptr.reserve(2);
     d_kt.reserve(kt_pad);
-    d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
+    d_out.reserve(static_cast<size_t>(TC_PROWS) * ncols);
     cudaStream_t st = ctx->stream;
     SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_b.p, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), kt_pad * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    SB_CUDA(cudaMemsetAsync(d_out.p, 0xff, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t), st));
+    SB_CUDA(cudaMemsetAsync(d_out.p, 0xff, static_cast<size_t>(TC_PROWS) * ncols * sizeof(int32_t), st));
     GemmParams gp{};
     gp.a_bits = d_a.p;
     gp.tile_ptr = d_ptr.p;
@@ -1341,21 +1422,26 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     gp.q_chunks = 1;
     gp.q_per = 1;
     gp.mode = TCM_RAW;
-    gp.n = TC_ROWS;
+    gp.n = TC_PROWS;
     gp.m = 64;
     gp.mpad = 64;
     gp.pps = 1;
     gp.batch_perms = 1;
     gp.raw_out = d_out.p;
-    gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
+    gp.b_lbo = static_cast<uint32_t>(ncols) / 2 * 8;
     gp.b_sbo = 128;
     gp.q_wrap = INT_MAX;
-    gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
+    gp.b_kstep = 4 * (static_cast<uint32_t>(ncols) / 2) * 8;
     if (variant & 2) std::swap(gp.b_lbo, gp.b_sbo);  // deliberately wrong descriptor (negative control)
     launch_gemm_d(ctx, D, gp, 1);
-    SB_CUDA(cudaMemcpyAsync(d_host, d_out.p, static_cast<size_t>(TC_ROWS) * ncols * sizeof(int32_t),
-                            cudaMemcpyDeviceToHost, st));
+    std::vector<int32_t> both(static_cast<size_t>(TC_PROWS) * ncols);
+    SB_CUDA(cudaMemcpyAsync(both.data(), d_out.p, both.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    const size_t half_elems = static_cast<size_t>(TC_ROWS) * ncols;
+    memcpy(d_host, both.data(), half_elems * sizeof(int32_t));
+    if (!(variant & 2))
+        SB_CHECK(memcmp(both.data(), both.data() + half_elems, half_elems * sizeof(int32_t)) == 0,
+                 "sb_selftest_mma_i8: the two CTAs of the pair disagree");
     SB_API_END
 }
 
@@ -1375,13 +1461,13 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     DevBuf<uint64_t> d_a;
     DevBuf<int8_t> d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
-    d_a.reserve(static_cast<size_t>(ktiles) * TC_ROWS);
+    d_a.reserve(static_cast<size_t>(ktiles) * TC_PROWS);
     d_b.reserve(static_cast<size_t>(ktiles) * tile_b);
     d_ptr.reserve(2);
     d_kt.reserve(ktiles);
-    d_out.reserve(static_cast<size_t>(TC_ROWS) * ncols);
+    d_out.reserve(static_cast<size_t>(TC_PROWS) * ncols);
     cudaStream_t st = ctx->stream;
-    SB_CUDA(cudaMemsetAsync(d_a.p, 0x55, static_cast<size_t>(ktiles) * TC_ROWS * sizeof(uint64_t), st));
+    SB_CUDA(cudaMemsetAsync(d_a.p, 0x55, static_cast<size_t>(ktiles) * TC_PROWS * sizeof(uint64_t), st));
     SB_CUDA(cudaMemsetAsync(d_b.p, 1, static_cast<size_t>(ktiles) * tile_b, st));
     std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
     for (int i = 0; i < ktiles; ++i) kts[i] = i;
@@ -1397,20 +1483,21 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     gp.n_rb = 1;
     gp.n_cg = 1;
     gp.q_per = slots;
-    gp.q_chunks = grid;
-    gp.q_total = slots * grid;
+    gp.q_chunks = std::max(1, grid / 2);
+    gp.q_total = slots * gp.q_chunks;
     gp.q_wrap = 1;
     gp.dbg = dbg;
     gp.mode = TCM_RAW;
-    gp.n = TC_ROWS;
+    gp.n = TC_PROWS;
     gp.m = 64;
     gp.mpad = 64;
     gp.pps = 1;
     gp.batch_perms = 1;
     gp.raw_out = d_out.p;
-    gp.b_lbo = static_cast<uint32_t>(ncols) * 8;
+    gp.b_lbo = static_cast<uint32_t>(ncols) / 2 * 8;
     gp.b_sbo = 128;
-    gp.b_kstep = 4 * static_cast<uint32_t>(ncols) * 8;
+    gp.b_kstep = 4 * (static_cast<uint32_t>(ncols) / 2) * 8;
+    grid = std::max(1, grid / 2);  // CTA pairs
     if (desc_override) {  // speed-only experiments with other descriptor fields (results are not checked)
         gp.b_lbo = desc_override[0];
         gp.b_sbo = desc_override[1];

@@ -46,7 +46,11 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock + throttle reasons sampled every 100 ms while the timed region runs.
+
+    NVML is read in-process (pynvml): an `nvidia-smi -lms` child polling the same fields was measured to stall CUDA
+    memory-management calls of the benchmarked process for tens of milliseconds per query.  nvidia-smi remains the
+    fallback when pynvml is unavailable."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -55,22 +59,74 @@ class ClockSampler:
         self.idx = device_index
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.nvml = None
+        self.how = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if visible:
+                try:
+                    phys = int(visible.split(",")[self.idx])
+                except (ValueError, IndexError):
+                    phys = self.idx
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.QUERY,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nvml
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        try:
+            smax = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            smax = None
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                mask = get_reasons(self.handle)
+                self.samples.append((float(sm), smax, {k for k, bit in names.items() if mask & bit}))
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.1)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = [x[0] for x in self.samples]
+            smax = [x[1] for x in self.samples if x[1]]
+            reasons = set().union(*[x[2] for x in self.samples]) if self.samples else set()
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -94,13 +150,14 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------ workload
 def build_workload(args):
     from safepy_b200 import synthetic as syn
-    cfg = syn.make_config(args.workload, args.scale)
+    # nodes are renumbered randomly: the input order carries no locality, the library gets its hint from the layout
+    cfg = syn.make_config(args.workload, args.scale, shuffle=True)
     if args.perms:
         cfg["perms"] = args.perms
     if cfg["perms"] <= 0:
@@ -222,6 +279,11 @@ def run_ours(args):
     t0 = time.perf_counter()
     rows_all = make_perm_rows(attrs, P, 7)
     t_rng = time.perf_counter() - t0
+    # locality hint, computed from the layout exactly as SAFE.define_neighborhoods does (safepy_b200/safe.py)
+    from safepy_b200.ordering import kd_order
+    t0 = time.perf_counter()
+    node_order = kd_order(net["x"], net["y"])
+    t_order = time.perf_counter() - t0
     lo, hi = shard_bounds(P, world, rank)
     rows_host = torch.from_numpy(rows_all[lo:hi]).pin_memory()
     attrs_host = torch.from_numpy(attrs).pin_memory()
@@ -236,6 +298,7 @@ def run_ours(args):
     def step_resident():
         counts.zero_()
         plan = _lib.Enrichment(nb, b_dev=attrs_dev.data_ptr(), dtype=np.float32, shape=(n, m))
+        plan.set_node_order(node_order)
         plan.perm_counts_dev(rows_dev.data_ptr(), hi - lo, counts[0].data_ptr(), counts[1].data_ptr(), "sum",
                              args.engine)
         if world > 1:
@@ -249,6 +312,7 @@ def run_ours(args):
             # the host-buffer C-ABI entry points: sb_neigh_upload_packed + sb_enrich_create + sb_enrich_perm_counts
             nbh = _lib.Neighborhoods(ctx, n).upload_packed(packed_host.numpy().view(np.uint32))
             plan = _lib.Enrichment(nbh, attrs_host.numpy())
+            plan.set_node_order(node_order)
             out = counts_host.numpy().view(np.uint32)
             plan.perm_counts(rows_host.numpy(), "sum", args.engine, out=(out[0], out[1]))
             plan.close()
@@ -260,6 +324,7 @@ def run_ours(args):
             counts.zero_()
             nbh = _lib.Neighborhoods(ctx, n, words_dev=pk.data_ptr())
             plan = _lib.Enrichment(nbh, b_dev=b.data_ptr(), dtype=np.float32, shape=(n, m))
+            plan.set_node_order(node_order)
             plan.perm_counts_dev(r.data_ptr(), hi - lo, counts[0].data_ptr(), counts[1].data_ptr(), "sum", args.engine)
             dist.all_reduce(counts)
             counts_host.copy_(counts, non_blocking=True)
@@ -350,6 +415,8 @@ def run_ours(args):
                 "parallelism": "permutations sharded %d-way" % world,
                 "l2": "working set per batch (gathered operand %.0f MB/permutation) exceeds the 126 MB L2"
                       % (n * ((m + 63) // 64 * 64) * stats["digits"] / 1e6),
+                "node_order": "input nodes randomly renumbered; k-d tree order of the layout passed as a hint "
+                              "(sb_enrich_set_node_order)",
                 "mean_neighborhood": float(rowsums.mean()), "nonempty_a_tiles": tiles,
                 "dense_a_tiles": stats["a_tiles_dense"], "digits": stats["digits"],
                 "fixup_fraction": stats["fixups"] / max(1, stats["fixups"] + stats["decided"]),
@@ -375,7 +442,8 @@ def run_ours(args):
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
             },
             "stages": {"define_neighborhoods_s": t_stage1, "define_neighborhoods_kernel_ms": k1_ms,
-                       "perm_index_replay_host_s": t_rng, "compute_pvalues_null_s": sec_per_step},
+                       "perm_index_replay_host_s": t_rng, "node_order_hint_host_s": t_order,
+                       "compute_pvalues_null_s": sec_per_step},
         }
         if not args.no_cpu_baseline and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

@@ -121,6 +121,13 @@ int sb_enrich_create_dev(sb_ctx* ctx, sb_neigh* a, const void* b_dev, int dtype,
                          sb_enrich** out);
 int sb_enrich_destroy(sb_enrich* e);
 
+/* Optional locality hint for the tensor-core null: order[i] = node placed at internal position i (a permutation of
+ * 0..n-1, e.g. nodes sorted along a space-filling curve of the layout).  The null skips all-zero 256 x 64 tiles of
+ * the neighborhood matrix, so an order in which neighborhoods are contiguous cuts its work by an order of
+ * magnitude; results are identical for any order (inputs and outputs stay in the caller's node numbering).
+ * NULL restores the identity.  Call before sb_enrich_perm_counts*. */
+int sb_enrich_set_node_order(sb_enrich* e, const int32_t* order_host);
+
 /* compute_neighborhood_score(A, B, type), safe_extras.py:6-33 -> fp64 [n x m] */
 int sb_enrich_score(sb_enrich* e, int score_type, double* out_host);
 int sb_enrich_score_dev(sb_enrich* e, int score_type, double* out_dev);

@@ -51,6 +51,7 @@ SIGNATURES = {
     "sb_enrich_create": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.POINTER(_vp)]),
     "sb_enrich_create_dev": (C.c_int, [_vp, _vp, _vp, C.c_int, _i64, _i64, C.POINTER(_vp)]),
     "sb_enrich_destroy": (C.c_int, [_vp]),
+    "sb_enrich_set_node_order": (C.c_int, [_vp, _vp]),
     "sb_enrich_score": (C.c_int, [_vp, C.c_int, _vp]),
     "sb_enrich_score_dev": (C.c_int, [_vp, C.c_int, _vp]),
     "sb_enrich_perm_counts": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
@@ -293,6 +294,15 @@ class Enrichment:
             _check(self.lib, self.lib.sb_enrich_create_dev(self.ctx.h, neigh.h, _vp(int(b_dev)), code, self.n,
                                                            self.m, C.byref(h)))
         self.h = h
+
+    def set_node_order(self, order):
+        """Locality hint for the tensor-core null: order[i] = node at internal position i (None: identity)."""
+        if order is not None:
+            order = _as(order, np.int32)
+            if order.shape != (self.n,):
+                raise ValueError("order must have n entries")
+        _check(self.lib, self.lib.sb_enrich_set_node_order(self.h, _ptr(order)))
+        return self
 
     def score(self, score_type="sum"):
         out = np.empty((self.n, self.m), dtype=np.float64)

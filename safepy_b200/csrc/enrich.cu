@@ -145,22 +145,42 @@ __global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ 
     if (s >= o) atomicAdd(&cpos[i * m + j], 1u);
 }
 
+// Exact re-evaluation of the comparisons the fixed-point GEMM could not decide.  One warp per flagged
+// (node i, attribute j, permutation p): the lanes stride over the neighborhood, accumulate the permuted AND the
+// observed score in fp64 and combine the 32 partial sums in a fixed butterfly order.  (For the input classes whose
+// counts are pinned against the reference -- binary, integer, dyadic, float32-valued data -- these sums are exact in
+// fp64, so the summation order is immaterial; for the rest the reference's own BLAS order is unspecified.)
 template <class T>
-__global__ void k_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                        const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n, int64_t m,
-                        const uint64_t* __restrict__ flag_ij, const uint32_t* __restrict__ flag_p,
-                        const unsigned int* __restrict__ flag_count, unsigned int capacity,
-                        const double* __restrict__ s0, uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
+__global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                               const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                               int64_t m, const uint64_t* __restrict__ flag_ij,
+                                               const uint32_t* __restrict__ flag_p,
+                                               const unsigned int* __restrict__ flag_count, unsigned int capacity,
+                                               uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
     const unsigned int total = min(*flag_count, capacity);
-    unsigned int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned int step = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31;
+    unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int step = (gridDim.x * blockDim.x) >> 5;
     for (; k < total; k += step) {
         const uint64_t ij = flag_ij[k];
         const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
-        const double s = score_one<T, false>(row_ptr, col_idx, b, perm, n, m, i, flag_p[k], j);
-        const double o = s0[i * m + j];
-        if (s <= o) atomicAdd(&cneg[i * m + j], 1u);
-        if (s >= o) atomicAdd(&cpos[i * m + j], 1u);
+        const int32_t* pr = perm + static_cast<int64_t>(flag_p[k]) * n;
+        double sp = 0.0, so = 0.0;
+        for (int64_t e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
+            const int32_t t = col_idx[e];
+            const T vo = b[static_cast<int64_t>(t) * m + j];
+            const T vp = b[static_cast<int64_t>(pr[t]) * m + j];
+            if (vo == vo) so += static_cast<double>(vo);
+            if (vp == vp) sp += static_cast<double>(vp);
+        }
+        for (int o = 16; o; o >>= 1) {
+            sp += __shfl_xor_sync(0xffffffffu, sp, o);
+            so += __shfl_xor_sync(0xffffffffu, so, o);
+        }
+        if (lane == 0) {
+            if (sp <= so) atomicAdd(&cneg[i * m + j], 1u);
+            if (sp >= so) atomicAdd(&cpos[i * m + j], 1u);
+        }
     }
 }
 
@@ -382,17 +402,16 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
                  const unsigned int* flag_count_dev, unsigned int capacity, uint32_t* cneg, uint32_t* cpos) {
     sb_ctx* ctx = e->ctx;
-    const double* s0 = enrich_observed(e, SB_SCORE_SUM);
     const unsigned blocks = static_cast<unsigned>(ctx->num_sms * 8);
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
-        k_fixup<float><<<blocks, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
+        k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
                                                         perm_dev, e->n, e->m, flag_ij, flag_p, flag_count_dev,
-                                                        capacity, s0, cneg, cpos);
+                                                        capacity, cneg, cpos);
     else
-        k_fixup<double><<<blocks, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p,
+        k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p,
                                                          static_cast<const double*>(e->b), perm_dev, e->n, e->m,
-                                                         flag_ij, flag_p, flag_count_dev, capacity, s0, cneg, cpos);
+                                                         flag_ij, flag_p, flag_count_dev, capacity, cneg, cpos);
     SB_LAUNCH_CHECK(ctx);
 }
 
@@ -588,6 +607,37 @@ int sb_enrich_perm_counts(sb_enrich* e, int score_type, int engine, const int32_
     SB_CUDA(cudaMemcpyAsync(counts_pos_host, cnt.p + cells, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                             ctx->stream));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_API_END
+}
+
+int sb_enrich_set_node_order(sb_enrich* e, const int32_t* order_host) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_set_node_order: NULL handle");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    if (e->tc) {  // operands were built for another order
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));
+        tc_plan_destroy(e->tc);
+        e->tc = nullptr;
+    }
+    if (!order_host) {
+        e->have_order = false;
+        return 0;
+    }
+    const int64_t n = e->n;
+    std::vector<int32_t> inv(n, -1);
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t v = order_host[i];
+        SB_CHECK(v >= 0 && v < n && inv[v] < 0, "sb_enrich_set_node_order: order is not a permutation of 0..n-1 (entry %lld)",
+                 (long long)i);
+        inv[v] = static_cast<int32_t>(i);
+    }
+    e->order.reserve(n);
+    e->order_inv.reserve(n);
+    SB_CUDA(cudaMemcpyAsync(e->order.p, order_host, n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaMemcpyAsync(e->order_inv.p, inv.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    e->have_order = true;
     SB_API_END
 }
 

@@ -25,6 +25,10 @@ struct sb_enrich {
     sb::DevBuf<double> s0_z;
     bool have_s0_z = false;
 
+    // optional internal node order for the tensor-core path: order[i] = caller's node at internal position i
+    sb::DevBuf<int32_t> order, order_inv;
+    bool have_order = false;
+
     sb::TcPlan* tc = nullptr;
     int64_t stats[7] = {0, 0, 0, 0, 0, 0, 0};
 };

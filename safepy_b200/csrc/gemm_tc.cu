@@ -675,6 +675,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 }
 
 // ------------------------------------------------------------------------------------------------ operand builders
+// packed matrix in the internal node order: out[inv[s]][inv[t]] = A[s][t]; one warp per CSR row of A
+__global__ void __launch_bounds__(256) k_permute_packed(const int64_t* __restrict__ row_ptr,
+                                                        const int32_t* __restrict__ col_idx,
+                                                        const int32_t* __restrict__ inv, int64_t n, int64_t ld,
+                                                        uint32_t* __restrict__ out) {
+    const int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    uint32_t* const dst = out + static_cast<int64_t>(inv[row]) * ld;
+    for (int64_t e = row_ptr[row] + lane; e < row_ptr[row + 1]; e += 32) {
+        const int32_t t = inv[col_idx[e]];
+        atomicOr(&dst[t >> 5], 1u << (t & 31));
+    }
+}
+
+
 // occupancy of 256 x 64 tiles of the packed matrix; one block per row block (= rows of one CTA pair)
 __global__ void __launch_bounds__(256) k_tile_occ(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
                                                   int32_t n_kt, uint8_t* __restrict__ occ,
@@ -834,44 +850,95 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
 //   half = nc / (NC16/2),   16-byte chunk index inside the half = kg * (NC16/2 * 8) + (nc % (NC16/2)) * 8 + r
 // column nc*16+x of the tile = digit plane (nc / 4), attribute/permutation column c = (nc & 3) * 16 + x.
 template <int D>
+__device__ __forceinline__ int gather_chunk_pos(int k, int nc) {
+    constexpr int HC = 2 * D;  // 16-column chunks per half
+    return (nc / HC) * (TC_KT * HC) + (k >> 3) * (HC * 8) + (nc % HC) * 8 + (k & 7);
+}
+
+// M >= 64: one block builds the tiles of GCG consecutive column groups for one (permutation, k-tile).  The source
+// rows are resolved once per block; reads are 64*GCG contiguous bytes per (source row, digit plane); the tiles are
+// assembled in shared memory and written out linearly.
+template <int D>
+struct GatherCfg {
+    static constexpr int GCG = D == 1 ? 8 : (D == 2 ? 4 : 3);  // column groups per block (tiles <= 36 KB of smem)
+};
+template <int D>
 __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digits, const int32_t* __restrict__ perm,
-                                                int64_t n, int64_t mpad, int32_t n_kt, int32_t n_cg, int32_t pps,
-                                                int32_t log2_mpad, int32_t batch_perms, int8_t* __restrict__ bcat) {
+                                                const int32_t* __restrict__ order, int64_t n, int64_t mpad,
+                                                int32_t n_kt, int32_t n_cg, int8_t* __restrict__ bcat) {
+    constexpr int NC16 = 4 * D;
+    constexpr int CHUNKS = TC_KT * NC16;       // 16-byte chunks per tile
+    constexpr int GCG = GatherCfg<D>::GCG;
+    __shared__ uint4 s_tile[GCG * CHUNKS];
+    __shared__ int32_t s_src[TC_KT];
+    const int kt = blockIdx.x;
+    const int q = blockIdx.z;
+    const int cg0 = blockIdx.y * GCG, ncg = min(GCG, n_cg - cg0);
+    if (threadIdx.x < TC_KT) {
+        const int64_t t = static_cast<int64_t>(kt) * TC_KT + threadIdx.x;
+        int32_t src = -1;
+        if (t < n) {
+            const int64_t node = order ? order[t] : t;  // internal position t holds the caller's node `node`
+            src = perm ? perm[static_cast<int64_t>(q) * n + node] : static_cast<int32_t>(node);
+        }
+        s_src[threadIdx.x] = src;
+    }
+    __syncthreads();
+    const size_t plane = static_cast<size_t>(n) * mpad;
+    const int per_row = ncg * 4;               // 16-byte chunks per (row, plane) in this block's column range
+    const int total = TC_KT * D * per_row;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int c16 = idx % per_row, rest = idx / per_row;
+        const int d = rest % D, k = rest / D;
+        const int g = c16 >> 2, jc = c16 & 3;
+        const int32_t src = s_src[k];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src >= 0)
+            v = *reinterpret_cast<const uint4*>(digits + d * plane + static_cast<size_t>(src) * mpad +
+                                                static_cast<size_t>(cg0) * 64 + c16 * 16);
+        s_tile[g * CHUNKS + gather_chunk_pos<D>(k, d * 4 + jc)] = v;
+    }
+    __syncthreads();
+    for (int g = 0; g < ncg; ++g) {
+        const size_t slot = static_cast<size_t>(q) * n_cg + cg0 + g;
+        uint4* dst = reinterpret_cast<uint4*>(bcat + (slot * n_kt + kt) * (TC_KT * 64 * D));
+        for (int i = threadIdx.x; i < CHUNKS; i += blockDim.x) dst[i] = s_tile[g * CHUNKS + i];
+    }
+}
+
+// M < 64: a slot holds pps = 64 / mpad permutations of all attributes; byte-wise assembly (tiny problems only)
+template <int D>
+__global__ void __launch_bounds__(256) k_gather_small(const int8_t* __restrict__ digits,
+                                                      const int32_t* __restrict__ perm,
+                                                      const int32_t* __restrict__ order, int64_t n, int64_t mpad,
+                                                      int32_t n_kt, int32_t pps, int32_t log2_mpad,
+                                                      int32_t batch_perms, int8_t* __restrict__ bcat) {
     constexpr int NC16 = 4 * D;
     constexpr int CHUNKS = TC_KT * NC16;
     const int kt = blockIdx.x;
-    const int slot = blockIdx.y;
-    const int q = slot / n_cg, cg = slot % n_cg;
-    uint4* dst = reinterpret_cast<uint4*>(bcat + (static_cast<size_t>(slot) * n_kt + kt) * (TC_KT * 64 * D));
+    const int q = blockIdx.y;  // n_cg == 1: slot == q
+    uint4* dst = reinterpret_cast<uint4*>(bcat + (static_cast<size_t>(q) * n_kt + kt) * (TC_KT * 64 * D));
     const size_t plane = static_cast<size_t>(n) * mpad;
-    for (int ch = threadIdx.x; ch < CHUNKS; ch += blockDim.x) {
-        const int kg = ch / (NC16 * 8), rem = ch % (NC16 * 8), nc = rem >> 3, r = rem & 7;
-        const int64_t t = static_cast<int64_t>(kt) * TC_KT + kg * 8 + r;
+    for (int idx = threadIdx.x; idx < CHUNKS; idx += blockDim.x) {
+        const int k = idx / NC16, nc = idx % NC16;
+        const int64_t t = static_cast<int64_t>(kt) * TC_KT + k;
         const int d = nc >> 2, jc = nc & 3;
-        uint4 v = make_uint4(0, 0, 0, 0);
+        uint32_t w[4] = {0, 0, 0, 0};
         if (t < n) {
-            if (mpad >= 64) {
-                const int64_t src = perm ? perm[static_cast<int64_t>(q) * n + t] : t;
-                v = *reinterpret_cast<const uint4*>(digits + d * plane + src * mpad + static_cast<int64_t>(cg) * 64 +
-                                                    jc * 16);
-            } else {
-                uint32_t w[4] = {0, 0, 0, 0};
+            const int64_t node = order ? order[t] : t;
 #pragma unroll
-                for (int x = 0; x < 16; ++x) {
-                    const int c = jc * 16 + x;
-                    const int pl = q * pps + (c >> log2_mpad);
-                    const int j = c & (static_cast<int>(mpad) - 1);
-                    if (pl < batch_perms) {
-                        const int64_t src = perm ? perm[static_cast<int64_t>(pl) * n + t] : t;
-                        const uint32_t byte = static_cast<uint8_t>(digits[d * plane + src * mpad + j]);
-                        w[x >> 2] |= byte << ((x & 3) * 8);
-                    }
+            for (int x = 0; x < 16; ++x) {
+                const int c = jc * 16 + x;
+                const int pl = q * pps + (c >> log2_mpad);
+                const int j = c & (static_cast<int>(mpad) - 1);
+                if (pl < batch_perms) {
+                    const int64_t src = perm ? perm[static_cast<int64_t>(pl) * n + node] : node;
+                    const uint32_t byte = static_cast<uint8_t>(digits[d * plane + src * mpad + j]);
+                    w[x >> 2] |= byte << ((x & 3) * 8);
                 }
-                v = make_uint4(w[0], w[1], w[2], w[3]);
             }
         }
-        constexpr int HC = NC16 / 2;  // 16-column chunks per half
-        dst[(nc / HC) * (TC_KT * HC) + kg * (HC * 8) + (nc % HC) * 8 + r] = v;
+        dst[gather_chunk_pos<D>(k, nc)] = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -898,6 +965,7 @@ struct TcPlan {
     int64_t n_tiles_real = 0;  // non-empty tiles
     bool usable = true;  // false: data contains +-inf -> SIMT engine
     DevBuf<uint64_t> a_bits;
+    const int32_t* order = nullptr;  // e->order.p when the caller supplied a node order (internal row -> node)
     DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
     DevBuf<int8_t> digits;
     DevBuf<uint8_t> inexact;
@@ -978,19 +1046,37 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
 }
 
 static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
-    dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
-    SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
     KernelTimer kt(ctx, SB_K_GATHER);
-#define SB_G(DD)                                                                                              \
-    k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->n, pl->mpad, pl->n_kt, pl->n_cg, pl->pps, \
-                                                pl->log2_mpad, batch_perms, ctx->ws_bcat.p)
-    if (pl->D == 1)
-        SB_G(1);
-    else if (pl->D == 2)
-        SB_G(2);
-    else
-        SB_G(3);
+    if (pl->mpad >= 64) {
+        const int nq = slots / pl->n_cg;
+        const int gcg = pl->D == 1 ? GatherCfg<1>::GCG : (pl->D == 2 ? GatherCfg<2>::GCG : GatherCfg<3>::GCG);
+        dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(sb_ceil_div(pl->n_cg, gcg)),
+                  static_cast<unsigned>(nq));
+        SB_CHECK(grid.y <= 65535 && grid.z <= 65535, "too many column groups / permutations in one batch");
+#define SB_G(DD) \
+    k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt, pl->n_cg, \
+                                                ctx->ws_bcat.p)
+        if (pl->D == 1)
+            SB_G(1);
+        else if (pl->D == 2)
+            SB_G(2);
+        else
+            SB_G(3);
 #undef SB_G
+    } else {
+        dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
+        SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
+#define SB_G(DD)                                                                                                  \
+    k_gather_small<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt,   \
+                                                      pl->pps, pl->log2_mpad, batch_perms, ctx->ws_bcat.p)
+        if (pl->D == 1)
+            SB_G(1);
+        else if (pl->D == 2)
+            SB_G(2);
+        else
+            SB_G(3);
+#undef SB_G
+    }
     SB_LAUNCH_CHECK(ctx);
 }
 
@@ -1011,6 +1097,7 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.pps = pl->pps;
     gp.s0fix = pl->s0fix.p;
     gp.row_ptr = e->row_ptr.p;
+    gp.node_of_row = pl->order;
     gp.inexact = pl->inexact.p;
     gp.flag_ij = ctx->ws_flag_ij.p;
     gp.flag_p = ctx->ws_flag_p.p;
@@ -1068,13 +1155,26 @@ static TcPlan* build_plan(sb_enrich* e) {
             }
         }
 
+        // ---- internal node order (optional): tiles are built from the permuted matrix, everything that addresses
+        // the caller's arrays (gather source rows, counts, bands, fix-ups) goes through order[]
+        const uint32_t* a_words = e->a->words;
+        DevBuf<uint32_t> permuted;
+        if (e->have_order) {
+            pl->order = e->order.p;
+            permuted.reserve(static_cast<size_t>(n) * e->a->ld);
+            SB_CUDA(cudaMemsetAsync(permuted.p, 0, static_cast<size_t>(n) * e->a->ld * sizeof(uint32_t), st));
+            k_permute_packed<<<static_cast<unsigned>(sb_ceil_div(n * 32, 256)), 256, 0, st>>>(
+                e->row_ptr.p, e->col_idx.p, e->order_inv.p, n, e->a->ld, permuted.p);
+            SB_LAUNCH_CHECK(ctx);
+            a_words = permuted.p;
+        }
         // ---- A tiles
         PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.a_tiles");
         DevBuf<uint8_t> occ;
         DevBuf<int32_t> rb_count;
         occ.reserve(static_cast<size_t>(pl->n_rb) * pl->n_kt);
         rb_count.reserve(pl->n_rb);
-        k_tile_occ<<<pl->n_rb, 256, 0, st>>>(e->a->words, n, e->a->ld, pl->n_kt, occ.p, rb_count.p);
+        k_tile_occ<<<pl->n_rb, 256, 0, st>>>(a_words, n, e->a->ld, pl->n_kt, occ.p, rb_count.p);
         SB_LAUNCH_CHECK(ctx);
         std::vector<int32_t> h_cnt(pl->n_rb), h_ptr(pl->n_rb + 1);
         SB_CUDA(cudaMemcpyAsync(h_cnt.data(), rb_count.p, pl->n_rb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -1098,7 +1198,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         k_tile_list<<<pl->n_rb, 256, 0, st>>>(occ.p, pl->n_kt, pl->tile_ptr.p, pl->tile_kt.p, pl->tile_rb.p);
         SB_LAUNCH_CHECK(ctx);
         k_pack_tiles<<<static_cast<unsigned>(sb_ceil_div(run * TC_PROWS, 256)), 256, 0, st>>>(
-            e->a->words, n, e->a->ld, pl->tile_kt.p, pl->tile_rb.p, run, pl->a_bits.p);
+            a_words, n, e->a->ld, pl->tile_kt.p, pl->tile_rb.p, run, pl->a_bits.p);
         SB_LAUNCH_CHECK(ctx);
 
         delete tr;
@@ -1270,10 +1370,6 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     if (!pl->usable) {  // +-inf in the data: fixed point cannot represent it
         simt_perm_counts(e, SB_SCORE_SUM, perm_dev, num_perm, cneg, cpos);
         return;
-    }
-    {
-        PhaseTrace tr(ctx, "tc.observed_fp64");
-        enrich_observed(e, SB_SCORE_SUM);  // fp64 observed scores for the fix-up kernel
     }
     PhaseTrace* tr_ws = new PhaseTrace(ctx, "tc.workspace");
 

@@ -21,6 +21,7 @@ class PackedNeighborhoods:
         self.words = np.ascontiguousarray(words, dtype=np.uint32).reshape(n, _lib.neigh_ld(n))
         self.n = int(n)
         self._device = device  # _lib.Neighborhoods or None
+        self.node_order = None  # optional locality hint for the enrichment plan (see ordering.py)
 
     # -- ndarray-like surface
     @property
@@ -77,11 +78,12 @@ class PackedNeighborhoods:
         return dev
 
     def __getstate__(self):
-        return {"words": self.words, "n": self.n}
+        return {"words": self.words, "n": self.n, "node_order": self.node_order}
 
     def __setstate__(self, state):
         self.words = state["words"]
         self.n = state["n"]
+        self.node_order = state.get("node_order")
         self._device = None
 
 

@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from .neighborhood_matrix import PackedNeighborhoods, as_packed
+from .ordering import kd_order
 from .permutations import make_perm_rows
 
 DEFAULTS = {
@@ -123,6 +124,8 @@ class SafeB200Mixin:
             self.node_distances = None
 
         packed = PackedNeighborhoods(dev.packed(), n, device=dev)
+        # locality hint for stage 2 (nodes sorted spatially); results do not depend on it
+        packed.node_order = kd_order(x, y)
         num_neighbors = packed.row_sums()
         if self.verbose:
             logging.info("Node distance metric: %s" % self.node_distance_metric)
@@ -167,7 +170,11 @@ class SafeB200Mixin:
         b = np.asarray(self.node2attribute)
         if b.shape[0] != packed.n:
             raise ValueError("node2attribute has %d rows but the network has %d nodes" % (b.shape[0], packed.n))
-        return _lib.Enrichment(packed.on_device(ctx), b)
+        plan = _lib.Enrichment(packed.on_device(ctx), b)
+        order = getattr(packed, "node_order", None)
+        if order is not None:
+            plan.set_node_order(order)
+        return plan
 
     def compute_pvalues_by_randomization(self, **kwargs):
         if kwargs:

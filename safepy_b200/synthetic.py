@@ -143,8 +143,31 @@ CONFIGS = {
 }
 
 
-def make_config(name, scale=1.0):
-    """Inputs of a named configuration; `scale` < 1 shrinks n, edges and m proportionally (tests)."""
+def relabel_nodes(net, attrs, seed):
+    """Random renumbering of the nodes (the generators emit them along a Morton curve; real inputs come in file order).
+    Returns (net, attrs) with coordinates, edges, CSR and attribute rows permuted consistently."""
+    n = net["n"]
+    new_of_old = np.random.default_rng(seed).permutation(n)
+    old_of_new = np.argsort(new_of_old)
+    x, y = net["x"][old_of_new], net["y"][old_of_new]
+    edges, length = net["edges"], net["length"]
+    if len(edges):
+        eu, ev = new_of_old[edges[:, 0]], new_of_old[edges[:, 1]]
+        lo, hi = np.minimum(eu, ev), np.maximum(eu, ev)
+        order = np.lexsort((hi, lo))
+        eu, ev, length = lo[order], hi[order], length[order]
+        indptr, indices, csr_len = edges_to_csr(n, eu, ev, length)
+        edges = np.column_stack([eu, ev])
+    else:
+        indptr, indices, csr_len = net["indptr"], net["indices"], net["csr_length"]
+    out = dict(n=n, x=np.ascontiguousarray(x), y=np.ascontiguousarray(y), edges=edges, length=length, indptr=indptr,
+               indices=indices, csr_length=csr_len)
+    return out, np.ascontiguousarray(attrs[old_of_new])
+
+
+def make_config(name, scale=1.0, shuffle=False):
+    """Inputs of a named configuration; `scale` < 1 shrinks n, edges and m proportionally (tests); `shuffle`
+    renumbers the nodes randomly so that the input order carries no spatial locality."""
     c = dict(CONFIGS[name])
     n = max(64, int(c["n"] * scale))
     m = max(1, int(c["m"] * scale)) if c["m"] > 1 else 1
@@ -156,5 +179,7 @@ def make_config(name, scale=1.0):
                    indptr=np.zeros(n + 1, dtype=np.int64), indices=np.zeros(0, dtype=np.int32),
                    csr_length=np.zeros(0))
     attrs = make_attributes(n, m, c["seed"] + 7, c["kind"], c["nan_row_frac"], c["nan_cell_frac"])
+    if shuffle:
+        net, attrs = relabel_nodes(net, attrs, c["seed"] + 13)
     c.update(n=n, m=m, net=net, attributes=attrs)
     return c

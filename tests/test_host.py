@@ -139,3 +139,22 @@ def test_synthetic_configs_are_deterministic():
     assert np.array_equal(a["net"]["edges"], b["net"]["edges"]) and np.array_equal(a["net"]["x"], b["net"]["x"])
     assert np.array_equal(a["attributes"], b["attributes"], equal_nan=True)
     assert a["attributes"].dtype == np.float32
+
+
+def test_kd_order_and_relabelling():
+    from safepy_b200.ordering import kd_order, graph_order
+    c0 = syn.make_config("C1", 0.15)
+    c1 = syn.make_config("C1", 0.15, shuffle=True)
+    n = c0["n"]
+    for c in (c0, c1):
+        o = kd_order(c["net"]["x"], c["net"]["y"])
+        assert o.dtype == np.int32 and np.array_equal(np.sort(o), np.arange(n))
+    # relabelling keeps the geometry: same multiset of coordinates and edge lengths, same attribute rows
+    assert np.allclose(np.sort(c0["net"]["x"]), np.sort(c1["net"]["x"]))
+    assert np.allclose(np.sort(c0["net"]["length"]), np.sort(c1["net"]["length"]))
+    assert np.array_equal(np.sort(np.nan_to_num(c0["attributes"][:, 0])), np.sort(np.nan_to_num(c1["attributes"][:, 0])))
+    e = c1["net"]["edges"]
+    d = np.hypot(c1["net"]["x"][e[:, 0]] - c1["net"]["x"][e[:, 1]], c1["net"]["y"][e[:, 0]] - c1["net"]["y"][e[:, 1]])
+    assert np.allclose(d, c1["net"]["length"])
+    g = graph_order(c1["net"]["indptr"], c1["net"]["indices"], n)
+    assert np.array_equal(np.sort(g), np.arange(n))

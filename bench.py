@@ -61,10 +61,17 @@ class ClockSampler:
         self.lines = []
         self.samples = []
         self.stop_flag = threading.Event()
+        self.recording = threading.Event()
+        self.call_ms = (0.0, 0.0)
         self.nvml = None
         self.how = None
 
     def start(self):
+        """begin recording (prepare() must have run: NVML is initialised and polled before the timed region, so
+        that its first-use costs do not land inside it)"""
+        self.recording.set()
+
+    def prepare(self):
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -107,16 +114,22 @@ class ClockSampler:
             getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
         while not self.stop_flag.is_set():
             try:
+                t0 = time.perf_counter()
                 sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                t1 = time.perf_counter()
                 mask = get_reasons(self.handle)
-                self.samples.append((float(sm), smax, {k for k, bit in names.items() if mask & bit}))
+                t2 = time.perf_counter()
+                self.call_ms = (max(self.call_ms[0], 1e3 * (t1 - t0)), max(self.call_ms[1], 1e3 * (t2 - t1)))
+                if self.recording.is_set():
+                    self.samples.append((float(sm), smax, {k for k, bit in names.items() if mask & bit}))
             except Exception:  # noqa: BLE001
                 pass
             self.stop_flag.wait(0.1)
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            if self.recording.is_set():
+                self.lines.append(line.strip())
 
     def stop(self):
         if self.nvml is not None:
@@ -126,7 +139,8 @@ class ClockSampler:
             smax = [x[1] for x in self.samples if x[1]]
             reasons = set().union(*[x[2] for x in self.samples]) if self.samples else set()
             return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(smax)) if smax else None,
-                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml"}
+                    "reasons": sorted(reasons), "samples": len(sm), "source": "nvml",
+                    "max_query_ms": [round(self.call_ms[0], 2), round(self.call_ms[1], 2)]}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -345,8 +359,12 @@ def run_ours(args):
         t0 = time.perf_counter()
         e0.record()
         last = None
+        walls = []
         for _ in range(steps):
+            ts = time.perf_counter()
             last = fn()
+            walls.append(1e3 * (time.perf_counter() - ts))
+        timed.last_walls = walls
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -359,19 +377,20 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count
+        sampler.prepare()
+    # warm-up with the per-kernel event brackets already on (their first use allocates the driver's event pool, which
+    # would otherwise land in the first timed step), then drop what the warm-up recorded
     ctx.profile(True)
-    for k in _lib.KERNEL_CLASSES:
-        ctx.kernel_ms(k)
-    # warm-up outside the profiled window, then the timed steps with per-kernel event brackets on
-    ctx.profile(False)
     for _ in range(args.warmup):
         step_resident()
-    ctx.profile(True)
+    for k in _lib.KERNEL_CLASSES:
+        ctx.kernel_ms(k)
     launches0 = ctx.launch_count
+    if rank == 0:
+        sampler.start()
     ms_total, wall_total, stats = timed(step_resident, args.steps, 0)
     launches = ctx.launch_count - launches0
+    step_walls = list(getattr(timed, "last_walls", []))
     kern = {k: ctx.kernel_ms(k) for k in ("gemm", "gather", "fixup", "prep", "score")}
     ctx.profile(False)
     clocks = sampler.stop() if rank == 0 else None
@@ -440,6 +459,7 @@ def run_ours(args):
                 "executed_int8_tops": int8_ops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None,
                 "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in kern.items()},
+                "host_wall_ms_of_each_step": step_walls,
             },
             "stages": {"define_neighborhoods_s": t_stage1, "define_neighborhoods_kernel_ms": k1_ms,
                        "perm_index_replay_host_s": t_rng, "node_order_hint_host_s": t_order,

@@ -134,21 +134,21 @@ namespace sb {
 struct PhaseTrace {
     sb_ctx* ctx;
     const char* name;
-    bool on;
+    int mode;  // 0 off, 1 SB_TRACE (phases closed by a stream synchronize), 2 SB_TRACE_HOST (host wall time only)
     std::chrono::steady_clock::time_point t0;
     PhaseTrace(sb_ctx* c, const char* n) : ctx(c), name(n) {
-        static const bool enabled = getenv("SB_TRACE") != nullptr;
-        on = enabled;
-        if (on) {
-            cudaStreamSynchronize(ctx->stream);
+        static const int enabled = getenv("SB_TRACE") ? 1 : (getenv("SB_TRACE_HOST") ? 2 : 0);
+        mode = enabled;
+        if (mode) {
+            if (mode == 1) cudaStreamSynchronize(ctx->stream);
             t0 = std::chrono::steady_clock::now();
         }
     }
     ~PhaseTrace() {
-        if (!on) return;
-        cudaStreamSynchronize(ctx->stream);
+        if (!mode) return;
+        if (mode == 1) cudaStreamSynchronize(ctx->stream);
         const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-        fprintf(stderr, "[sb_trace] %-28s %9.3f ms\n", name, ms);
+        if (mode == 1 || ms > 5.0) fprintf(stderr, "[sb_trace] %-28s %9.3f ms\n", name, ms);
     }
 };
 }  // namespace sb

@@ -894,15 +894,17 @@ __global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digit
         const int32_t src = s_src[k];
         uint4 v = make_uint4(0, 0, 0, 0);
         if (src >= 0)
-            v = *reinterpret_cast<const uint4*>(digits + d * plane + static_cast<size_t>(src) * mpad +
-                                                static_cast<size_t>(cg0) * 64 + c16 * 16);
+            v = __ldg(reinterpret_cast<const uint4*>(digits + d * plane + static_cast<size_t>(src) * mpad +
+                                                     static_cast<size_t>(cg0) * 64 + c16 * 16));
         s_tile[g * CHUNKS + gather_chunk_pos<D>(k, d * 4 + jc)] = v;
     }
     __syncthreads();
+    // streaming stores: the tiles are read once by the GEMM much later; they must not evict the digit planes (re-read
+    // by every permutation of the batch) from L2
     for (int g = 0; g < ncg; ++g) {
         const size_t slot = static_cast<size_t>(q) * n_cg + cg0 + g;
         uint4* dst = reinterpret_cast<uint4*>(bcat + (slot * n_kt + kt) * (TC_KT * 64 * D));
-        for (int i = threadIdx.x; i < CHUNKS; i += blockDim.x) dst[i] = s_tile[g * CHUNKS + i];
+        for (int i = threadIdx.x; i < CHUNKS; i += blockDim.x) __stcs(dst + i, s_tile[g * CHUNKS + i]);
     }
 }
 

@@ -40,6 +40,7 @@ def main():
     hdr = src[1]
     data = src[2:]
     isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
+    data = [r for r in data if len(r) > max(isrc, isamp, iex) and r[isamp].isdigit()]
     total = sum(int(r[isamp]) for r in data)
     print("== source page: %d SASS instructions, %d stall samples" % (len(data), total))
     idx = sorted(range(len(data)), key=lambda i: -int(data[i][isamp]))[:top]

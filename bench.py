@@ -243,7 +243,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "scores/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -480,13 +480,26 @@ def run_ours(args):
             else:
                 out["cpu_baseline"] = {"value": None, "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
                                        "sample": "dense int64 neighborhood matrix does not fit in host memory"}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's original stdout; everything else that libraries print (NCCL banners,
+    warnings) is routed to stderr for the whole run."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

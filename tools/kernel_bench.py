@@ -1,0 +1,96 @@
+"""Device time and roofline bookkeeping of the non-GEMM kernels at the BASELINE.json shapes.
+
+    python tools/kernel_bench.py [--only sssp|euclid|hypergeom] [--small]
+
+Algorithmic bytes follow SURVEY.md section 8(d):
+  k_sssp      sum over sources s and settled nodes t of (8 + deg(t) * 12) + N*N/8   (computed exactly from the result)
+  k_euclid    16 N + N*N/8 bytes, 5 N*N fp64 flops
+  k_hypergeom 20 bytes per (node, attribute) element (X in, p and NES out)
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from safepy_b200 import _lib, get_context, synthetic as syn  # noqa: E402
+
+PEAK = 6536.4
+try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+        PEAK = json.load(f)["hbm_gbs"]
+except OSError:
+    pass
+
+
+def timed(ctx, cls, fn, reps=3):
+    fn()
+    ctx.profile(True)
+    ctx.kernel_ms(cls)
+    for _ in range(reps):
+        fn()
+    ms, cnt = ctx.kernel_ms(cls)
+    ctx.profile(False)
+    return ms / max(cnt, 1)
+
+
+def main():
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    small = "--small" in sys.argv
+    ctx = get_context()
+    out = []
+    if only in (None, "sssp"):
+        for name in (("C1",) if small else ("C1", "C3", "C5")):
+            cfg = syn.make_config(name, shuffle=True)
+            net, n = cfg["net"], cfg["n"]
+            nr = cfg["radius"] * (net["x"].max() - net["x"].min())
+            nb = _lib.Neighborhoods(ctx, n)
+            ms = timed(ctx, "sssp", lambda: nb.shortpath(net["indptr"], net["indices"], net["csr_length"], nr))
+            deg = np.diff(net["indptr"]).astype(np.float64)
+            # settled (s, t) pairs: column sums of the matrix weight each node by how often it was settled
+            sums = nb.rowsums().astype(np.float64)  # symmetric up to last-ulp effects: row sums ~ column sums
+            pairs = float(sums.sum())
+            alg = float(np.dot(sums, 8 + deg * 12)) + n * n / 8.0
+            out.append(dict(kernel="k_sssp", workload=name, n=n, edges=int(len(net["edges"])), ms=ms,
+                            settled_pairs=pairs, pairs_per_s=pairs / (ms * 1e-3), algorithmic_bytes=alg,
+                            achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=PEAK, frac=alg / (ms * 1e-3) / 1e9 / PEAK))
+            nb.close()
+    if only in (None, "euclid"):
+        cfg = syn.make_config("C4", 0.1 if small else 1.0, shuffle=True)
+        net, n = cfg["net"], cfg["n"]
+        nr = cfg["radius"] * (net["x"].max() - net["x"].min())
+        nb = _lib.Neighborhoods(ctx, n)
+        ms = timed(ctx, "euclid", lambda: nb.euclid(net["x"], net["y"], nr))
+        alg = 16.0 * n + n * n / 8.0
+        out.append(dict(kernel="k_euclid", workload="C4", n=n, ms=ms, pairs_per_s=float(n) * n / (ms * 1e-3),
+                        algorithmic_bytes=alg, achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=PEAK,
+                        frac=alg / (ms * 1e-3) / 1e9 / PEAK, fp64_gflops=5.0 * n * n / (ms * 1e-3) / 1e9))
+        nb.close()
+    if only in (None, "hypergeom"):
+        cfg = syn.make_config("C2", 0.2 if small else 1.0, shuffle=True)
+        net, n, m = cfg["net"], cfg["n"], cfg["m"]
+        nr = cfg["radius"] * (net["x"].max() - net["x"].min())
+        nb = _lib.Neighborhoods(ctx, n).shortpath(net["indptr"], net["indices"], net["csr_length"], nr)
+        plan = _lib.Enrichment(nb, cfg["attributes"])
+        t0 = time.perf_counter()
+        plan.hypergeom()
+        wall_first = time.perf_counter() - t0
+        ms = timed(ctx, "hypergeom", lambda: plan.hypergeom())
+        t0 = time.perf_counter()
+        plan.hypergeom()
+        wall = time.perf_counter() - t0
+        alg = 20.0 * n * m
+        out.append(dict(kernel="k_hypergeom", workload="C2", n=n, m=m, ms=ms, elements_per_s=n * m / (ms * 1e-3),
+                        algorithmic_bytes=alg, achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=PEAK,
+                        frac=alg / (ms * 1e-3) / 1e9 / PEAK, call_wall_s=wall, first_call_wall_s=wall_first))
+        plan.close()
+        nb.close()
+    for o in out:
+        print(json.dumps(o))
+
+
+if __name__ == "__main__":
+    main()

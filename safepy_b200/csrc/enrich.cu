@@ -155,9 +155,8 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
                                                const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
                                                int64_t m, const uint64_t* __restrict__ flag_ij,
                                                const uint32_t* __restrict__ flag_p,
-                                               const unsigned int* __restrict__ flag_count, unsigned int capacity,
-                                               uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
-    const unsigned int total = min(*flag_count, capacity);
+                                               unsigned int total, uint32_t* __restrict__ cneg,
+                                               uint32_t* __restrict__ cpos) {
     const int lane = threadIdx.x & 31;
     unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int step = (gridDim.x * blockDim.x) >> 5;
@@ -400,18 +399,18 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
 }
 
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
-                 const unsigned int* flag_count_dev, unsigned int capacity, uint32_t* cneg, uint32_t* cpos) {
+                 unsigned int count, uint32_t* cneg, uint32_t* cpos) {
     sb_ctx* ctx = e->ctx;
-    const unsigned blocks = static_cast<unsigned>(ctx->num_sms * 8);
+    const unsigned blocks = static_cast<unsigned>(
+        std::min<int64_t>(sb_ceil_div(static_cast<int64_t>(count), 8), static_cast<int64_t>(ctx->num_sms) * 8));
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
         k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
-                                                        perm_dev, e->n, e->m, flag_ij, flag_p, flag_count_dev,
-                                                        capacity, cneg, cpos);
+                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos);
     else
         k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p,
                                                          static_cast<const double*>(e->b), perm_dev, e->n, e->m,
-                                                         flag_ij, flag_p, flag_count_dev, capacity, cneg, cpos);
+                                                         flag_ij, flag_p, count, cneg, cpos);
     SB_LAUNCH_CHECK(ctx);
 }
 

@@ -42,7 +42,7 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
                       uint32_t* cpos);
 // exact fp64 re-evaluation of flagged (i, j, p) comparisons; entries are (i << 32 | j) , p pairs
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
-                 const unsigned int* flag_count_dev, unsigned int capacity, uint32_t* cneg, uint32_t* cpos);
+                 unsigned int count, uint32_t* cneg, uint32_t* cpos);
 
 // gemm_tc.cu
 void tc_plan_destroy(TcPlan* p);

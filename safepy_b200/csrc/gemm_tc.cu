@@ -72,8 +72,8 @@ struct GemmParams {
     uint32_t* cpk;            // packed counts (pos << 16 | neg) per (node, attribute), one atomic per cell
     uint64_t* flag_ij;
     uint32_t* flag_p;
-    unsigned int* flag_count;
-    unsigned int flag_cap;
+    unsigned int* flag_count;  // [n_cg]: the list is bucketed by column group (locality of the fix-up kernel)
+    unsigned int flag_cap;     // capacity of one bucket
     int32_t* raw_out;         // TCM_RAW: [256][64*D]
     uint32_t b_lbo, b_sbo;
     int32_t q_wrap;           // 1: every slot re-reads slot 0 (rate self-test); otherwise unused
@@ -634,10 +634,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                             const int64_t j = SMALL_M ? (c & (p.mpad - 1)) : jbase + c;
                             const int pl = SMALL_M ? q * p.pps + (c >> p.log2_mpad) : q;
                             if (j < p.m) {
-                                const unsigned int k = atomicAdd(p.flag_count, 1u);
+                                const unsigned int k = atomicAdd(&p.flag_count[cg], 1u);
                                 if (k < p.flag_cap) {
-                                    p.flag_ij[k] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(j);
-                                    p.flag_p[k] = static_cast<uint32_t>(pl);
+                                    const size_t at = static_cast<size_t>(cg) * p.flag_cap + k;
+                                    p.flag_ij[at] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(j);
+                                    p.flag_p[at] = static_cast<uint32_t>(pl);
                                 }
                             }
                         }
@@ -1104,7 +1105,7 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.flag_ij = ctx->ws_flag_ij.p;
     gp.flag_p = ctx->ws_flag_p.p;
     gp.flag_count = pl->flag_count.p;
-    gp.flag_cap = pl->flag_cap;
+    gp.flag_cap = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
     gp.cpk = ctx->ws_cpk.p;
     const uint32_t ncols = 64u * pl->D;
     gp.b_lbo = ncols / 2 * 8;  // MN-major B half tile: stride between 8-row K groups
@@ -1281,7 +1282,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         pl->flag_cap = static_cast<unsigned int>(std::min<int64_t>(std::max<int64_t>(4ll << 20, worst_slot), 1ll << 31));
         ctx->ws_flag_ij.reserve(pl->flag_cap);
         ctx->ws_flag_p.reserve(pl->flag_cap);
-        pl->flag_count.reserve(1);
+        pl->flag_count.reserve(pl->n_cg);
         ctx->ws_cpk.reserve(static_cast<size_t>(n) * m);
 
         delete tr;
@@ -1409,24 +1410,39 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
             launch_gather(ctx, pl, perm, slots, static_cast<int>(np));
         }
         PhaseTrace tr_b(ctx, "tc.batch.gemm+fixup");
-        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+        const unsigned int cap_cg = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
+        std::vector<unsigned int> h_flags(pl->n_cg);
+        // fix-ups bucket by bucket: the flags of one column group touch 64 attribute columns only, so the scattered
+        // row reads of the fix-up kernel stay L2-resident
+        auto run_fixups = [&](const int32_t* perm_base) -> int64_t {
+            SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
+                                    cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            int64_t total = 0;
+            for (int cg = 0; cg < pl->n_cg; ++cg) {
+                if (h_flags[cg] > cap_cg) return -1;
+                total += h_flags[cg];
+            }
+            for (int cg = 0; cg < pl->n_cg; ++cg)
+                if (h_flags[cg])
+                    fixup_flags(e, perm_base, ctx->ws_flag_ij.p + static_cast<size_t>(cg) * cap_cg,
+                                ctx->ws_flag_p.p + static_cast<size_t>(cg) * cap_cg, h_flags[cg], cneg, cpos);
+            return total;
+        };
+        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
         if (pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);
         pl->cpk_perms += np;
         run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, q_total, static_cast<int>(np));
         ktile_iters += tiles_per_pass * q_total;
-        unsigned int h_flags = 0;
-        SB_CUDA(cudaMemcpyAsync(&h_flags, pl->flag_count.p, sizeof h_flags, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (h_flags <= pl->flag_cap) {
-            if (h_flags)
-                fixup_flags(e, perm, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
-            flagged += h_flags;
+        const int64_t got = run_fixups(perm);
+        if (got >= 0) {
+            flagged += got;
         } else {
-            // The list overflowed: nothing of it is used.  Re-emit the flags slot by slot (one slot's worst case
+            // A bucket overflowed: nothing of the list is used.  Re-emit the flags slot by slot (one slot's worst case
             // always fits) without re-adding the decided counts.
             ++overflow_batches;
             for (int q = 0; q < q_total; ++q) {
-                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
                 GemmParams gp = base_params(e, pl);
                 gp.mode = TCM_FLAG;
                 gp.bcat = ctx->ws_bcat.p + static_cast<size_t>(q) * pl->n_cg * slot_bytes;
@@ -1439,12 +1455,9 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
                 launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms / 2));
                 ktile_iters += tiles_per_pass;
                 const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
-                fixup_flags(e, perm_q, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->flag_cap, cneg, cpos);
-                unsigned int hq = 0;
-                SB_CUDA(cudaMemcpyAsync(&hq, pl->flag_count.p, sizeof hq, cudaMemcpyDeviceToHost, st));
-                SB_CUDA(cudaStreamSynchronize(st));
-                SB_CHECK(hq <= pl->flag_cap, "internal error: flag list overflow in single-slot recovery");
-                flagged += hq;
+                const int64_t gq = run_fixups(perm_q);
+                SB_CHECK(gq >= 0, "internal error: flag list overflow in single-slot recovery");
+                flagged += gq;
             }
         }
     }

@@ -55,11 +55,12 @@ struct Error : std::runtime_error {
 
 // Device allocations are stream-ordered and cached: cudaMallocAsync / cudaFreeAsync on the stream of the context
 // the calling thread bound last (sb_ctx::bind), from the device's default memory pool whose release threshold
-// sb_ctx_create raises to "keep everything".  A plan that is created and destroyed per call therefore costs no
-// cudaMalloc / cudaFree (both of which synchronise the device) after the first call.
+// sb_ctx_create raises to "keep everything", behind a size-matched block cache (neigh.cu).  A plan that is created
+// and destroyed per call therefore costs no allocator calls after the first call.
 cudaStream_t& alloc_stream();  // thread-local
 void* dev_alloc(size_t bytes);
 void dev_free(void* p);
+void dev_cache_trim(int device);  // return the parked blocks of one device to the driver
 
 template <class T>
 struct DevBuf {
@@ -103,6 +104,7 @@ struct sb_ctx {
     sb::DevBuf<uint32_t> ws_flag_p;
     sb::DevBuf<uint32_t> ws_cpk;
     sb::DevBuf<unsigned int> ws_counter;
+    size_t bcat_budget = 0;  // 1/8 of the free device memory seen at the first null of this context
     void bind() const {
         SB_CUDA(cudaSetDevice(device));
         sb::alloc_stream() = stream;

@@ -1377,8 +1377,13 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     PhaseTrace* tr_ws = new PhaseTrace(ctx, "tc.workspace");
 
     // batch size: Bcat workspace <= ~1/8 of free memory (at most 16 GiB), q per unit < 32768 (16-bit counters)
-    size_t free_b = 0, total_b = 0;
-    SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    // (cudaMemGetInfo was seen to take hundreds of ms on a busy device: ask once per context)
+    if (ctx->bcat_budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
+    }
+    const size_t free_b = ctx->bcat_budget * 8;
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
     const size_t budget = std::max(std::min<size_t>(std::max<size_t>(free_b / 8, slot_bytes * slots_for(pl, 1)), 16ull << 30),

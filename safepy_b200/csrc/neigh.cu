@@ -7,6 +7,8 @@
 //                frontier compaction; the source's row lives as a bitmap in shared memory and is stored once.
 #include <cooperative_groups.h>
 
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -31,17 +33,87 @@ cudaStream_t& alloc_stream() {
     thread_local cudaStream_t s = nullptr;
     return s;
 }
+// Block cache in front of cudaMallocAsync.  The driver's pool was observed to stall for 400-600 ms now and then when
+// a plan's large buffers (hundreds of MB) were re-requested right after having been freed (pool growth / remapping),
+// so freed blocks are parked here, keyed by (device, stream), and handed back on a size match: every
+// compute_pvalues call asks for the same sizes, so steady state makes no allocator calls at all.  Reuse is safe
+// because allocation and release are both ordered on the same stream.
+namespace {
+struct CachedBlock {
+    int device;
+    cudaStream_t stream;
+    void* p;
+    size_t bytes;
+};
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;
+std::unordered_map<void*, size_t> g_live;  // size of every block handed out
+size_t g_cached_bytes = 0;
+constexpr size_t kCacheLimit = 96ull << 30;
+}  // namespace
+
 void* dev_alloc(size_t bytes) {
+    if (bytes == 0) bytes = 1;
+    int device = 0;
+    cudaGetDevice(&device);
+    cudaStream_t st = alloc_stream();
+    {
+        std::lock_guard<std::mutex> lk(g_cache_mu);
+        int best = -1;
+        for (int i = 0; i < static_cast<int>(g_cache.size()); ++i) {
+            const CachedBlock& b = g_cache[i];
+            if (b.device != device || b.stream != st || b.bytes < bytes || b.bytes > bytes + bytes / 4 + 4096) continue;
+            if (best < 0 || b.bytes < g_cache[best].bytes) best = i;
+        }
+        if (best >= 0) {
+            void* p = g_cache[best].p;
+            g_cached_bytes -= g_cache[best].bytes;
+            g_live[p] = g_cache[best].bytes;
+            g_cache.erase(g_cache.begin() + best);
+            return p;
+        }
+    }
     void* p = nullptr;
-    cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, alloc_stream());
+    cudaError_t e = cudaMallocAsync(&p, bytes, st);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dev_cache_trim(device);  // give the parked blocks back and retry once
+        e = cudaMallocAsync(&p, bytes, st);
+    }
     if (e != cudaSuccess) {
         cudaGetLastError();
         fail("device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     }
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    g_live[p] = bytes;
     return p;
 }
 void dev_free(void* p) {
-    if (p) cudaFreeAsync(p, alloc_stream());
+    if (!p) return;
+    int device = 0;
+    cudaGetDevice(&device);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    auto it = g_live.find(p);
+    const size_t bytes = it == g_live.end() ? 0 : it->second;
+    if (it != g_live.end()) g_live.erase(it);
+    if (bytes == 0 || g_cached_bytes + bytes > kCacheLimit) {
+        cudaFreeAsync(p, alloc_stream());
+        return;
+    }
+    g_cache.push_back(CachedBlock{device, alloc_stream(), p, bytes});
+    g_cached_bytes += bytes;
+}
+void dev_cache_trim(int device) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = 0; i < g_cache.size();) {
+        if (g_cache[i].device == device) {
+            cudaFreeAsync(g_cache[i].p, g_cache[i].stream);
+            g_cached_bytes -= g_cache[i].bytes;
+            g_cache.erase(g_cache.begin() + i);
+        } else {
+            ++i;
+        }
+    }
 }
 void fail(const char* fmt, ...) {
     char buf[1024];
@@ -296,6 +368,7 @@ int sb_ctx_release_memory(sb_ctx* ctx) {
     ctx->ws_flag_p.release();
     ctx->ws_cpk.release();
     ctx->ws_counter.release();
+    dev_cache_trim(ctx->device);
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaMemPool_t pool;
     SB_CUDA(cudaDeviceGetDefaultMemPool(&pool, ctx->device));

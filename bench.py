@@ -270,20 +270,35 @@ def run_ours(args):
 
     ctx = _lib.Context(local_rank, stream=torch.cuda.current_stream().cuda_stream)
 
-    # ---- stage 1 (timed separately; reported as define_neighborhoods seconds)
+    # ---- stage 1 (timed separately; reported as define_neighborhoods seconds).  With several ranks the source rows
+    # are sharded (independent searches, no data-path collective inside) and the packed rows all-gathered once,
+    # because the permutation-sharded stage 2 wants the whole matrix on every rank.
+    from safepy_b200.distributed import row_shard
+    ld = _lib.neigh_ld(n)
+    r0, r1 = row_shard(n, world, rank)
+    rows_pad = -(-n // world)                      # rows per rank in the gather buffer (last shard zero-padded)
+    words_t = torch.zeros((world * rows_pad, ld), dtype=torch.int32, device=dev)
+
     def stage1():
-        nbh = _lib.Neighborhoods(ctx, n)
+        nbh = _lib.Neighborhoods(ctx, n, words_dev=words_t.data_ptr())
         if cfg["metric"] == "euclidean":
-            nbh.euclid(net["x"], net["y"], cfg["nr"])
+            nbh.euclid(net["x"], net["y"], cfg["nr"], r0, r1)
         else:
-            nbh.shortpath(net["indptr"], net["indices"], net["csr_length"], cfg["nr"])
+            nbh.shortpath(net["indptr"], net["indices"], net["csr_length"], cfg["nr"], r0, r1)
+        if world > 1:
+            mine = words_t[rank * rows_pad:(rank + 1) * rows_pad]
+            if r0 != rank * rows_pad:                 # cannot happen with row_shard's equal-size shards
+                raise RuntimeError("row shard does not line up with the gather buffer")
+            dist.all_gather_into_tensor(words_t, mine.clone())
         return nbh
 
     stage1().close()
+    words_t.zero_()
     ctx.profile(True)
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     nb = stage1()
-    ctx.synchronize()
+    torch.cuda.synchronize()
     t_stage1 = time.perf_counter() - t0
     k1_ms, _ = ctx.kernel_ms("euclid" if cfg["metric"] == "euclidean" else "sssp")
     ctx.profile(False)
@@ -431,7 +446,8 @@ def run_ours(args):
                 "workload": workload_name(cfg, args),
                 "step": "whole permutation null (operand prep + gather + tcgen05 digit GEMM with fused compare + "
                         "fp64 fix-up%s)" % (" + NCCL all-reduce of counts" if world > 1 else ""),
-                "parallelism": "permutations sharded %d-way" % world,
+                "parallelism": "stage 2: permutations sharded %d-way + one all-reduce of the counts; stage 1: source "
+                               "rows sharded %d-way + one all-gather of the packed rows" % (world, world),
                 "l2": "working set per batch (gathered operand %.0f MB/permutation) exceeds the 126 MB L2"
                       % (n * ((m + 63) // 64 * 64) * stats["digits"] / 1e6),
                 "node_order": "input nodes randomly renumbered; k-d tree order of the layout passed as a hint "

@@ -10,6 +10,14 @@ import numpy as np
 from .permutations import make_perm_rows, shard_bounds
 
 
+def row_shard(n, world_size, rank):
+    """Source rows [r0, r1) of stage 1 owned by `rank`: equal blocks of ceil(n / world) rows (the last may be short
+    or empty), so that the shards line up with an all-gather buffer of world * ceil(n / world) rows."""
+    per = -(-n // world_size)
+    r0 = min(n, rank * per)
+    return r0, min(n, r0 + per)
+
+
 def local_perm_rows(node2attribute, num_permutations, random_seed, world_size, rank):
     """Gather rows of this rank's shard.  Every rank replays the whole RNG stream (cumulative shuffles cannot be
     skipped ahead) and keeps its slice; returns (rows[lo:hi], lo, hi)."""

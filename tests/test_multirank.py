@@ -71,3 +71,14 @@ def test_shards_partition_the_stream():
     got = [local_perm_rows(b, 13, 5, 4, r) for r in range(4)]
     assert np.array_equal(np.concatenate([g[0] for g in got]), full)
     assert [(g[1], g[2]) for g in got] == [(0, 4), (4, 8), (8, 12), (12, 13)]
+
+
+def test_row_shards_cover_all_sources():
+    from safepy_b200.distributed import row_shard
+    for n, w in ((20000, 8), (3971, 4), (10, 4), (7, 8)):
+        per = -(-n // w)
+        got = [row_shard(n, w, r) for r in range(w)]
+        assert got[0][0] == 0 and max(b for _, b in got) == n
+        assert all(a == min(n, r * per) for r, (a, _) in enumerate(got))
+        covered = sorted(i for a, b in got for i in range(a, b))
+        assert covered == list(range(n))

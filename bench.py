@@ -437,6 +437,16 @@ def run_ours(args):
         flops_total = 2.0 * tiles * 256 * 64 * m * (hi - lo) * args.steps
         achieved_tf = flops_total / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None
         int8_ops = 2.0 * stats["ktile_iters"] * 256 * 64 * 64 * stats["digits"] * args.steps
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu capture (same workload): bytes per
+        # permutation x permutations per launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")) as f:
+                tr = json.load(f)
+            if args.workload == "C3" and args.scale == 1.0 and gemm_launches:
+                traffic = tr["dram_bytes_per_permutation"] * (hi - lo) * args.steps / gemm_launches
+        except (OSError, KeyError, ValueError):
+            traffic = None
         out = {
             "metric": "enrichment node-attr-perm scores/s", "value": value, "unit": "scores/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step,
@@ -470,7 +480,9 @@ def run_ours(args):
             "roofline": {
                 "kernel": "k_gemm<%d> (tcgen05.mma.kind::i8, %d launches)" % (stats["digits"], gemm_launches),
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": None,
+                "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": traffic,
+                "traffic_note": "DRAM read+write bytes per k_gemm launch, scaled from the ncu capture in "
+                                "profiles/r1d_gemm_traffic.json (bytes per permutation x permutations per launch)",
                 "peak_source": peak_src,
                 "executed_int8_tops": int8_ops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None,
                 "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,

@@ -152,6 +152,31 @@ int sb_enrich_stats(sb_enrich* e, int64_t* out7_host);
 int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host);
 int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev);
 
+/* ------------------------------------------------------------------ graph-side helpers (next rows) */
+
+/* safe_io.calculate_edge_lengths, safepy/safe_io.py:311-333: length[e] = sqrt(dx*dx + dy*dy) * weight[e], every
+ * operation rounded separately (pdist + np.multiply); weight_host == NULL means weight 1.  A zero weight yields NaN:
+ * the reference sets no 'length' attribute for such an edge (Dijkstra then charges its default cost 1). */
+int sb_graph_edge_lengths(sb_ctx* ctx, int64_t n, const double* x_host, const double* y_host, int64_t n_edges,
+                          const int32_t* eu_host, const int32_t* ev_host, const double* weight_host,
+                          double* length_out_host);
+
+/* Symmetric CSR of an undirected edge list (both directions stored, a self loop once, columns ascending inside a
+ * row) -- the adjacency networkx's all_pairs_dijkstra_path_length walks in safe.py:406-410.
+ * indices_out / value_out need room for 2 * n_edges entries; *nnz_out receives the number used. */
+int sb_graph_csr(sb_ctx* ctx, int64_t n, int64_t n_edges, const int32_t* eu_host, const int32_t* ev_host,
+                 const double* value_host, int64_t* indptr_out_host, int32_t* indices_out_host,
+                 double* value_out_host, int64_t* nnz_out);
+
+/* SAFE.define_top_attributes' connectivity test, safepy/safe.py:632-658: for every candidate attribute cand[k], the
+ * connected components of the subgraph induced by the nodes with member[v * m + cand[k]] != 0.
+ * labels_out (optional) [n_cand][n]: smallest node id of the node's component, -1 for non-members;
+ * num_cc_out[k] = number of components, num_large_out[k] = components with at least min_size nodes. */
+int sb_graph_components(sb_ctx* ctx, int64_t n, const int64_t* indptr_host, const int32_t* indices_host,
+                        const uint8_t* member_host, int64_t m, const int32_t* cand_host, int64_t n_cand,
+                        int32_t min_size, int32_t* labels_out_host, int32_t* num_cc_out_host,
+                        int32_t* num_large_out_host);
+
 /* ------------------------------------------------------------------ self-test hook (tests only)
  * Runs one 128 x N x K int8 tcgen05 GEMM from host operands through the production tile layouts and returns the
  * int32 accumulators; used to pin descriptor / layout encodings against a CPU product. */

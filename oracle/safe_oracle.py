@@ -240,3 +240,46 @@ def score_sum_csr(neighborhoods_u8, node2attribute, rows=None):
             acc += b[t]
         out[i] = acc
     return out
+
+
+# --------------------------------------------------------------------------------------------- next rows (8f)
+def edge_lengths(x, y, eu, ev, weight=None):
+    """safe_io.py:318-331 per edge: squareform(pdist(coords))[u, v] * adjacency[u, v]; zero adjacency entries become
+    NaN there and get no 'length' attribute (returned as NaN here).  pdist's sqrt(dx*dx + dy*dy) is unfused, and so
+    is NumPy's elementwise arithmetic."""
+    x = np.asarray(x, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64)
+    dx = x[eu] - x[ev]
+    dy = y[eu] - y[ev]
+    d = np.sqrt(dx * dx + dy * dy)
+    if weight is None:
+        return d
+    w = np.asarray(weight, dtype=np.float64)
+    out = d * w
+    out[w == 0] = np.nan
+    return out
+
+
+def top_attributes(indptr, indices, nes_binary, min_size):
+    """safe.py:626-658 with attribute_unimodality_metric='connectivity': (top, num_connected_components,
+    num_large_connected_components, list of component-size arrays sorted descending).  Attributes below the minimum
+    number of enriched neighborhoods are not examined (their counters stay 0, safe.py:635-638)."""
+    from scipy.sparse.csgraph import connected_components
+    nes_binary = np.asarray(nes_binary)
+    n, m = nes_binary.shape
+    g = csr_matrix((np.ones(len(indices), dtype=np.int8), indices, indptr), shape=(n, n))
+    num_enriched = np.sum(nes_binary, axis=0)
+    top = num_enriched >= min_size
+    num_cc = np.zeros(m, dtype=np.int64)
+    num_large = np.zeros(m, dtype=np.int64)
+    sizes = [None] * m
+    for j in np.nonzero(top)[0]:
+        nodes = np.nonzero(nes_binary[:, j] > 0)[0]
+        sub = g[nodes][:, nodes]
+        k, lab = connected_components(sub, directed=False)
+        s = np.sort(np.bincount(lab, minlength=k))[::-1]
+        num_cc[j] = k
+        num_large[j] = int(np.sum(s >= min_size))
+        sizes[j] = s
+    top = top & ~(num_cc > 1)
+    return top, num_cc, num_large, sizes

@@ -59,6 +59,9 @@ SIGNATURES = {
     "sb_enrich_stats": (C.c_int, [_vp, _vp]),
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
+    "sb_graph_edge_lengths": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "sb_graph_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
+    "sb_graph_components": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
     "sb_selftest_mma_i8": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "sb_selftest_mma_rate": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
 }
@@ -353,6 +356,52 @@ class Enrichment:
             self.close()
         except Exception:
             pass
+
+
+def edge_lengths(ctx, x, y, eu, ev, weight=None):
+    """safe_io.calculate_edge_lengths on the device: sqrt(dx*dx + dy*dy) * weight per edge (NaN for zero weights)."""
+    x = _as(x, np.float64)
+    y = _as(y, np.float64)
+    eu = _as(eu, np.int32)
+    ev = _as(ev, np.int32)
+    w = None if weight is None else _as(weight, np.float64)
+    out = np.empty(eu.shape[0], dtype=np.float64)
+    _check(ctx.lib, ctx.lib.sb_graph_edge_lengths(ctx.h, x.shape[0], _ptr(x), _ptr(y), eu.shape[0], _ptr(eu), _ptr(ev),
+                                                  _ptr(w), _ptr(out)))
+    return out
+
+
+def build_csr(ctx, n, eu, ev, value=None):
+    """Symmetric CSR (indptr int64, indices int32 ascending per row, values) of an undirected edge list."""
+    eu = _as(eu, np.int32)
+    ev = _as(ev, np.int32)
+    ne = eu.shape[0]
+    val = None if value is None else _as(value, np.float64)
+    indptr = np.empty(n + 1, dtype=np.int64)
+    indices = np.empty(max(2 * ne, 1), dtype=np.int32)
+    vout = None if value is None else np.empty(max(2 * ne, 1), dtype=np.float64)
+    nnz = _i64()
+    _check(ctx.lib, ctx.lib.sb_graph_csr(ctx.h, int(n), ne, _ptr(eu), _ptr(ev), _ptr(val), _ptr(indptr), _ptr(indices),
+                                         _ptr(vout), C.byref(nnz)))
+    k = nnz.value
+    return indptr, indices[:k].copy(), (None if vout is None else vout[:k].copy())
+
+
+def components(ctx, indptr, indices, member, candidates, min_size, want_labels=False):
+    """Connected components of the subgraphs induced by member[:, j] for j in candidates.
+    Returns (num_components, num_large_components, labels or None)."""
+    indptr = _as(indptr, np.int64)
+    indices = _as(indices, np.int32)
+    member = np.ascontiguousarray(np.asarray(member) != 0, dtype=np.uint8)
+    n, m = member.shape
+    cand = _as(candidates, np.int32)
+    k = cand.shape[0]
+    ncc = np.zeros(k, dtype=np.int32)
+    nlarge = np.zeros(k, dtype=np.int32)
+    labels = np.empty((k, n), dtype=np.int32) if want_labels else None
+    _check(ctx.lib, ctx.lib.sb_graph_components(ctx.h, n, _ptr(indptr), _ptr(indices), _ptr(member), m, _ptr(cand), k,
+                                                int(min_size), _ptr(labels), _ptr(ncc), _ptr(nlarge)))
+    return ncc, nlarge, labels
 
 
 def selftest_mma_i8(ctx, a, b, variant=0):

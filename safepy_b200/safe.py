@@ -77,8 +77,12 @@ def graph_csr(graph, weight):
     eu = np.empty(ne, dtype=np.int64)
     ev = np.empty(ne, dtype=np.int64)
     w = np.empty(ne, dtype=np.float64)
-    for k, (u, v, c) in enumerate(graph.edges(data=weight, default=1)):
-        eu[k], ev[k], w[k] = u, v, c
+    if weight is None:  # structure only
+        for k, (u, v) in enumerate(graph.edges()):
+            eu[k], ev[k], w[k] = u, v, 1.0
+    else:
+        for k, (u, v, c) in enumerate(graph.edges(data=weight, default=1)):
+            eu[k], ev[k], w[k] = u, v, c
     loop = eu == ev
     src = np.concatenate([eu, ev[~loop]])
     dst = np.concatenate([ev, eu[~loop]])
@@ -250,6 +254,45 @@ class SafeB200Mixin:
         self.nes = nes
 
 
+    # ---------------------------------------------------------------------------------- next call of the workflow
+    def define_top_attributes(self, **kwargs):
+        """safe.py:610-661.  The connectivity test (connected components of the subgraph induced by the enriched
+        nodes, one attribute after the other through networkx upstream) runs batched over attributes on the GPU."""
+        for k in ("attribute_unimodality_metric", "attribute_enrichment_min_size"):
+            if k in kwargs:
+                setattr(self, k, kwargs[k])
+        self.validate_config()
+        logging.info("Criteria for top attributes:")
+        logging.info("- minimum number of enriched neighborhoods: %d" % self.attribute_enrichment_min_size)
+        logging.info("- region-specific distribution of enriched neighborhoods as defined by: %s"
+                     % self.attribute_unimodality_metric)
+        self.attributes["top"] = False
+        self.attributes.loc[
+            self.attributes["num_neighborhoods_enriched"] >= self.attribute_enrichment_min_size, "top"] = True
+        if self.attribute_unimodality_metric == "connectivity":
+            self.attributes["num_connected_components"] = 0
+            self.attributes["size_connected_components"] = None
+            self.attributes["size_connected_components"] = self.attributes["size_connected_components"].astype(object)
+            self.attributes["num_large_connected_components"] = 0
+            cand = self.attributes.index.values[self.attributes["top"].values.astype(bool)]
+            if len(cand):
+                # safe.py:644-645: an edgeless network falls back to the Euclidean-distance graph
+                graph = self.graph_euclidean if getattr(self, "graph_euclidean", None) else self.graph
+                indptr, indices, _ = graph_csr(graph, None)
+                ncc, nlarge, labels = _lib.components(get_context(self.device), indptr, indices, self.nes_binary > 0,
+                                                      cand, self.attribute_enrichment_min_size, want_labels=True)
+                for k, attribute in enumerate(cand):
+                    lab = labels[k]
+                    sizes = np.sort(np.bincount(lab[lab >= 0]))[::-1]
+                    sizes = sizes[sizes > 0]
+                    self.attributes.loc[attribute, "num_connected_components"] = int(ncc[k])
+                    self.attributes.at[attribute, "size_connected_components"] = sizes
+                    self.attributes.loc[attribute, "num_large_connected_components"] = int(nlarge[k])
+            self.attributes.loc[self.attributes["num_connected_components"] > 1, "top"] = False
+        if self.verbose:
+            logging.info("Number of top attributes: %d" % np.sum(self.attributes["top"]))
+
+
 def _fdr_rows(pvalues):
     """Benjamini-Hochberg adjustment of every row across attributes (what safe.py:536-542 / 599-605 obtain from
     statsmodels.stats.multitest.fdrcorrection(method='indep')[1] per row)."""
@@ -353,10 +396,11 @@ class SAFE(SafeB200Mixin):
             raise ValueError("attribute_distance_threshold must be a float number in the (0,1) range.")
 
     # -- in-memory loaders (the reference's file formats are out of scope here)
-    def load_network(self, graph=None, edges=None, x=None, y=None, length=None, **kwargs):
+    def load_network(self, graph=None, edges=None, x=None, y=None, length=None, weight=None, **kwargs):
         """Either an nx.Graph in the reference's conventions (nodes 0..N-1 with 'x', 'y'; edges with 'length'), or
-        arrays: edges [E, 2], coordinates x, y and optional edge lengths (default: Euclidean layout distance, the
-        value safe_io.calculate_edge_lengths assigns for unit adjacency weights, safe_io.py:311-333)."""
+        arrays: edges [E, 2], coordinates x, y and either edge lengths or adjacency weights (default 1): lengths are
+        then computed on the device as safe_io.calculate_edge_lengths does (layout distance x weight,
+        safe_io.py:311-333; an edge with weight 0 gets no 'length', like upstream)."""
         import networkx as nx
         if "node_key_attribute" in kwargs:
             self.node_key_attribute = kwargs["node_key_attribute"]
@@ -366,13 +410,13 @@ class SAFE(SafeB200Mixin):
             y = np.asarray(y, dtype=np.float64)
             edges = np.zeros((0, 2), dtype=np.int64) if edges is None else np.asarray(edges, dtype=np.int64)
             if length is None and len(edges):
-                dx, dy = x[edges[:, 0]] - x[edges[:, 1]], y[edges[:, 0]] - y[edges[:, 1]]
-                length = np.sqrt(dx * dx + dy * dy)
+                length = _lib.edge_lengths(get_context(self.device), x, y, edges[:, 0], edges[:, 1], weight)
             graph = nx.Graph()
             graph.add_nodes_from((i, {"key": i, "x": float(x[i]), "y": float(y[i]), "label": str(i),
                                       self.node_key_attribute: str(i)}) for i in range(x.shape[0]))
             if len(edges):
-                graph.add_edges_from((int(u), int(v), {"length": float(w)}) for (u, v), w in zip(edges, length))
+                graph.add_edges_from((int(u), int(v), {} if w != w else {"length": float(w)})
+                                     for (u, v), w in zip(edges, length))
         self.graph = graph
 
     def load_attributes(self, attribute_file=None, **kwargs):

@@ -123,7 +123,8 @@ def test_fdr_rows_is_benjamini_hochberg():
 def test_loaders_accept_arrays_and_frames(stage1_small):
     net = net_from_golden(stage1_small)
     sf = SAFE(verbose=False)
-    sf.load_network(edges=net["edges"], x=net["x"], y=net["y"])
+    # explicit lengths: nothing to compute (without them the lengths come from the device, tests/test_next_rows.py)
+    sf.load_network(edges=net["edges"], x=net["x"], y=net["y"], length=net["length"])
     assert sf.graph.number_of_nodes() == net["n"] and sf.graph.number_of_edges() == len(net["edges"])
     _, _, w = graph_csr(sf.graph, "length")
     assert np.array_equal(w, net["csr_length"])

@@ -150,9 +150,11 @@ __global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ 
 // observed score in fp64 and combine the 32 partial sums in a fixed butterfly order.  (For the input classes whose
 // counts are pinned against the reference -- binary, integer, dyadic, float32-valued data -- these sums are exact in
 // fp64, so the summation order is immaterial; for the rest the reference's own BLAS order is unspecified.)
+// b_t is the attribute matrix TRANSPOSED ([m][n]): the scattered reads of one comparison then fall into one
+// n-element column (a bucket of 64 columns stays L2-resident even at 100k nodes x 5000 attributes).
 template <class T>
 __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                                               const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                               const T* __restrict__ b_t, const int32_t* __restrict__ perm, int64_t n,
                                                int64_t m, const uint64_t* __restrict__ flag_ij,
                                                const uint32_t* __restrict__ flag_p,
                                                unsigned int total, uint32_t* __restrict__ cneg,
@@ -164,11 +166,12 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
         const uint64_t ij = flag_ij[k];
         const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
         const int32_t* pr = perm + static_cast<int64_t>(flag_p[k]) * n;
+        const T* col = b_t + j * n;
         double sp = 0.0, so = 0.0;
         for (int64_t e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
             const int32_t t = col_idx[e];
-            const T vo = b[static_cast<int64_t>(t) * m + j];
-            const T vp = b[static_cast<int64_t>(pr[t]) * m + j];
+            const T vo = col[t];
+            const T vp = col[pr[t]];
             if (vo == vo) so += static_cast<double>(vo);
             if (vp == vp) sp += static_cast<double>(vp);
         }
@@ -398,19 +401,53 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
     }
 }
 
+// tiled transpose [n][m] -> [m][n]
+template <class T>
+__global__ void __launch_bounds__(256) k_transpose(const T* __restrict__ in, int64_t n, int64_t m, T* __restrict__ out) {
+    __shared__ T tile[32][33];
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32, c0 = static_cast<int64_t>(blockIdx.x) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k, c = c0 + tx;
+        if (r < n && c < m) tile[k][tx] = in[r * m + c];
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t c = c0 + k, r = r0 + tx;
+        if (r < n && c < m) out[c * n + r] = tile[tx][k];
+    }
+}
+
+static const void* transposed_b(sb_enrich* e) {
+    if (e->b_t) return e->b_t;
+    sb_ctx* ctx = e->ctx;
+    const size_t bytes = static_cast<size_t>(e->n) * e->m * (e->dtype == SB_F32 ? 4 : 8);
+    e->b_t = dev_alloc(bytes);
+    dim3 grid(static_cast<unsigned>(sb_ceil_div(e->m, 32)), static_cast<unsigned>(sb_ceil_div(e->n, 32)));
+    SB_CHECK(grid.y <= 65535, "attribute matrix has too many rows for the transpose kernel");
+    if (e->dtype == SB_F32)
+        k_transpose<float><<<grid, 256, 0, ctx->stream>>>(static_cast<const float*>(e->b), e->n, e->m,
+                                                          static_cast<float*>(e->b_t));
+    else
+        k_transpose<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(e->b), e->n, e->m,
+                                                           static_cast<double*>(e->b_t));
+    SB_LAUNCH_CHECK(ctx);
+    return e->b_t;
+}
+
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
                  unsigned int count, uint32_t* cneg, uint32_t* cpos) {
     sb_ctx* ctx = e->ctx;
+    const void* bt = transposed_b(e);
     const unsigned blocks = static_cast<unsigned>(
         std::min<int64_t>(sb_ceil_div(static_cast<int64_t>(count), 8), static_cast<int64_t>(ctx->num_sms) * 8));
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
-        k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b),
+        k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt),
                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos);
     else
-        k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p,
-                                                         static_cast<const double*>(e->b), perm_dev, e->n, e->m,
-                                                         flag_ij, flag_p, count, cneg, cpos);
+        k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt),
+                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos);
     SB_LAUNCH_CHECK(ctx);
 }
 
@@ -534,6 +571,7 @@ int sb_enrich_destroy(sb_enrich* e) {
         PhaseTrace tr(e->ctx, "enrich.destroy");
         if (e->tc) tc_plan_destroy(e->tc);
         if (e->b_owned && e->b) dev_free(const_cast<void*>(e->b));
+        if (e->b_t) dev_free(e->b_t);
         delete e;
     }
     SB_API_END

@@ -13,6 +13,7 @@ struct sb_enrich {
     int dtype = SB_F32;
     const void* b = nullptr;  // [n x m] row-major on the device, NaN = no data
     bool b_owned = false;
+    void* b_t = nullptr;      // [m x n] transposed copy for the fix-up kernel, built on first use
 
     // CSR view of the packed matrix (ascending column order inside a row)
     sb::DevBuf<int64_t> row_ptr;   // n + 1

@@ -88,6 +88,34 @@ def main():
                         frac=alg / (ms * 1e-3) / 1e9 / PEAK, call_wall_s=wall, first_call_wall_s=wall_first))
         plan.close()
         nb.close()
+    if only in (None, "components"):
+        # define_top_attributes' connectivity test at C3 size: 2000 attributes, each enriched in 1-3 spatial blobs
+        cfg = syn.make_config("C3", 0.1 if small else 1.0, shuffle=True)
+        net, n, m = cfg["net"], cfg["n"], cfg["m"]
+        rng = np.random.default_rng(3)
+        nb = np.zeros((n, m), dtype=np.uint8)
+        for j in range(m):
+            for _ in range(rng.integers(1, 4)):
+                c = rng.integers(0, n)
+                d = np.hypot(net["x"] - net["x"][c], net["y"] - net["y"][c])
+                nb[d < rng.uniform(0.03, 0.12), j] = 1
+        cand = np.nonzero(nb.sum(axis=0) >= 10)[0]
+        _lib.components(ctx, net["indptr"], net["indices"], nb, cand[:8], 10)
+        t0 = time.perf_counter()
+        ncc, nlarge, _ = _lib.components(ctx, net["indptr"], net["indices"], nb, cand, 10)
+        wall = time.perf_counter() - t0
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import safe_oracle as orc
+        t0 = time.perf_counter()
+        k = min(len(cand), 100)
+        sub = np.zeros_like(nb)
+        sub[:, cand[:k]] = nb[:, cand[:k]]
+        _, occ, _, _ = orc.top_attributes(net["indptr"], net["indices"], sub, 10)
+        cpu = (time.perf_counter() - t0) / k
+        assert np.array_equal(occ[cand[:k]], ncc[:k])
+        out.append(dict(kernel="k_components", workload="C3 nodes x %d candidate attributes" % len(cand), n=n,
+                        call_wall_s=wall, attributes_per_s=len(cand) / wall,
+                        cpu_scipy_s_per_attribute=cpu, mean_components=float(ncc.mean())))
     for o in out:
         print(json.dumps(o))
 

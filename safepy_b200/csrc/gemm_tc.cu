@@ -722,6 +722,25 @@ __global__ void __launch_bounds__(256) k_tile_occ(const uint32_t* __restrict__ w
     }
 }
 
+// number of distinct k-tiles that the row blocks of every band touch (one block per band)
+__global__ void __launch_bounds__(256) k_band_kt(const uint8_t* __restrict__ occ, int32_t n_rb, int32_t n_kt,
+                                                 int32_t band_rb, int32_t* __restrict__ band_cnt) {
+    const int b = blockIdx.x;
+    const int r0 = b * band_rb, r1 = min(n_rb, r0 + band_rb);
+    __shared__ int s_total;
+    if (threadIdx.x == 0) s_total = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int kt = threadIdx.x; kt < n_kt; kt += blockDim.x) {
+        int any = 0;
+        for (int r = r0; r < r1 && !any; ++r) any = occ[static_cast<size_t>(r) * n_kt + kt];
+        mine += any;
+    }
+    if (mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) band_cnt[b] = s_total;
+}
+
 // tile_kt / tile_rb lists from the occupancy flags; one block per row block (serial chunks + block scan).
 // Row blocks are padded to a multiple of TC_TPS tiles: padding entries get tile_rb = -1 (expanded as all-zero A
 // tiles, so they contribute nothing) and repeat the last valid k-tile id.
@@ -966,6 +985,7 @@ struct TcPlan {
     int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
     int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
     int64_t n_tiles_real = 0;  // non-empty tiles
+    int32_t band_rb = 0, n_bands = 1, band_kt = 0;  // L2 blocking: row blocks per band, max distinct k-tiles of a band
     bool usable = true;  // false: data contains +-inf -> SIMT engine
     DevBuf<uint64_t> a_bits;
     const int32_t* order = nullptr;  // e->order.p when the caller supplied a node order (internal row -> node)
@@ -1182,6 +1202,22 @@ static TcPlan* build_plan(sb_enrich* e) {
         std::vector<int32_t> h_cnt(pl->n_rb), h_ptr(pl->n_rb + 1);
         SB_CUDA(cudaMemcpyAsync(h_cnt.data(), rb_count.p, pl->n_rb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
+        {
+            // bands of about one row block per CTA pair: all pairs then work on the same (q chunk, column group) and
+            // the gathered slab they share is only what the band's neighborhoods reach
+            const int pairs = std::max(1, ctx->num_sms / 2);
+            pl->n_bands = std::max(1, static_cast<int>((pl->n_rb + pairs / 2) / pairs));
+            pl->band_rb = static_cast<int32_t>(sb_ceil_div(pl->n_rb, pl->n_bands));
+            pl->n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, pl->band_rb));
+            DevBuf<int32_t> band_cnt;
+            band_cnt.reserve(pl->n_bands);
+            k_band_kt<<<pl->n_bands, 256, 0, st>>>(occ.p, pl->n_rb, pl->n_kt, pl->band_rb, band_cnt.p);
+            SB_LAUNCH_CHECK(ctx);
+            std::vector<int32_t> h_band(pl->n_bands);
+            SB_CUDA(cudaMemcpyAsync(h_band.data(), band_cnt.p, pl->n_bands * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            pl->band_kt = *std::max_element(h_band.begin(), h_band.end());
+        }
         int64_t run = 0, real = 0;
         for (int i = 0; i < pl->n_rb; ++i) {
             h_ptr[i] = static_cast<int32_t>(run);
@@ -1317,20 +1353,14 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
     gp.mode = mode;
     gp.q_total = q_total;
     gp.batch_perms = batch_perms;
-    // L2 blocking (see decode_unit).  A band of row blocks keeps its A bit tiles (<= ~32 MB) resident.  The number of
+    // L2 blocking (see decode_unit; bands are chosen in build_plan).  The number of
     // slots per unit (q_per) trades per-unit epilogue overhead (observed-score preload, count flush) against the
     // gathered slab a band touches per (q chunk, column group): measured on C3, 13+ slots per unit (64 MB slabs, the
     // default; SB_SLAB_MB overrides) run 20 % faster than 4 and the 5-stage ring still hides the L2 / HBM latency.
     const double tile_b = static_cast<double>(TC_KT) * 64 * pl->D;
-    const double a_per_rb = static_cast<double>(pl->n_tiles) * TC_PROWS * 8 / pl->n_rb;
-    int band = static_cast<int>(std::max(1.0, (32 << 20) / a_per_rb));
-    band = std::max(band, std::min(pl->n_rb, ctx->num_sms / 2));
-    band = std::min(band, static_cast<int>(pl->n_rb));
-    gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, band));
-    gp.band_rb = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.n_bands));
-    gp.n_bands = static_cast<int32_t>(sb_ceil_div(pl->n_rb, gp.band_rb));
-    const double touched = std::min(1.0, 3.0 * gp.band_rb * TC_PROWS / static_cast<double>(pl->n));
-    const double slab = pl->n_kt * tile_b * touched;
+    gp.band_rb = pl->band_rb;
+    gp.n_bands = pl->n_bands;
+    const double slab = std::max(1, pl->band_kt) * tile_b;  // gathered bytes a band touches per (slot, column group)
     static const double slab_mb = getenv("SB_SLAB_MB") ? atof(getenv("SB_SLAB_MB")) : 64.0;
     int q_per = static_cast<int>(std::max(1.0, std::min(64.0, slab_mb * (1 << 20) / slab)));
     // enough units to keep every SM busy with a few units each

@@ -153,17 +153,19 @@ def test_counts_properties_without_reference(ctx, stage1_small):
     assert np.all(cneg <= 25) and np.all(cpos <= 25)
 
 
-def test_node_order_hint_does_not_change_counts(ctx, stage1_mid):
-    """Any internal node order (identity, random, k-d tree of the layout) must give the same counts."""
+@pytest.mark.parametrize("m", [3, 70])
+def test_node_order_hint_does_not_change_counts(ctx, stage1_mid, m):
+    """Any internal node order (identity, random, k-d tree of the layout) must give the same counts
+    (m = 3 exercises the packed small-M slots, m = 70 two column groups)."""
     from safepy_b200.ordering import kd_order
     from safepy_b200.permutations import make_perm_rows
     g = stage1_mid
     n = g["x"].shape[0]
     rng = np.random.default_rng(5)
-    attrs = rng.standard_normal((n, 70)).astype(np.float32)
+    attrs = rng.standard_normal((n, m)).astype(np.float32)
     attrs[rng.uniform(size=n) < 0.05] = np.nan
     nb = _lib.Neighborhoods(ctx, n).upload_packed(g["nb_layout"])
-    rows = make_perm_rows(attrs, 9, 3)
+    rows = make_perm_rows(attrs, 70 if m < 64 else 9, 3)
     ref = _lib.Enrichment(nb, attrs).perm_counts(rows, "sum", "simt")
     for order in (None, rng.permutation(n), kd_order(g["x"], g["y"])):
         plan = _lib.Enrichment(nb, attrs)

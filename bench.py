@@ -441,7 +441,7 @@ def run_ours(args):
         # permutation x permutations per launch
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r1d_gemm_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r1e_gemm_traffic.json")) as f:
                 tr = json.load(f)
             if args.workload == "C3" and args.scale == 1.0 and gemm_launches:
                 traffic = tr["dram_bytes_per_permutation"] * (hi - lo) * args.steps / gemm_launches
@@ -482,7 +482,7 @@ def run_ours(args):
                 "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf if achieved_tf else None, "traffic": traffic,
                 "traffic_note": "DRAM read+write bytes per k_gemm launch, scaled from the ncu capture in "
-                                "profiles/r1d_gemm_traffic.json (bytes per permutation x permutations per launch)",
+                                "profiles/r1e_gemm_traffic.json (bytes per permutation x permutations per launch)",
                 "peak_source": peak_src,
                 "executed_int8_tops": int8_ops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else None,
                 "gemm_share_of_step": gemm_ms / ms_total if ms_total else None,

@@ -152,6 +152,40 @@ int sb_enrich_stats(sb_enrich* e, int64_t* out7_host);
 int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host);
 int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev);
 
+/* ------------------------------------------------------------------ stage 2: streaming null + fused tail
+ * Same arithmetic as sb_enrich_perm_counts, but the two count arrays stay on the device between calls: the caller feeds
+ * permutation indices in pieces while it is still replaying the reference's sequential RNG stream
+ * (safe_extras.py:46-58), and sb_enrich_null_finalize turns the counts into everything compute_pvalues leaves on the
+ * SAFE object without the counts visiting the host. */
+int sb_enrich_null_begin(sb_enrich* e, int score_type, int engine);
+/* perm_rows_host: [num_perm][n] gather rows as for sb_enrich_perm_counts; may be called any number of times */
+int sb_enrich_null_add(sb_enrich* e, const int32_t* perm_rows_host, int64_t num_perm);
+/* permutations counted so far and (optionally) the raw counts; any pointer may be NULL */
+int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_neg_host, uint32_t* counts_pos_host);
+
+/* Tail of SAFE.compute_pvalues_by_randomization (safe.py:526-554) and of SAFE.compute_pvalues (safe.py:466-472):
+ *   p = counts / P (NaN where the observed score is NaN); optional Benjamini-Hochberg adjustment of every row across
+ *   attributes (multiple_testing, safe.py:536-542); NES+- = -log10(p == 0 ? zero_pvalue_floor : p);
+ *   nes = NES+ (attribute_sign 0 'highest'), NES- (1 'lowest') or NES+ - NES- (2 'both');
+ *   nes_binary = |nes| > nes_threshold; num_enriched[j] = sum_i nes_binary[i][j].
+ * The caller supplies pvalue_of_count[c] = c / P and nes_of_count[c] = -log10(c == 0 ? 1/P : c / P) for c = 0..P
+ * (table_len = P + 1) computed with its own libm, so that without FDR every output carries exactly the bits the
+ * reference's NumPy expressions produce.  Outputs are [n x m] fp64 (num_enriched: [m]); any of them may be NULL. */
+int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, const double* nes_of_count_host,
+                            int64_t table_len, int multiple_testing, double zero_pvalue_floor, int attribute_sign,
+                            double nes_threshold, double* ns_host, double* pvalues_neg_host, double* pvalues_pos_host,
+                            double* nes_host, double* nes_binary_host, double* num_enriched_host);
+
+/* sb_enrich_hypergeom followed by the optional row-wise FDR (safe.py:599-605), nes = -log10 p and the same
+ * nes_binary / num_enriched tail (safe.py:466-472).  Any output may be NULL. */
+int sb_enrich_hypergeom_finalize(sb_enrich* e, int multiple_testing, double nes_threshold, double* pvalues_host,
+                                 double* nes_host, double* nes_binary_host, double* num_enriched_host);
+
+/* Benjamini-Hochberg adjustment of every row of pvalues [n x m] across its m entries -- what
+ * np.apply_along_axis(statsmodels.stats.multitest.fdrcorrection, 1, p)[:, 1, :] yields in safe.py:536-542 / 599-605
+ * (method 'indep': sorted p / ((k + 1) / m), reverse running minimum, capped at 1; a NaN makes its whole row NaN). */
+int sb_fdr_rows(sb_ctx* ctx, int64_t n, int64_t m, const double* pvalues_host, double* adjusted_host);
+
 /* ------------------------------------------------------------------ graph-side helpers (next rows) */
 
 /* safe_io.calculate_edge_lengths, safepy/safe_io.py:311-333: length[e] = sqrt(dx*dx + dy*dy) * weight[e], every
@@ -176,6 +210,13 @@ int sb_graph_components(sb_ctx* ctx, int64_t n, const int64_t* indptr_host, cons
                         const uint8_t* member_host, int64_t m, const int32_t* cand_host, int64_t n_cand,
                         int32_t min_size, int32_t* labels_out_host, int32_t* num_cc_out_host,
                         int32_t* num_large_out_host);
+
+/* The metric evaluation inside SAFE.define_domains' linkage(nes_binary[:, top].T, 'average', metric='jaccard'),
+ * safepy/safe.py:672-675 (scipy pdist 'jaccard' on 0/1 rows): for the columns cols[0..n_cols) of member [n x m]
+ * (non-zero = enriched), d(a, b) = |a xor b| / |a or b| (0 when both are empty), in pdist's condensed order
+ * (n_cols * (n_cols - 1) / 2 doubles). */
+int sb_attr_jaccard(sb_ctx* ctx, int64_t n, const uint8_t* member_host, int64_t m, const int32_t* cols_host,
+                    int64_t n_cols, double* condensed_out_host);
 
 /* ------------------------------------------------------------------ self-test hook (tests only)
  * Runs one 128 x N x K int8 tcgen05 GEMM from host operands through the production tile layouts and returns the

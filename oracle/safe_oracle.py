@@ -283,3 +283,86 @@ def top_attributes(indptr, indices, nes_binary, min_size):
         sizes[j] = s
     top = top & ~(num_cc > 1)
     return top, num_cc, num_large, sizes
+
+
+# --------------------------------------------------------------------------------------------- FDR
+def fdrcorrection(pvals):
+    """statsmodels.stats.multitest.fdrcorrection(pvals, alpha=0.05, method='indep', is_sorted=False)[1], the call
+    safe.py:538,541,604 makes through np.apply_along_axis.  PARITY UNPINNED: statsmodels==0.14.4 (pinned in the
+    reference's extras/requirements.txt:6) is not installed in this image and cannot be (no network), so this is a
+    restatement of its published algorithm, not a replay:
+        sortind = argsort(p); ps = p[sortind]; ecdf = arange(1, n + 1) / float(n)
+        raw = ps / ecdf; adj = minimum.accumulate(raw[::-1])[::-1]; adj[adj > 1] = 1; out[sortind] = adj
+    NaNs sort last and np.minimum propagates them, so one NaN turns the whole vector into NaN."""
+    pvals = np.asarray(pvals, dtype=np.float64)
+    nobs = len(pvals)
+    sortind = np.argsort(pvals)
+    ps = np.take(pvals, sortind)
+    ecdf = np.arange(1, nobs + 1) / float(nobs)
+    with np.errstate(invalid="ignore"):
+        raw = ps / ecdf
+        adj = np.minimum.accumulate(raw[::-1])[::-1]
+        adj[adj > 1] = 1
+    out = np.empty_like(adj)
+    out[sortind] = adj
+    return out
+
+
+def fdr_rows(pvalues):
+    """np.apply_along_axis(fdrcorrection, 1, pvalues)[:, 1, :] of safe.py:538-542 / 604-605."""
+    pvalues = np.asarray(pvalues, dtype=np.float64)
+    return np.stack([fdrcorrection(r) for r in pvalues]) if len(pvalues) else pvalues.copy()
+
+
+def randomization_tail(ns, counts_neg, counts_pos, num_permutations, attribute_sign, multiple_testing,
+                       enrichment_threshold):
+    """safe.py:528-554 followed by safe.py:466-472: (pvalues_neg, pvalues_pos, nes, nes_binary, num_enriched)."""
+    counts_neg = np.array(counts_neg, dtype=np.float64)
+    counts_pos = np.array(counts_pos, dtype=np.float64)
+    idx = np.isnan(ns)
+    counts_neg[idx] = np.nan
+    counts_pos[idx] = np.nan
+    pvalues_neg = counts_neg / num_permutations
+    pvalues_pos = counts_pos / num_permutations
+    if multiple_testing:
+        pvalues_neg = fdr_rows(pvalues_neg)
+        pvalues_pos = fdr_rows(pvalues_pos)
+    nes_pos = -np.log10(np.where(pvalues_pos == 0, 1 / num_permutations, pvalues_pos))
+    nes_neg = -np.log10(np.where(pvalues_neg == 0, 1 / num_permutations, pvalues_neg))
+    nes = {"highest": nes_pos, "lowest": nes_neg}.get(attribute_sign, nes_pos - nes_neg)
+    nb = nes_binary(nes, enrichment_threshold)
+    return pvalues_neg, pvalues_pos, nes, nb, np.sum(nb, axis=0)
+
+
+# --------------------------------------------------------------------------------------------- domains (8f rank 4)
+def jaccard_condensed(nes_binary_matrix, columns):
+    """The distances linkage(m, metric='jaccard') evaluates for m = nes_binary[:, top].T (safe.py:672-673):
+    scipy.spatial.distance.pdist on the 0/1 float rows."""
+    m = np.asarray(nes_binary_matrix, dtype=np.float64)[:, columns].T
+    return pdist(m, metric="jaccard")
+
+
+def define_domains(nes, nes_binary_matrix, top, attribute_distance_threshold, attribute_distance_metric="jaccard"):
+    """safe.py:672-708: (domain per attribute, node2domain counts [n, n_domains + 1] with column d = domain id d,
+    primary_domain, primary_nes).  The reference's two `groupby(level='domain', axis=1)` calls (sum / max over the
+    attributes of a domain; pandas >= 3 no longer accepts axis=1) are written out with NumPy."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    nes = np.asarray(nes)
+    nb = np.asarray(nes_binary_matrix)
+    top = np.asarray(top, dtype=bool)
+    Z = linkage(nb[:, top].T, method="average", metric=attribute_distance_metric)
+    max_d = np.max(Z[:, 2] * attribute_distance_threshold)
+    domains = fcluster(Z, max_d, criterion="distance")
+    domain = np.zeros(nb.shape[1], dtype=np.int64)
+    domain[top] = domains
+    ids = np.unique(domain)                                    # groupby sorts its keys
+    counts = np.stack([nb[:, domain == d].sum(axis=1) for d in ids], axis=1)
+    maxnes = np.stack([nes[:, domain == d].max(axis=1) for d in ids], axis=1)
+    real = ids >= 1                                            # .loc[:, 1:]
+    t_max = counts[:, real].max(axis=1)
+    primary = ids[real][np.argmax(counts[:, real], axis=1)]    # idxmax: first maximum
+    primary[t_max == 0] = 0
+    col_of = {d: k for k, d in enumerate(ids)}
+    has0 = 0 in col_of
+    primary_nes = np.array([maxnes[i, col_of[d]] if (d != 0 or has0) else np.nan for i, d in enumerate(primary)])
+    return domain, ids, counts, primary, primary_nes

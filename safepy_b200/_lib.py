@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libsafe_b200.so")
 SB_F32, SB_F64 = 0, 1
 SCORE_TYPES = {"sum": 0, "z-score": 1}
 ENGINES = {"auto": 0, "simt": 1, "tc": 2}
+ATTRIBUTE_SIGNS = {"highest": 0, "lowest": 1, "both": 2}
 KERNEL_CLASSES = {"gemm": 0, "gather": 1, "fixup": 2, "sssp": 3, "euclid": 4, "hypergeom": 5, "score": 6, "prep": 7}
 
 _vp = C.c_void_p
@@ -59,6 +60,14 @@ SIGNATURES = {
     "sb_enrich_stats": (C.c_int, [_vp, _vp]),
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
+    "sb_enrich_null_begin": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "sb_enrich_null_add": (C.c_int, [_vp, _vp, _i64]),
+    "sb_enrich_null_counts": (C.c_int, [_vp, C.POINTER(_i64), _vp, _vp]),
+    "sb_enrich_null_finalize": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_double, C.c_int, C.c_double,
+                                          _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sb_enrich_hypergeom_finalize": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
+    "sb_fdr_rows": (C.c_int, [_vp, _i64, _i64, _vp, _vp]),
+    "sb_attr_jaccard": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "sb_graph_edge_lengths": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sb_graph_csr": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64)]),
     "sb_graph_components": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp]),
@@ -334,6 +343,58 @@ class Enrichment:
                                                             _vp(int(perm_dev)), int(num_perm), _vp(int(cneg_dev)),
                                                             _vp(int(cpos_dev))))
 
+    # -- streaming null: counts stay on the device until null_finalize / null_counts
+    def null_begin(self, score_type="sum", engine="auto"):
+        _check(self.lib, self.lib.sb_enrich_null_begin(self.h, SCORE_TYPES[score_type], ENGINES[engine]))
+        return self
+
+    def null_add(self, perm_rows):
+        perm_rows = _as(perm_rows, np.int32)
+        if perm_rows.ndim != 2 or perm_rows.shape[1] != self.n:
+            raise ValueError("perm_rows must be [num_permutations, n]")
+        _check(self.lib, self.lib.sb_enrich_null_add(self.h, _ptr(perm_rows), perm_rows.shape[0]))
+        return self
+
+    def null_counts(self, want_counts=True):
+        """(permutations counted so far, counts_neg, counts_pos)"""
+        num = _i64()
+        cneg = np.empty((self.n, self.m), dtype=np.uint32) if want_counts else None
+        cpos = np.empty((self.n, self.m), dtype=np.uint32) if want_counts else None
+        _check(self.lib, self.lib.sb_enrich_null_counts(self.h, C.byref(num), _ptr(cneg), _ptr(cpos)))
+        return num.value, cneg, cpos
+
+    def null_finalize(self, num_permutations, attribute_sign="both", enrichment_threshold=0.05,
+                      multiple_testing=False, want=("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")):
+        """Counts -> everything compute_pvalues leaves on the SAFE object (safe.py:526-554, 466-472).  The p-value and
+        NES of every possible count are computed here with NumPy, by the reference's own expressions, and looked up
+        on the device."""
+        num_permutations = int(num_permutations)
+        counts = np.arange(num_permutations + 1, dtype=np.float64)
+        ptab = counts / num_permutations                                            # safe.py:532-533
+        floor = 1 / num_permutations
+        nestab = -np.log10(np.where(ptab == 0, floor, ptab))                        # safe.py:546-547
+        thr = float(-np.log10(enrichment_threshold))                                # safe.py:468
+        out = {k: np.empty((self.n, self.m), dtype=np.float64) for k in want}
+        out["num_neighborhoods_enriched"] = np.empty(self.m, dtype=np.float64)
+        _check(self.lib, self.lib.sb_enrich_null_finalize(
+            self.h, _ptr(ptab), _ptr(nestab), ptab.shape[0], int(bool(multiple_testing)), float(floor),
+            ATTRIBUTE_SIGNS[attribute_sign], thr, _ptr(out.get("ns")), _ptr(out.get("pvalues_neg")),
+            _ptr(out.get("pvalues_pos")), _ptr(out.get("nes")), _ptr(out.get("nes_binary")),
+            _ptr(out["num_neighborhoods_enriched"])))
+        return out
+
+    def hypergeom_finalize(self, enrichment_threshold=0.05, multiple_testing=False,
+                           want=("pvalues_pos", "nes", "nes_binary")):
+        """Hypergeometric p-values, optional row-wise FDR, NES, nes_binary and the enriched-neighborhood counts
+        (safe.py:573-608, 466-472)."""
+        thr = float(-np.log10(enrichment_threshold))
+        out = {k: np.empty((self.n, self.m), dtype=np.float64) for k in want}
+        out["num_neighborhoods_enriched"] = np.empty(self.m, dtype=np.float64)
+        _check(self.lib, self.lib.sb_enrich_hypergeom_finalize(
+            self.h, int(bool(multiple_testing)), thr, _ptr(out.get("pvalues_pos")), _ptr(out.get("nes")),
+            _ptr(out.get("nes_binary")), _ptr(out["num_neighborhoods_enriched"])))
+        return out
+
     def stats(self):
         out = np.zeros(7, dtype=np.int64)
         _check(self.lib, self.lib.sb_enrich_stats(self.h, _ptr(out)))
@@ -402,6 +463,28 @@ def components(ctx, indptr, indices, member, candidates, min_size, want_labels=F
     _check(ctx.lib, ctx.lib.sb_graph_components(ctx.h, n, _ptr(indptr), _ptr(indices), _ptr(member), m, _ptr(cand), k,
                                                 int(min_size), _ptr(labels), _ptr(ncc), _ptr(nlarge)))
     return ncc, nlarge, labels
+
+
+def fdr_rows(ctx, pvalues):
+    """Benjamini-Hochberg adjustment of every row across its entries (statsmodels fdrcorrection, method 'indep')."""
+    p = _as(pvalues, np.float64)
+    if p.ndim != 2:
+        raise ValueError("pvalues must be 2-D")
+    out = np.empty_like(p)
+    if p.size:
+        _check(ctx.lib, ctx.lib.sb_fdr_rows(ctx.h, p.shape[0], p.shape[1], _ptr(p), _ptr(out)))
+    return out
+
+
+def jaccard(ctx, member, columns):
+    """Condensed Jaccard distance matrix (scipy pdist order) between the given columns of a 0/1 [n, m] matrix."""
+    member = np.ascontiguousarray(np.asarray(member) != 0, dtype=np.uint8)
+    n, m = member.shape
+    cols = _as(columns, np.int32)
+    k = cols.shape[0]
+    out = np.empty(k * (k - 1) // 2, dtype=np.float64)
+    _check(ctx.lib, ctx.lib.sb_attr_jaccard(ctx.h, n, _ptr(member), m, _ptr(cols), k, _ptr(out)))
+    return out
 
 
 def selftest_mma_i8(ctx, a, b, variant=0):

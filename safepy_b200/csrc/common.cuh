@@ -169,5 +169,12 @@ struct sb_neigh {
     bool owned = false;
 };
 
+namespace sb {
+// Device -> pageable host copy of a large result array (finalize.cu): pieces go through a pinned ring at full PCIe
+// speed and worker threads move them into the caller's buffer, so that the first-touch page faults of a freshly
+// allocated destination are taken in parallel.  Returns after the whole copy has landed.
+void copy_out(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+}  // namespace sb
+
 static inline int64_t sb_ld_words(int64_t n) { return ((n + 31) / 32 + 3) / 4 * 4; }
 static inline int64_t sb_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -32,6 +32,14 @@ struct sb_enrich {
 
     sb::TcPlan* tc = nullptr;
     int64_t stats[7] = {0, 0, 0, 0, 0, 0, 0};
+
+    // streaming null (sb_enrich_null_*, finalize.cu): the two count arrays stay on the device between calls
+    sb::DevBuf<uint32_t> null_cnt;   // [2][n * m]: neg, pos
+    sb::DevBuf<int32_t> null_perm;   // staging for one piece of permutation indices
+    int null_score = -1;             // -1: no null open
+    int null_engine = 0;
+    int64_t null_perms = 0;
+    int64_t null_stats[7] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace sb {

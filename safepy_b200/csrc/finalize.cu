@@ -1,0 +1,590 @@
+// What follows the permutation null / the hypergeometric test inside SAFE.compute_pvalues, and the next rows of
+// SURVEY.md section 8f that consume its output:
+//   streaming null      sb_enrich_null_begin / _add / _counts: the count arrays stay on the device while the caller is
+//                       still replaying the reference's sequential RNG stream
+//   k_null_tail         counts -> p-values -> NES -> nes_binary -> enriched neighborhoods per attribute, i.e. the tail
+//                       of compute_pvalues_by_randomization (reference safepy/safe.py:526-554) and of compute_pvalues
+//                       (safe.py:466-472) in one pass; p-values and NES of the P + 1 possible counts come from
+//                       host-made tables, so they carry the host libm's bits
+//   k_bh_rows           Benjamini-Hochberg adjustment of every row across attributes (multiple_testing=True,
+//                       safe.py:536-542 / 599-605: statsmodels fdrcorrection(method='indep') per row) after a
+//                       segmented sort of the row
+//   k_jaccard           pairwise Jaccard distances between nes_binary columns of the top attributes, the metric
+//                       evaluation inside define_domains' linkage(..., metric='jaccard') (safe.py:672-675)
+//   copy_out            large device -> host result copies through a pinned ring drained by worker threads
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include <cub/device/device_segmented_sort.cuh>
+
+#include "enrich.cuh"
+
+namespace sb {
+
+// ================================================================================================ copy_out
+namespace {
+
+struct OutRing {
+    static constexpr int kSlots = 16;
+    static constexpr size_t kSlot = 4u << 20;
+    struct Task {
+        int slot;
+        int device;
+        void* dst;
+        size_t bytes;
+    };
+    char* pinned = nullptr;
+    cudaEvent_t ev[kSlots];
+    bool busy[kSlots];
+    std::mutex mu;                 // queue + busy flags
+    std::condition_variable cv_work, cv_done;
+    std::deque<Task> queue;
+    int pending = 0;
+    std::mutex call_mu;            // one copy_out at a time
+    int workers = 0;
+
+    void start() {
+        SB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pinned), kSlots * kSlot, cudaHostAllocDefault));
+        for (int i = 0; i < kSlots; ++i) {
+            SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+            busy[i] = false;
+        }
+        const unsigned hw = std::thread::hardware_concurrency();
+        workers = static_cast<int>(std::max(2u, std::min(8u, hw ? hw : 2u)));
+        for (int w = 0; w < workers; ++w) std::thread([this] { run(); }).detach();
+    }
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [this] { return !queue.empty(); });
+                t = queue.front();
+                queue.pop_front();
+            }
+            cudaSetDevice(t.device);
+            cudaEventSynchronize(ev[t.slot]);
+            memcpy(t.dst, pinned + static_cast<size_t>(t.slot) * kSlot, t.bytes);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                busy[t.slot] = false;
+                --pending;
+            }
+            cv_done.notify_all();
+        }
+    }
+};
+
+OutRing* out_ring() {
+    static OutRing* ring = nullptr;  // leaked on purpose: detached workers may outlive static destruction
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!ring) {
+        OutRing* r = new OutRing;
+        r->start();
+        ring = r;
+    }
+    return ring;
+}
+
+}  // namespace
+
+void copy_out(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (bytes == 0) return;
+    cudaStream_t st = ctx->stream;
+    if (bytes < 2 * OutRing::kSlot) {
+        SB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    PhaseTrace tr(ctx, "copy_out");
+    OutRing* r = out_ring();
+    std::lock_guard<std::mutex> call(r->call_mu);
+    const char* src = static_cast<const char*>(src_dev);
+    char* dst = static_cast<char*>(dst_host);
+    int slot = 0;
+    cudaError_t err = cudaSuccess;
+    for (size_t off = 0; off < bytes && err == cudaSuccess; off += OutRing::kSlot, slot = (slot + 1) % OutRing::kSlots) {
+        const size_t len = std::min(OutRing::kSlot, bytes - off);
+        {
+            std::unique_lock<std::mutex> lk(r->mu);
+            r->cv_done.wait(lk, [&] { return !r->busy[slot]; });
+            r->busy[slot] = true;
+            ++r->pending;
+        }
+        err = cudaMemcpyAsync(r->pinned + static_cast<size_t>(slot) * OutRing::kSlot, src + off, len,
+                              cudaMemcpyDeviceToHost, st);
+        if (err == cudaSuccess) err = cudaEventRecord(r->ev[slot], st);
+        {
+            // even after a failed launch the slot goes through a worker (the event then refers to earlier work)
+            std::lock_guard<std::mutex> lk(r->mu);
+            r->queue.push_back({slot, ctx->device, dst + off, err == cudaSuccess ? len : 0});
+        }
+        r->cv_work.notify_one();
+    }
+    {
+        std::unique_lock<std::mutex> lk(r->mu);
+        r->cv_done.wait(lk, [&] { return r->pending == 0; });
+    }
+    SB_CUDA(err);
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ================================================================================================ kernels
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7FF8000000000000ll); }
+
+constexpr int kTailRows = 16;  // rows per block of the column-strip kernels
+
+// One thread per attribute column, kTailRows consecutive rows per block: loads and stores of a warp are 256 contiguous
+// bytes of one row, and the enriched-neighborhood count of a column costs one atomic per thread.
+//   FROM_COUNTS   pn / pp / NES from the count tables (bit-identical to the host's division and log10)
+//   !FROM_COUNTS  pn / pp already hold (FDR-adjusted) p-values; NES = -log10(p == 0 ? floor : p) on the device
+template <bool FROM_COUNTS>
+__global__ void __launch_bounds__(256) k_null_tail(const uint32_t* __restrict__ cneg, const uint32_t* __restrict__ cpos,
+                                                   const double* __restrict__ ns, const double* __restrict__ ptab,
+                                                   const double* __restrict__ nestab, uint32_t tab_len, double floor_p,
+                                                   int sign, double thr, int64_t rows, int64_t m,
+                                                   double* __restrict__ pn, double* __restrict__ pp,
+                                                   double* __restrict__ nes, double* __restrict__ nb,
+                                                   int32_t* __restrict__ colcnt) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (j >= m) return;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kTailRows;
+    const int64_t r1 = min(rows, r0 + kTailRows);
+    int32_t enriched = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t at = r * m + j;
+        double nes_pos, nes_neg;
+        if (FROM_COUNTS) {
+            const uint32_t cn = min(cneg[at], tab_len - 1), cp = min(cpos[at], tab_len - 1);
+            const bool dead = isnan(ns[at]);  // safe.py:528-530
+            const double vn = dead ? qnan() : ptab[cn], vp = dead ? qnan() : ptab[cp];
+            pn[at] = vn;
+            pp[at] = vp;
+            nes_neg = dead ? qnan() : nestab[cn];
+            nes_pos = dead ? qnan() : nestab[cp];
+        } else {
+            const double vn = pn[at], vp = pp[at];
+            nes_neg = -log10(vn == 0.0 ? floor_p : vn);  // safe.py:546-547
+            nes_pos = -log10(vp == 0.0 ? floor_p : vp);
+        }
+        const double v = sign == 0 ? nes_pos : (sign == 1 ? nes_neg : __dsub_rn(nes_pos, nes_neg));
+        nes[at] = v;
+        const bool hit = fabs(v) > thr;  // NaN compares false: nes_binary stays 0 (safe.py:466-468)
+        nb[at] = hit ? 1.0 : 0.0;
+        enriched += hit;
+    }
+    if (enriched) atomicAdd(&colcnt[j], enriched);
+}
+
+// hypergeometric tail: optional nes = -log10(p) (after FDR), then nes_binary and the column counts
+template <bool NES_FROM_P>
+__global__ void __launch_bounds__(256) k_binarize(const double* __restrict__ p, double* __restrict__ nes, double thr,
+                                                  int64_t rows, int64_t m, double* __restrict__ nb,
+                                                  int32_t* __restrict__ colcnt) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (j >= m) return;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * kTailRows;
+    const int64_t r1 = min(rows, r0 + kTailRows);
+    int32_t enriched = 0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const int64_t at = r * m + j;
+        double v;
+        if (NES_FROM_P) {
+            v = -log10(p[at]);
+            nes[at] = v;
+        } else {
+            v = nes[at];
+        }
+        const bool hit = fabs(v) > thr;
+        nb[at] = hit ? 1.0 : 0.0;
+        enriched += hit;
+    }
+    if (enriched) atomicAdd(&colcnt[j], enriched);
+}
+
+__global__ void k_colcnt_to_f64(const int32_t* __restrict__ c, int64_t m, double* __restrict__ out) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j < m) out[j] = static_cast<double>(c[j]);
+}
+
+__global__ void k_bh_prepare(int64_t rows, int64_t m, int32_t* __restrict__ idx, int64_t* __restrict__ offsets) {
+    const int64_t cells = rows * m;
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t r = i; r <= rows; r += step) offsets[r] = r * m;
+    for (; i < cells; i += step) idx[i] = static_cast<int32_t>(i % m);
+}
+
+// One CTA per row.  keys = the row's p-values ascending, idx = their columns.  statsmodels' fdrcorrection:
+//   ecdf[k] = (k + 1) / m;  raw[k] = p_sorted[k] / ecdf[k];  adj = reverse running minimum of raw, capped at 1,
+// scattered back to the original columns.  A NaN anywhere in the row propagates through np.minimum.accumulate from
+// the end (NaNs sort last), so the whole row becomes NaN.  Tied p-values all receive the value of the last of them
+// (the quotient is monotone in k), so the order a sort leaves ties in does not matter.
+__global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys, const int32_t* __restrict__ idx,
+                                                 int64_t m, double* __restrict__ out) {
+    const int64_t row = blockIdx.x;
+    const double* k = keys + row * m;
+    const int32_t* ix = idx + row * m;
+    double* o = out + row * m;
+    const int t = threadIdx.x;
+    const bool has_nan = isnan(k[m - 1]) || isnan(k[0]);
+    const double dm = static_cast<double>(m);
+    const int64_t seg = (m + 255) / 256;
+    const int64_t b = min(m, t * seg), e = min(m, b + seg);
+    __shared__ double part[256];
+    double mn = __longlong_as_double(0x7FF0000000000000ll);  // +inf
+    for (int64_t i = b; i < e; ++i) mn = fmin(mn, __ddiv_rn(k[i], __ddiv_rn(static_cast<double>(i + 1), dm)));
+    part[t] = mn;
+    __syncthreads();
+    for (int off = 1; off < 256; off <<= 1) {  // inclusive suffix minimum
+        const double v = t + off < 256 ? part[t + off] : __longlong_as_double(0x7FF0000000000000ll);
+        __syncthreads();
+        part[t] = fmin(part[t], v);
+        __syncthreads();
+    }
+    double run = t + 1 < 256 ? part[t + 1] : __longlong_as_double(0x7FF0000000000000ll);
+    for (int64_t i = e - 1; i >= b; --i) {
+        run = fmin(run, __ddiv_rn(k[i], __ddiv_rn(static_cast<double>(i + 1), dm)));
+        o[ix[i]] = has_nan ? qnan() : fmin(run, 1.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- Jaccard
+// bits[k][w]: bit b of word w = member[(32 w + b) * m + cols[k]] != 0
+__global__ void k_pack_columns(const uint8_t* __restrict__ member, int64_t n, int64_t m,
+                               const int32_t* __restrict__ cols, int64_t ncols, int64_t words,
+                               uint32_t* __restrict__ bits) {
+    const int64_t k = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int64_t w = blockIdx.y;
+    if (k >= ncols) return;
+    const int64_t c = cols[k];
+    uint32_t v = 0;
+    const int64_t t0 = w * 32;
+#pragma unroll 8
+    for (int b = 0; b < 32; ++b) {
+        const int64_t t = t0 + b;
+        if (t < n && member[t * m + c]) v |= 1u << b;
+    }
+    bits[k * words + w] = v;
+}
+
+// One warp per pair (i < j): scipy's boolean Jaccard, d = |a xor b| / |a or b| (0 when both are empty), written at
+// the pair's position in pdist's condensed order.
+__global__ void __launch_bounds__(256) k_jaccard(const uint32_t* __restrict__ bits, int64_t ncols, int64_t words,
+                                                 double* __restrict__ out) {
+    const int64_t i = blockIdx.x;
+    const int64_t j = static_cast<int64_t>(blockIdx.y) * 8 + (threadIdx.x >> 5);
+    if (j <= i || j >= ncols) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* a = bits + i * words;
+    const uint32_t* b = bits + j * words;
+    unsigned int nx = 0, no = 0;
+    for (int64_t w = lane; w < words; w += 32) {
+        const uint32_t x = a[w], y = b[w];
+        nx += __popc(x ^ y);
+        no += __popc(x | y);
+    }
+    for (int o = 16; o; o >>= 1) {
+        nx += __shfl_xor_sync(0xffffffffu, nx, o);
+        no += __shfl_xor_sync(0xffffffffu, no, o);
+    }
+    if (lane == 0) {
+        const int64_t at = i * ncols - i * (i + 1) / 2 + (j - i - 1);
+        out[at] = no ? __ddiv_rn(static_cast<double>(nx), static_cast<double>(no)) : 0.0;
+    }
+}
+
+// ================================================================================================ host side
+namespace {
+
+// Benjamini-Hochberg over the rows of p [rows][m], in place; scratch is sized by the caller for rows * m cells
+struct BhScratch {
+    DevBuf<double> keys;
+    DevBuf<int32_t> idx_in, idx_out;
+    DevBuf<int64_t> offsets;
+    DevBuf<char> temp;
+};
+
+void bh_rows(sb_ctx* ctx, BhScratch& s, double* p, int64_t rows, int64_t m) {
+    const int64_t cells = rows * m;
+    SB_CHECK(cells < (1ll << 31), "internal error: FDR chunk too large");
+    cudaStream_t st = ctx->stream;
+    s.keys.reserve(cells);
+    s.idx_in.reserve(cells);
+    s.idx_out.reserve(cells);
+    s.offsets.reserve(rows + 1);
+    k_bh_prepare<<<static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(cells, 256), ctx->num_sms * 8)), 256, 0, st>>>(
+        rows, m, s.idx_in.p, s.offsets.p);
+    SB_LAUNCH_CHECK(ctx);
+    size_t temp_bytes = 0;
+    SB_CUDA(cub::DeviceSegmentedSort::SortPairs(nullptr, temp_bytes, p, s.keys.p, s.idx_in.p, s.idx_out.p,
+                                                static_cast<int>(cells), static_cast<int>(rows), s.offsets.p,
+                                                s.offsets.p + 1, st));
+    s.temp.reserve(std::max<size_t>(temp_bytes, 1));
+    SB_CUDA(cub::DeviceSegmentedSort::SortPairs(s.temp.p, temp_bytes, p, s.keys.p, s.idx_in.p, s.idx_out.p,
+                                                static_cast<int>(cells), static_cast<int>(rows), s.offsets.p,
+                                                s.offsets.p + 1, st));
+    ctx->launches += 3;  // the segmented sort's partition + large/small segment kernels
+    k_bh_rows<<<static_cast<unsigned>(rows), 256, 0, st>>>(s.keys.p, s.idx_out.p, m, p);
+    SB_LAUNCH_CHECK(ctx);
+}
+
+int64_t chunk_rows(int64_t n, int64_t m) { return std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / m)); }
+
+dim3 tail_grid(int64_t rows, int64_t m) {
+    return dim3(static_cast<unsigned>(sb_ceil_div(m, 256)), static_cast<unsigned>(sb_ceil_div(rows, kTailRows)));
+}
+
+void colcnt_out(sb_ctx* ctx, const int32_t* colcnt, int64_t m, double* num_enriched_host) {
+    if (!num_enriched_host) return;
+    DevBuf<double> f;
+    f.reserve(m);
+    k_colcnt_to_f64<<<static_cast<unsigned>(sb_ceil_div(m, 256)), 256, 0, ctx->stream>>>(colcnt, m, f.p);
+    SB_LAUNCH_CHECK(ctx);
+    SB_CUDA(cudaMemcpyAsync(num_enriched_host, f.p, m * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ streaming null
+int sb_enrich_null_begin(sb_enrich* e, int score_type, int engine) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_null_begin: NULL handle");
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
+             engine);
+    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
+             "the tensor-core engine implements neighborhood_score_type 'sum' only");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    e->null_cnt.reserve(2 * cells);
+    SB_CUDA(cudaMemsetAsync(e->null_cnt.p, 0, 2 * cells * sizeof(uint32_t), ctx->stream));
+    e->null_score = score_type;
+    e->null_engine = engine;
+    e->null_perms = 0;
+    for (int i = 0; i < 7; ++i) e->null_stats[i] = 0;
+    SB_API_END
+}
+
+int sb_enrich_null_add(sb_enrich* e, const int32_t* perm_rows_host, int64_t num_perm) {
+    SB_API_BEGIN
+    SB_CHECK(e && perm_rows_host, "sb_enrich_null_add: NULL argument");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_add: call sb_enrich_null_begin first");
+    SB_CHECK(num_perm >= 0, "sb_enrich_null_add: num_perm < 0");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    const int64_t piece = std::max<int64_t>(1, (256ll << 20) / e->n);  // <= 1 GiB of indices on the device at a time
+    for (int64_t p0 = 0; p0 < num_perm; p0 += piece) {
+        const int64_t np = std::min(piece, num_perm - p0);
+        e->null_perm.reserve(static_cast<size_t>(np) * e->n);
+        SB_CUDA(cudaMemcpyAsync(e->null_perm.p, perm_rows_host + p0 * e->n, static_cast<size_t>(np) * e->n * sizeof(int32_t),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        int rc = sb_enrich_perm_counts_dev(e, e->null_score, e->null_engine, e->null_perm.p, np, e->null_cnt.p,
+                                           e->null_cnt.p + cells);
+        if (rc) fail("%s", sb_last_error());
+        SB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next piece
+        for (int i = 0; i < 7; ++i) {
+            if (i == 2 || i == 3 || i == 4)
+                e->null_stats[i] = e->stats[i];
+            else
+                e->null_stats[i] += e->stats[i];
+        }
+        e->null_perms += np;
+    }
+    for (int i = 0; i < 7; ++i) e->stats[i] = e->null_stats[i];
+    SB_API_END
+}
+
+int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_neg_host, uint32_t* counts_pos_host) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_null_counts: NULL handle");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_counts: no null has been started on this plan");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    if (num_perm_out) *num_perm_out = e->null_perms;
+    if (counts_neg_host) copy_out(ctx, counts_neg_host, e->null_cnt.p, cells * sizeof(uint32_t));
+    if (counts_pos_host) copy_out(ctx, counts_pos_host, e->null_cnt.p + cells, cells * sizeof(uint32_t));
+    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    SB_API_END
+}
+
+int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, const double* nes_of_count_host,
+                            int64_t table_len, int multiple_testing, double zero_pvalue_floor, int attribute_sign,
+                            double nes_threshold, double* ns_host, double* pvalues_neg_host, double* pvalues_pos_host,
+                            double* nes_host, double* nes_binary_host, double* num_enriched_host) {
+    SB_API_BEGIN
+    SB_CHECK(e && pvalue_of_count_host && nes_of_count_host, "sb_enrich_null_finalize: NULL argument");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_finalize: no null has been started on this plan");
+    SB_CHECK(table_len > e->null_perms && table_len < (1ll << 31),
+             "sb_enrich_null_finalize: tables hold %lld entries but %lld permutations were counted (need P + 1)",
+             (long long)table_len, (long long)e->null_perms);
+    SB_CHECK(attribute_sign >= 0 && attribute_sign <= 2, "sb_enrich_null_finalize: attribute_sign must be 0, 1 or 2");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    PhaseTrace tr(ctx, "null.finalize");
+    const int64_t n = e->n, m = e->m;
+    const size_t cells = static_cast<size_t>(n) * m;
+    const double* ns = enrich_observed(e, e->null_score);
+    DevBuf<double> ptab, nestab, pn, pp, nes, nb;
+    DevBuf<int32_t> colcnt;
+    ptab.reserve(table_len);
+    nestab.reserve(table_len);
+    SB_CUDA(cudaMemcpyAsync(ptab.p, pvalue_of_count_host, table_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(nestab.p, nes_of_count_host, table_len * sizeof(double), cudaMemcpyHostToDevice, st));
+    colcnt.reserve(m);
+    SB_CUDA(cudaMemsetAsync(colcnt.p, 0, m * sizeof(int32_t), st));
+    const int64_t rows_per = chunk_rows(n, m);
+    pn.reserve(rows_per * m);
+    pp.reserve(rows_per * m);
+    nes.reserve(rows_per * m);
+    nb.reserve(rows_per * m);
+    BhScratch bh;
+    // with FDR the first pass must not count enriched neighborhoods: give it a scratch counter
+    DevBuf<int32_t> colcnt_scratch;
+    if (multiple_testing) colcnt_scratch.reserve(m);
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t rows = std::min(rows_per, n - r0);
+        const size_t at = static_cast<size_t>(r0) * m, len = static_cast<size_t>(rows) * m;
+        k_null_tail<true><<<tail_grid(rows, m), 256, 0, st>>>(
+            e->null_cnt.p + at, e->null_cnt.p + cells + at, ns + at, ptab.p, nestab.p, static_cast<uint32_t>(table_len),
+            zero_pvalue_floor, attribute_sign, nes_threshold, rows, m, pn.p, pp.p, nes.p, nb.p,
+            multiple_testing ? colcnt_scratch.p : colcnt.p);
+        SB_LAUNCH_CHECK(ctx);
+        if (multiple_testing) {
+            bh_rows(ctx, bh, pn.p, rows, m);
+            bh_rows(ctx, bh, pp.p, rows, m);
+            k_null_tail<false><<<tail_grid(rows, m), 256, 0, st>>>(nullptr, nullptr, nullptr, nullptr, nullptr, 0,
+                                                                    zero_pvalue_floor, attribute_sign, nes_threshold,
+                                                                    rows, m, pn.p, pp.p, nes.p, nb.p, colcnt.p);
+            SB_LAUNCH_CHECK(ctx);
+        }
+        if (ns_host) copy_out(ctx, ns_host + at, ns + at, len * sizeof(double));
+        if (pvalues_neg_host) copy_out(ctx, pvalues_neg_host + at, pn.p, len * sizeof(double));
+        if (pvalues_pos_host) copy_out(ctx, pvalues_pos_host + at, pp.p, len * sizeof(double));
+        if (nes_host) copy_out(ctx, nes_host + at, nes.p, len * sizeof(double));
+        if (nes_binary_host) copy_out(ctx, nes_binary_host + at, nb.p, len * sizeof(double));
+    }
+    colcnt_out(ctx, colcnt.p, m, num_enriched_host);
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ hypergeometric
+int sb_enrich_hypergeom_finalize(sb_enrich* e, int multiple_testing, double nes_threshold, double* pvalues_host,
+                                 double* nes_host, double* nes_binary_host, double* num_enriched_host) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_hypergeom_finalize: NULL handle");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    const int64_t n = e->n, m = e->m;
+    const size_t cells = static_cast<size_t>(n) * m;
+    DevBuf<double> pv, nes, nb;
+    DevBuf<int32_t> colcnt;
+    pv.reserve(cells);
+    nes.reserve(cells);
+    colcnt.reserve(m);
+    SB_CUDA(cudaMemsetAsync(colcnt.p, 0, m * sizeof(int32_t), st));
+    int rc = sb_enrich_hypergeom_dev(e, pv.p, nes.p);
+    if (rc) fail("%s", sb_last_error());
+    PhaseTrace tr(ctx, "hypergeom.finalize");
+    const int64_t rows_per = chunk_rows(n, m);
+    nb.reserve(rows_per * m);
+    BhScratch bh;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t rows = std::min(rows_per, n - r0);
+        const size_t at = static_cast<size_t>(r0) * m, len = static_cast<size_t>(rows) * m;
+        if (multiple_testing) {
+            bh_rows(ctx, bh, pv.p + at, rows, m);
+            k_binarize<true><<<tail_grid(rows, m), 256, 0, st>>>(pv.p + at, nes.p + at, nes_threshold, rows, m, nb.p,
+                                                                  colcnt.p);
+        } else {
+            k_binarize<false><<<tail_grid(rows, m), 256, 0, st>>>(pv.p + at, nes.p + at, nes_threshold, rows, m, nb.p,
+                                                                   colcnt.p);
+        }
+        SB_LAUNCH_CHECK(ctx);
+        if (pvalues_host) copy_out(ctx, pvalues_host + at, pv.p + at, len * sizeof(double));
+        if (nes_host) copy_out(ctx, nes_host + at, nes.p + at, len * sizeof(double));
+        if (nes_binary_host) copy_out(ctx, nes_binary_host + at, nb.p, len * sizeof(double));
+    }
+    colcnt_out(ctx, colcnt.p, m, num_enriched_host);
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ stand-alone rows
+int sb_fdr_rows(sb_ctx* ctx, int64_t n, int64_t m, const double* pvalues_host, double* adjusted_host) {
+    SB_API_BEGIN
+    SB_CHECK(ctx && pvalues_host && adjusted_host, "sb_fdr_rows: NULL argument");
+    SB_CHECK(n > 0 && m > 0 && m < (1ll << 31), "sb_fdr_rows: bad shape %lld x %lld", (long long)n, (long long)m);
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    const int64_t rows_per = chunk_rows(n, m);
+    DevBuf<double> p;
+    p.reserve(rows_per * m);
+    BhScratch bh;
+    for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+        const int64_t rows = std::min(rows_per, n - r0);
+        const size_t at = static_cast<size_t>(r0) * m, len = static_cast<size_t>(rows) * m;
+        SB_CUDA(cudaMemcpyAsync(p.p, pvalues_host + at, len * sizeof(double), cudaMemcpyHostToDevice, st));
+        bh_rows(ctx, bh, p.p, rows, m);
+        copy_out(ctx, adjusted_host + at, p.p, len * sizeof(double));
+    }
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}
+
+int sb_attr_jaccard(sb_ctx* ctx, int64_t n, const uint8_t* member_host, int64_t m, const int32_t* cols_host,
+                    int64_t n_cols, double* condensed_out_host) {
+    SB_API_BEGIN
+    SB_CHECK(ctx && member_host && cols_host, "sb_attr_jaccard: NULL argument");
+    SB_CHECK(n > 0 && m > 0 && n_cols >= 0 && n_cols < (1ll << 31), "sb_attr_jaccard: bad shape");
+    for (int64_t k = 0; k < n_cols; ++k)
+        SB_CHECK(cols_host[k] >= 0 && cols_host[k] < m, "sb_attr_jaccard: column %d out of range", cols_host[k]);
+    if (n_cols < 2) return 0;
+    SB_CHECK(condensed_out_host, "sb_attr_jaccard: NULL output");
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    const int64_t words = sb_ceil_div(n, 32);
+    SB_CHECK(words <= 65535, "sb_attr_jaccard: n=%lld too large", (long long)n);
+    const int64_t pairs = n_cols * (n_cols - 1) / 2;
+    DevBuf<uint8_t> member;
+    DevBuf<int32_t> cols;
+    DevBuf<uint32_t> bits;
+    DevBuf<double> out;
+    member.reserve(static_cast<size_t>(n) * m);
+    cols.reserve(n_cols);
+    bits.reserve(static_cast<size_t>(n_cols) * words);
+    out.reserve(pairs);
+    SB_CUDA(cudaMemcpyAsync(member.p, member_host, static_cast<size_t>(n) * m, cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(cols.p, cols_host, n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    k_pack_columns<<<dim3(static_cast<unsigned>(sb_ceil_div(n_cols, 128)), static_cast<unsigned>(words)), 128, 0, st>>>(
+        member.p, n, m, cols.p, n_cols, words, bits.p);
+    SB_LAUNCH_CHECK(ctx);
+    const int64_t jgroups = sb_ceil_div(n_cols, 8);
+    SB_CHECK(jgroups <= 65535, "sb_attr_jaccard: %lld attributes are too many for one launch", (long long)n_cols);
+    k_jaccard<<<dim3(static_cast<unsigned>(n_cols), static_cast<unsigned>(jgroups)), 256, 0, st>>>(bits.p, n_cols, words,
+                                                                                                  out.p);
+    SB_LAUNCH_CHECK(ctx);
+    copy_out(ctx, condensed_out_host, out.p, pairs * sizeof(double));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}
+
+}  // extern "C"

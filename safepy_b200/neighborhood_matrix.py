@@ -18,10 +18,20 @@ class PackedNeighborhoods:
     dtype = np.dtype(np.int64)  # what the reference's matrix reports
 
     def __init__(self, words, n, device=None):
-        self.words = np.ascontiguousarray(words, dtype=np.uint32).reshape(n, _lib.neigh_ld(n))
+        """`words` may be None when `device` holds the matrix: the host copy is then fetched on first use."""
+        if words is None and device is None:
+            raise ValueError("PackedNeighborhoods needs packed words or a device handle")
+        self._words = None if words is None else \
+            np.ascontiguousarray(words, dtype=np.uint32).reshape(n, _lib.neigh_ld(n))
         self.n = int(n)
         self._device = device  # _lib.Neighborhoods or None
         self.node_order = None  # optional locality hint for the enrichment plan (see ordering.py)
+
+    @property
+    def words(self):
+        if self._words is None:
+            self._words = self._device.packed()
+        return self._words
 
     # -- ndarray-like surface
     @property
@@ -32,8 +42,9 @@ class PackedNeighborhoods:
         return self.n
 
     def row_sums(self):
-        bits = np.unpackbits(self.words.view(np.uint8), axis=1)
-        return bits.sum(axis=1, dtype=np.int64)
+        if self._device is not None and self._device.h is not None:
+            return self._device.rowsums()
+        return np.bitwise_count(self.words).sum(axis=1, dtype=np.int64)
 
     def sum(self, axis=None, **kwargs):
         rs = self.row_sums()
@@ -81,7 +92,7 @@ class PackedNeighborhoods:
         return {"words": self.words, "n": self.n, "node_order": self.node_order}
 
     def __setstate__(self, state):
-        self.words = state["words"]
+        self._words = state["words"]
         self.n = state["n"]
         self.node_order = state.get("node_order")
         self._device = None

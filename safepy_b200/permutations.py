@@ -31,6 +31,57 @@ def make_perm_rows(node2attribute, num_permutations, random_seed, out=None):
     return rows
 
 
+def iter_perm_rows(node2attribute, num_permutations, random_seed, piece=128, depth=4):
+    """The same stream as make_perm_rows, produced `piece` permutations at a time by a background thread, so that
+    the GPU counts piece k (the C call releases the GIL) while the host replays the RNG for piece k + 1.
+    Yields int32 [<= piece, n] arrays that together equal make_perm_rows(...)."""
+    import queue
+    import threading
+
+    n = node2attribute.shape[0]
+    indx_vals = rows_with_data(node2attribute)
+    out = queue.Queue(maxsize=depth)
+    stop = threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                out.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def produce():
+        try:
+            np.random.seed(random_seed)
+            cur = np.arange(n, dtype=np.int32)
+            for p0 in range(0, num_permutations, piece):
+                rows = np.empty((min(piece, num_permutations - p0), n), dtype=np.int32)
+                for k in range(rows.shape[0]):
+                    cur[indx_vals] = cur[np.random.permutation(indx_vals)]
+                    rows[k] = cur
+                if not put(rows):
+                    return
+            put(None)
+        except BaseException as exc:  # noqa: BLE001  (handed to the consumer)
+            put(exc)
+
+    worker = threading.Thread(target=produce, name="safe-b200-perm-replay", daemon=True)
+    worker.start()
+    try:
+        while True:
+            item = out.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+    finally:
+        stop.set()
+        worker.join()
+
+
 def shard_bounds(num_permutations, world_size, rank):
     """Contiguous permutation range [lo, hi) owned by `rank` (the last ranks get the short shards)."""
     per = -(-num_permutations // world_size)

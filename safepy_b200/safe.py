@@ -13,13 +13,14 @@ below, which takes graphs / arrays / DataFrames directly.
 There is no CPU fallback: the methods raise `SafeB200Error` when the CUDA library or a B200 is missing.
 """
 import logging
+import time
 
 import numpy as np
 
 from . import _lib
 from .neighborhood_matrix import PackedNeighborhoods, as_packed
 from .ordering import kd_order
-from .permutations import make_perm_rows
+from .permutations import iter_perm_rows
 
 DEFAULTS = {
     # safepy/safe_default.ini:1-24 and safepy/safe.py:57-107
@@ -99,6 +100,7 @@ class SafeB200Mixin:
     """The four hot-path methods; the host class supplies graph / node2attribute / attributes / settings."""
 
     device = -1
+    _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
     # ---------------------------------------------------------------------------------- stage 1
     def define_neighborhoods(self, **kwargs):
@@ -127,7 +129,7 @@ class SafeB200Mixin:
             # safe.py:417 stores the dict-of-dicts of distances; nothing in safepy reads it
             self.node_distances = None
 
-        packed = PackedNeighborhoods(dev.packed(), n, device=dev)
+        packed = PackedNeighborhoods(None, n, device=dev)    # host copy of the words is fetched on first use
         # locality hint for stage 2 (nodes sorted spatially); results do not depend on it
         packed.node_order = kd_order(x, y)
         num_neighbors = packed.row_sums()
@@ -152,21 +154,33 @@ class SafeB200Mixin:
             logging.info("Setting all null attribute values to 0. Using the network as background for enrichment.")
             self.node2attribute[np.isnan(self.node2attribute)] = 0
 
-        nan_mask = np.isnan(self.node2attribute)
-        if np.any(np.sum(nan_mask, axis=0) / self.node2attribute.shape[0] > 0.5):
+        b = self.node2attribute
+        nan_mask = np.isnan(b)
+        if np.any(np.sum(nan_mask, axis=0) / b.shape[0] > 0.5):
             logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored for "
                             "calculating enrichment.\n'Consider setting sf.background = ''network''.'")
-        num_other_values = np.sum(~nan_mask & ~np.isin(self.node2attribute, [0, 1]))
+        binary = False
+        if self.enrichment_type == "auto":
+            # safe.py:458: no value other than 0, 1 and NaN (NaN != 0 and NaN != 1 hold, hence the mask)
+            binary = np.count_nonzero((b != 0) & (b != 1) & ~nan_mask) == 0
+        del nan_mask
 
-        if self.enrichment_type == "hypergeometric" or (self.enrichment_type == "auto" and num_other_values == 0):
+        self._tail = None
+        if self.enrichment_type == "hypergeometric" or binary:
             self.compute_pvalues_by_hypergeom(**kwargs)
         else:
             self.compute_pvalues_by_randomization(**kwargs)
 
-        idx = ~np.isnan(self.nes)
-        self.nes_binary = np.zeros(self.nes.shape)
-        self.nes_binary[idx] = np.abs(self.nes[idx]) > -np.log10(self.enrichment_threshold)
-        self.attributes["num_neighborhoods_enriched"] = np.sum(self.nes_binary, axis=0)
+        if self._tail is not None:
+            # nes_binary and the per-attribute sums came out of the same kernel pass as the NES (safe.py:466-472)
+            self.nes_binary, enriched = self._tail
+            self._tail = None
+        else:
+            idx = ~np.isnan(self.nes)
+            self.nes_binary = np.zeros(self.nes.shape)
+            self.nes_binary[idx] = np.abs(self.nes[idx]) > -np.log10(self.enrichment_threshold)
+            enriched = np.sum(self.nes_binary, axis=0)
+        self.attributes["num_neighborhoods_enriched"] = enriched
 
     def _enrichment_plan(self):
         ctx = get_context(self.device)
@@ -197,37 +211,31 @@ class SafeB200Mixin:
             per = int(np.ceil(self.num_permutations / num_processes))
             self.num_permutations = per * num_processes
 
+        # The host replays the reference's RNG stream piece by piece (background thread) while the device counts
+        # the previous piece; counts -> p-values -> (FDR) -> NES -> nes_binary happen on the device in one tail
+        # pass (safe.py:526-554, 466-472), so the count arrays never visit the host.
+        t0 = time.perf_counter()
         plan = self._enrichment_plan()
         try:
-            self.ns = plan.score(self.neighborhood_score_type)
-            rows = make_perm_rows(self.node2attribute, self.num_permutations, self.random_seed)
-            cneg, cpos = plan.perm_counts(rows, self.neighborhood_score_type, getattr(self, "engine", "auto"))
+            t1 = time.perf_counter()
+            plan.null_begin(self.neighborhood_score_type, getattr(self, "engine", "auto"))
+            for rows in iter_perm_rows(self.node2attribute, self.num_permutations, self.random_seed):
+                plan.null_add(rows)
+            t2 = time.perf_counter()
+            if self.multiple_testing:
+                logging.info("Running FDR-adjustment of p-values...")
+            out = plan.null_finalize(self.num_permutations, self.attribute_sign, self.enrichment_threshold,
+                                     self.multiple_testing)
             self.last_enrichment_stats = plan.stats()
         finally:
             plan.close()
-
-        counts_neg = cneg.astype(np.float64)
-        counts_pos = cpos.astype(np.float64)
-        idx = np.isnan(self.ns)                                              # safe.py:528-530
-        counts_neg[idx] = np.nan
-        counts_pos[idx] = np.nan
-        self.pvalues_neg = counts_neg / self.num_permutations
-        self.pvalues_pos = counts_pos / self.num_permutations
-
-        if self.multiple_testing:
-            logging.info("Running FDR-adjustment of p-values...")
-            self.pvalues_neg = _fdr_rows(self.pvalues_neg)
-            self.pvalues_pos = _fdr_rows(self.pvalues_pos)
-
-        floor = 1 / self.num_permutations                                    # safe.py:546-547
-        nes_pos = -np.log10(np.where(self.pvalues_pos == 0, floor, self.pvalues_pos))
-        nes_neg = -np.log10(np.where(self.pvalues_neg == 0, floor, self.pvalues_neg))
-        if self.attribute_sign == "highest":
-            self.nes = nes_pos
-        elif self.attribute_sign == "lowest":
-            self.nes = nes_neg
-        elif self.attribute_sign == "both":
-            self.nes = nes_pos - nes_neg
+        # host wall clock of the three phases (upload + CSR view, streamed null, fused tail + result copies)
+        self.last_enrichment_seconds = {"plan": t1 - t0, "null": t2 - t1, "tail": time.perf_counter() - t2}
+        self.ns = out["ns"]
+        self.pvalues_neg = out["pvalues_neg"]
+        self.pvalues_pos = out["pvalues_pos"]
+        self.nes = out["nes"]
+        self._tail = (out["nes_binary"], out["num_neighborhoods_enriched"])
 
     def compute_pvalues_by_hypergeom(self, **kwargs):
         if kwargs:
@@ -240,19 +248,16 @@ class SafeB200Mixin:
         self.validate_config()
         if self.verbose:
             logging.info("Using the hypergeometric test to calculate enrichment...")
+        if self.multiple_testing and self.verbose:
+            logging.info("Running FDR-adjustment of p-values...")
         plan = self._enrichment_plan()
         try:
-            self.pvalues_pos, nes = plan.hypergeom(want_pvalues=True, want_nes=not self.multiple_testing)
+            out = plan.hypergeom_finalize(self.enrichment_threshold, self.multiple_testing)
         finally:
             plan.close()
-        if self.multiple_testing:
-            if self.verbose:
-                logging.info("Running FDR-adjustment of p-values...")
-            self.pvalues_pos = _fdr_rows(self.pvalues_pos)
-            with np.errstate(divide="ignore"):
-                nes = -np.log10(self.pvalues_pos)
-        self.nes = nes
-
+        self.pvalues_pos = out["pvalues_pos"]
+        self.nes = out["nes"]
+        self._tail = (out["nes_binary"], out["num_neighborhoods_enriched"])
 
     # ---------------------------------------------------------------------------------- next call of the workflow
     def define_top_attributes(self, **kwargs):
@@ -293,18 +298,51 @@ class SafeB200Mixin:
             logging.info("Number of top attributes: %d" % np.sum(self.attributes["top"]))
 
 
-def _fdr_rows(pvalues):
-    """Benjamini-Hochberg adjustment of every row across attributes (what safe.py:536-542 / 599-605 obtain from
-    statsmodels.stats.multitest.fdrcorrection(method='indep')[1] per row)."""
-    p = np.asarray(pvalues, dtype=np.float64)
-    m = p.shape[1]
-    order = np.argsort(p, axis=1)
-    ranked = np.take_along_axis(p, order, axis=1) * (m / np.arange(1, m + 1))[None, :]
-    ranked = np.minimum.accumulate(ranked[:, ::-1], axis=1)[:, ::-1]
-    ranked = np.minimum(ranked, 1.0)
-    out = np.empty_like(p)
-    np.put_along_axis(out, order, ranked, axis=1)
-    return out
+    def define_domains(self, **kwargs):
+        """safe.py:661-716.  The pairwise Jaccard distances between the nes_binary columns of the top attributes
+        (the metric evaluation inside the reference's linkage(m, 'average', metric='jaccard')) are computed on the
+        GPU from bit-packed columns; the O(k^2) average-linkage clustering of the k top attributes itself is SciPy's,
+        as upstream.  Any other attribute_distance_metric goes to SciPy unchanged."""
+        import pandas as pd
+        from scipy.cluster.hierarchy import fcluster, linkage
+        if "attribute_distance_threshold" in kwargs:
+            self.attribute_distance_threshold = kwargs["attribute_distance_threshold"]
+        self.validate_config()
+
+        top = self.attributes["top"].values.astype(bool)
+        if self.attribute_distance_metric == "jaccard":
+            cols = np.flatnonzero(top)
+            if len(cols) < 2:   # what scipy's linkage raises for a single observation
+                raise ValueError("The number of observations cannot be determined on an empty distance matrix.")
+            dist = _lib.jaccard(get_context(self.device), self.nes_binary, cols)
+            Z = linkage(dist, method="average")
+        else:
+            Z = linkage(self.nes_binary[:, top].T, method="average", metric=self.attribute_distance_metric)
+        max_d = np.max(Z[:, 2] * self.attribute_distance_threshold)
+        domains = fcluster(Z, max_d, criterion="distance")
+
+        self.attributes["domain"] = 0
+        self.attributes.loc[self.attributes["top"], "domain"] = domains
+
+        # node2nes_binary.groupby(level='domain', axis=1).sum() / node2nes.groupby(...).max(), safe.py:680-701
+        domain = self.attributes["domain"].values
+        ids = np.unique(domain)
+        counts = np.stack([self.nes_binary[:, domain == d].sum(axis=1) for d in ids], axis=1)
+        maxnes = np.stack([self.nes[:, domain == d].max(axis=1) for d in ids], axis=1)
+        self.node2domain = pd.DataFrame(counts, columns=pd.Index(ids, name="domain"))
+        real = ids >= 1
+        t_max = counts[:, real].max(axis=1)
+        t_idxmax = ids[real][np.argmax(counts[:, real], axis=1)]
+        t_idxmax[t_max == 0] = 0
+        self.node2domain["primary_domain"] = t_idxmax
+        col_of = {d: k for k, d in enumerate(ids)}
+        self.node2domain["primary_nes"] = [maxnes[i, col_of[d]] for i, d in enumerate(t_idxmax)]
+
+        if self.verbose:
+            num_domains = len(np.unique(domains))
+            per_domain = self.attributes.loc[self.attributes["domain"] > 0].groupby("domain")["id"].count()
+            logging.info("Number of domains: %d (containing %d-%d attributes)"
+                         % (num_domains, per_domain.min(), per_domain.max()))
 
 
 class SAFE(SafeB200Mixin):

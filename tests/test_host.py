@@ -10,8 +10,8 @@ from conftest import net_from_golden
 from safepy_b200 import SAFE, PackedNeighborhoods, synthetic as syn
 from safepy_b200._lib import pack_dense, unpack_packed
 from safepy_b200.neighborhood_matrix import as_packed
-from safepy_b200.permutations import make_perm_rows, shard_bounds
-from safepy_b200.safe import _fdr_rows, graph_csr
+from safepy_b200.permutations import iter_perm_rows, make_perm_rows, shard_bounds
+from safepy_b200.safe import graph_csr
 
 
 def test_defaults_match_reference_ini():
@@ -106,18 +106,27 @@ def test_graph_csr_follows_networkx_weight_rule(stage1_small):
     assert np.array_equal(ipo, ip) and np.array_equal(ixo, ix) and np.array_equal(wo, w)
 
 
-def test_fdr_rows_is_benjamini_hochberg():
-    rng = np.random.default_rng(3)
-    p = rng.uniform(size=(7, 40))
-    adj = _fdr_rows(p)
-    for r in range(p.shape[0]):
-        order = np.argsort(p[r])
-        expect = np.empty(40)
-        run = 1.0
-        for rank in range(40, 0, -1):
-            run = min(run, p[r][order[rank - 1]] * 40 / rank)
-            expect[order[rank - 1]] = run
-        assert np.allclose(adj[r], expect, rtol=0, atol=1e-15)
+def test_streamed_perm_rows_equal_the_one_shot_replay():
+    rng = np.random.default_rng(5)
+    attrs = rng.standard_normal((57, 3)).astype(np.float32)
+    attrs[rng.random(57) < 0.2] = np.nan
+    full = make_perm_rows(attrs, 23, 11)
+    state_after = np.random.get_state()[1].copy()
+    pieces = list(iter_perm_rows(attrs, 23, 11, piece=5, depth=2))
+    assert [p.shape[0] for p in pieces] == [5, 5, 5, 5, 3]
+    assert np.array_equal(np.concatenate(pieces), full)
+    assert np.array_equal(np.random.get_state()[1], state_after)      # the global stream ends where upstream's does
+    # abandoning the iterator must not leave the producer thread blocked
+    it = iter_perm_rows(attrs, 1000, 11, piece=2, depth=1)
+    next(it)
+    it.close()
+
+
+def test_packed_row_sums_on_the_host(stage1_small):
+    g = stage1_small
+    n = g["x"].shape[0]
+    pk = PackedNeighborhoods(g["nb_layout"], n)
+    assert np.array_equal(pk.row_sums(), unpack_packed(g["nb_layout"], n).sum(axis=1))
 
 
 def test_loaders_accept_arrays_and_frames(stage1_small):

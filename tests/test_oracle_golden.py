@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import safe_oracle as orc
-from conftest import net_from_golden
+from conftest import load_golden, net_from_golden
 from safepy_b200 import synthetic as syn
 from safepy_b200._lib import pack_dense, unpack_packed
 
@@ -105,3 +105,52 @@ def test_pack_roundtrip():
         w = pack_dense(d)
         assert w.shape[1] % 4 == 0
         assert np.array_equal(unpack_packed(w, n), d)
+
+
+@pytest.mark.parametrize("kind", ["normal32", "binary", "single"])
+def test_randomization_tail_matches_reference(stage2_small, kind):
+    """safe.py:528-554 + 466-472 restated (oracle.randomization_tail) against the reference's recorded outputs."""
+    g = stage2_small
+    pn, pp, nes, nb, enriched = orc.randomization_tail(
+        g["ns_%s_sum" % kind], g["cneg_%s_sum" % kind], g["cpos_%s_sum" % kind], int(g["num_permutations"]), "both",
+        False, 0.05)
+    assert np.array_equal(pn, g["rand_pneg_" + kind], equal_nan=True)
+    assert np.array_equal(pp, g["rand_ppos_" + kind], equal_nan=True)
+    assert np.array_equal(nes, g["rand_nes_" + kind], equal_nan=True)
+    assert np.array_equal(nb, g["rand_nesbin_" + kind])
+    assert np.array_equal(enriched, g["rand_enriched_" + kind])
+
+
+def test_fdr_restatement_is_benjamini_hochberg():
+    """statsmodels is not installed here (parity unpinned, see oracle.fdrcorrection): check the restatement against
+    the textbook definition, adj_(k) = min_{k' >= k} p_(k') * m / k', its tie and NaN behaviour."""
+    rng = np.random.default_rng(3)
+    p = rng.uniform(size=(7, 40))
+    p[1, 5:9] = p[1, 4]                                  # ties
+    adj = orc.fdr_rows(p)
+    for r in range(p.shape[0]):
+        order = np.argsort(p[r], kind="stable")
+        expect = np.empty(40)
+        run = 1.0
+        for rank in range(40, 0, -1):
+            run = min(run, p[r][order[rank - 1]] * 40 / rank)
+            expect[order[rank - 1]] = run
+        assert np.allclose(adj[r], expect, rtol=0, atol=1e-15)
+    assert np.all(adj >= p - 1e-18) and np.all(adj <= 1)
+    assert len(set(adj[1, 4:9])) == 1
+    q = p.copy()
+    q[3, 7] = np.nan
+    adj2 = orc.fdr_rows(q)
+    assert np.isnan(adj2[3]).all() and np.array_equal(np.delete(adj2, 3, 0), np.delete(adj, 3, 0))
+
+
+def test_domains_oracle_matches_reference():
+    g = load_golden("domains_small.npz")
+    top = g["top"]
+    assert np.array_equal(orc.jaccard_condensed(g["nes_binary"], np.flatnonzero(top)), g["jaccard"])
+    domain, ids, counts, primary, primary_nes = orc.define_domains(g["nes"], g["nes_binary"], top,
+                                                                   float(g["threshold"]))
+    assert np.array_equal(domain, g["domain"]) and np.array_equal(ids, g["domain_ids"])
+    assert np.array_equal(counts, g["node2domain"])
+    assert np.array_equal(primary, g["primary_domain"])
+    assert np.array_equal(primary_nes, g["primary_nes"])

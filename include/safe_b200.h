@@ -70,7 +70,8 @@ int sb_ctx_release_memory(sb_ctx* ctx);
 int64_t sb_ctx_launch_count(sb_ctx* ctx);
 /* Device-time accounting: with profiling on, launches are bracketed by CUDA events on the context's stream.
  * sb_ctx_kernel_ms synchronizes, returns the summed milliseconds and the number of brackets of one kernel class
- * (0 score GEMM, 1 operand gather, 2 fp64 fix-up, 3 SSSP, 4 euclid, 5 hypergeom, 6 fp64 scores, 7 operand prep)
+ * (0 score GEMM, 1 operand gather, 2 fp64 fix-up, 3 SSSP, 4 euclid, 5 hypergeom, 6 fp64 scores, 7 operand prep,
+ * 8 p-value/NES tail, 9 row-wise FDR, 10 Jaccard)
  * and clears that class. */
 int sb_ctx_profile(sb_ctx* ctx, int enable);
 int sb_ctx_kernel_ms(sb_ctx* ctx, int kernel_class, double* ms_out, int64_t* count_out);
@@ -151,6 +152,10 @@ int sb_enrich_stats(sb_enrich* e, int64_t* out7_host);
  * Either output may be NULL. */
 int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host);
 int sb_enrich_hypergeom_dev(sb_enrich* e, double* pvalues_dev, double* nes_dev);
+
+/* What SAFE.compute_pvalues inspects before choosing a test (safe.py:453-458): the number of NaNs in every attribute
+ * column ([m]) and the number of values that are neither 0, 1 nor NaN (0 => 'auto' picks the hypergeometric test). */
+int sb_enrich_attr_summary(sb_enrich* e, int64_t* nan_per_column_host, int64_t* other_values_out);
 
 /* ------------------------------------------------------------------ stage 2: streaming null + fused tail
  * Same arithmetic as sb_enrich_perm_counts, but the two count arrays stay on the device between calls: the caller feeds

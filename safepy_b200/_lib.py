@@ -17,7 +17,8 @@ SB_F32, SB_F64 = 0, 1
 SCORE_TYPES = {"sum": 0, "z-score": 1}
 ENGINES = {"auto": 0, "simt": 1, "tc": 2}
 ATTRIBUTE_SIGNS = {"highest": 0, "lowest": 1, "both": 2}
-KERNEL_CLASSES = {"gemm": 0, "gather": 1, "fixup": 2, "sssp": 3, "euclid": 4, "hypergeom": 5, "score": 6, "prep": 7}
+KERNEL_CLASSES = {"gemm": 0, "gather": 1, "fixup": 2, "sssp": 3, "euclid": 4, "hypergeom": 5, "score": 6, "prep": 7,
+                  "tail": 8, "fdr": 9, "jaccard": 10}
 
 _vp = C.c_void_p
 _i64 = C.c_int64
@@ -60,6 +61,7 @@ SIGNATURES = {
     "sb_enrich_stats": (C.c_int, [_vp, _vp]),
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
+    "sb_enrich_attr_summary": (C.c_int, [_vp, _vp, C.POINTER(_i64)]),
     "sb_enrich_null_begin": (C.c_int, [_vp, C.c_int, C.c_int]),
     "sb_enrich_null_add": (C.c_int, [_vp, _vp, _i64]),
     "sb_enrich_null_counts": (C.c_int, [_vp, C.POINTER(_i64), _vp, _vp]),
@@ -342,6 +344,13 @@ class Enrichment:
         _check(self.lib, self.lib.sb_enrich_perm_counts_dev(self.h, SCORE_TYPES[score_type], ENGINES[engine],
                                                             _vp(int(perm_dev)), int(num_perm), _vp(int(cneg_dev)),
                                                             _vp(int(cpos_dev))))
+
+    def attr_summary(self):
+        """(NaNs per attribute column, number of values that are neither 0, 1 nor NaN) -- safe.py:453-458."""
+        nans = np.empty(self.m, dtype=np.int64)
+        other = _i64()
+        _check(self.lib, self.lib.sb_enrich_attr_summary(self.h, _ptr(nans), C.byref(other)))
+        return nans, other.value
 
     # -- streaming null: counts stay on the device until null_finalize / null_counts
     def null_begin(self, score_type="sum", engine="auto"):

@@ -88,7 +88,7 @@ struct DevBuf {
 
 // kernel classes whose device time can be accumulated with CUDA events (sb_ctx_profile / sb_ctx_kernel_ms)
 enum { SB_K_GEMM = 0, SB_K_GATHER = 1, SB_K_FIXUP = 2, SB_K_SSSP = 3, SB_K_EUCLID = 4, SB_K_HYPERGEOM = 5,
-       SB_K_SCORE = 6, SB_K_PREP = 7, SB_K_CLASSES = 8 };
+       SB_K_SCORE = 6, SB_K_PREP = 7, SB_K_TAIL = 8, SB_K_FDR = 9, SB_K_JACCARD = 10, SB_K_CLASSES = 11 };
 
 struct sb_ctx {
     int device = 0;

@@ -207,6 +207,29 @@ __global__ void __launch_bounds__(256) k_binarize(const double* __restrict__ p, 
     if (enriched) atomicAdd(&colcnt[j], enriched);
 }
 
+// compute_pvalues' look at the attribute matrix (safe.py:453-458): NaNs per column and the number of values that
+// are neither 0, 1 nor NaN.  Same column-strip layout as the tail kernels.
+template <class T>
+__global__ void __launch_bounds__(256) k_attr_summary(const T* __restrict__ b, int64_t n, int64_t m,
+                                                      unsigned long long* __restrict__ nan_per_col,
+                                                      unsigned long long* __restrict__ other) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * 256 + threadIdx.x;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 64;
+    const int64_t r1 = min(n, r0 + 64);
+    unsigned int nans = 0, oth = 0;
+    if (j < m) {
+        for (int64_t r = r0; r < r1; ++r) {
+            const T v = b[r * m + j];
+            const bool is_nan = v != v;
+            nans += is_nan;
+            oth += !is_nan && v != T(0) && v != T(1);
+        }
+        if (nans) atomicAdd(&nan_per_col[j], static_cast<unsigned long long>(nans));
+    }
+    oth = __reduce_add_sync(0xffffffffu, oth);
+    if ((threadIdx.x & 31) == 0 && oth) atomicAdd(other, static_cast<unsigned long long>(oth));
+}
+
 __global__ void k_colcnt_to_f64(const int32_t* __restrict__ c, int64_t m, double* __restrict__ out) {
     const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j < m) out[j] = static_cast<double>(c[j]);
@@ -220,10 +243,10 @@ __global__ void k_bh_prepare(int64_t rows, int64_t m, int32_t* __restrict__ idx,
     for (; i < cells; i += step) idx[i] = static_cast<int32_t>(i % m);
 }
 
-// One CTA per row.  keys = the row's p-values ascending, idx = their columns.  statsmodels' fdrcorrection:
+// One CTA per row.  keys = the row's p-values ascending, idx = their columns, out = the row itself (overwritten).  statsmodels' fdrcorrection:
 //   ecdf[k] = (k + 1) / m;  raw[k] = p_sorted[k] / ecdf[k];  adj = reverse running minimum of raw, capped at 1,
 // scattered back to the original columns.  A NaN anywhere in the row propagates through np.minimum.accumulate from
-// the end (NaNs sort last), so the whole row becomes NaN.  Tied p-values all receive the value of the last of them
+// the end (argsort puts NaNs last), so the whole row becomes NaN.  Tied p-values all receive the value of the last of them
 // (the quotient is monotone in k), so the order a sort leaves ties in does not matter.
 __global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys, const int32_t* __restrict__ idx,
                                                  int64_t m, double* __restrict__ out) {
@@ -232,15 +255,18 @@ __global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys
     const int32_t* ix = idx + row * m;
     double* o = out + row * m;
     const int t = threadIdx.x;
-    const bool has_nan = isnan(k[m - 1]) || isnan(k[0]);
     const double dm = static_cast<double>(m);
     const int64_t seg = (m + 255) / 256;
     const int64_t b = min(m, t * seg), e = min(m, b + seg);
     __shared__ double part[256];
     double mn = __longlong_as_double(0x7FF0000000000000ll);  // +inf
+    // NaNs are looked for in the unsorted row (`out` still holds it: the adjustment is in place): the segmented
+    // sort's comparison path for short rows can push a NaN behind its padding keys and lose it
+    int nan_here = 0;
+    for (int64_t i = t; i < m; i += 256) nan_here |= isnan(o[i]);
     for (int64_t i = b; i < e; ++i) mn = fmin(mn, __ddiv_rn(k[i], __ddiv_rn(static_cast<double>(i + 1), dm)));
     part[t] = mn;
-    __syncthreads();
+    const bool has_nan = __syncthreads_or(nan_here);
     for (int off = 1; off < 256; off <<= 1) {  // inclusive suffix minimum
         const double v = t + off < 256 ? part[t + off] : __longlong_as_double(0x7FF0000000000000ll);
         __syncthreads();
@@ -314,6 +340,7 @@ void bh_rows(sb_ctx* ctx, BhScratch& s, double* p, int64_t rows, int64_t m) {
     const int64_t cells = rows * m;
     SB_CHECK(cells < (1ll << 31), "internal error: FDR chunk too large");
     cudaStream_t st = ctx->stream;
+    KernelTimer kt(ctx, SB_K_FDR);
     s.keys.reserve(cells);
     s.idx_in.reserve(cells);
     s.idx_out.reserve(cells);
@@ -334,7 +361,10 @@ void bh_rows(sb_ctx* ctx, BhScratch& s, double* p, int64_t rows, int64_t m) {
     SB_LAUNCH_CHECK(ctx);
 }
 
-int64_t chunk_rows(int64_t n, int64_t m) { return std::max<int64_t>(1, std::min<int64_t>(n, (32ll << 20) / m)); }
+// rows per pass: <= 32 Mi cells of staging per output array, and a grid.y the launch accepts
+int64_t chunk_rows(int64_t n, int64_t m) {
+    return std::max<int64_t>(1, std::min<int64_t>({n, (32ll << 20) / m, 65535ll * kTailRows}));
+}
 
 dim3 tail_grid(int64_t rows, int64_t m) {
     return dim3(static_cast<unsigned>(sb_ceil_div(m, 256)), static_cast<unsigned>(sb_ceil_div(rows, kTailRows)));
@@ -461,11 +491,14 @@ int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, co
     for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
         const int64_t rows = std::min(rows_per, n - r0);
         const size_t at = static_cast<size_t>(r0) * m, len = static_cast<size_t>(rows) * m;
-        k_null_tail<true><<<tail_grid(rows, m), 256, 0, st>>>(
-            e->null_cnt.p + at, e->null_cnt.p + cells + at, ns + at, ptab.p, nestab.p, static_cast<uint32_t>(table_len),
-            zero_pvalue_floor, attribute_sign, nes_threshold, rows, m, pn.p, pp.p, nes.p, nb.p,
-            multiple_testing ? colcnt_scratch.p : colcnt.p);
-        SB_LAUNCH_CHECK(ctx);
+        {
+            KernelTimer kt(ctx, SB_K_TAIL);
+            k_null_tail<true><<<tail_grid(rows, m), 256, 0, st>>>(
+                e->null_cnt.p + at, e->null_cnt.p + cells + at, ns + at, ptab.p, nestab.p,
+                static_cast<uint32_t>(table_len), zero_pvalue_floor, attribute_sign, nes_threshold, rows, m, pn.p, pp.p,
+                nes.p, nb.p, multiple_testing ? colcnt_scratch.p : colcnt.p);
+            SB_LAUNCH_CHECK(ctx);
+        }
         if (multiple_testing) {
             bh_rows(ctx, bh, pn.p, rows, m);
             bh_rows(ctx, bh, pp.p, rows, m);
@@ -482,6 +515,31 @@ int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, co
     }
     colcnt_out(ctx, colcnt.p, m, num_enriched_host);
     SB_CUDA(cudaStreamSynchronize(st));
+    SB_API_END
+}
+
+int sb_enrich_attr_summary(sb_enrich* e, int64_t* nan_per_column_host, int64_t* other_values_out) {
+    SB_API_BEGIN
+    SB_CHECK(e && nan_per_column_host && other_values_out, "sb_enrich_attr_summary: NULL argument");
+    sb_ctx* ctx = e->ctx;
+    ctx->bind();
+    cudaStream_t st = ctx->stream;
+    const int64_t n = e->n, m = e->m;
+    DevBuf<unsigned long long> acc;
+    acc.reserve(m + 1);
+    SB_CUDA(cudaMemsetAsync(acc.p, 0, (m + 1) * sizeof(unsigned long long), st));
+    const dim3 grid(static_cast<unsigned>(sb_ceil_div(m, 256)), static_cast<unsigned>(sb_ceil_div(n, 64)));
+    SB_CHECK(grid.y <= 65535, "sb_enrich_attr_summary: n=%lld too large for one launch", (long long)n);
+    if (e->dtype == SB_F32)
+        k_attr_summary<float><<<grid, 256, 0, st>>>(static_cast<const float*>(e->b), n, m, acc.p, acc.p + m);
+    else
+        k_attr_summary<double><<<grid, 256, 0, st>>>(static_cast<const double*>(e->b), n, m, acc.p, acc.p + m);
+    SB_LAUNCH_CHECK(ctx);
+    std::vector<unsigned long long> h(m + 1);
+    SB_CUDA(cudaMemcpyAsync(h.data(), acc.p, (m + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    for (int64_t j = 0; j < m; ++j) nan_per_column_host[j] = static_cast<int64_t>(h[j]);
+    *other_values_out = static_cast<int64_t>(h[m]);
     SB_API_END
 }
 
@@ -579,9 +637,12 @@ int sb_attr_jaccard(sb_ctx* ctx, int64_t n, const uint8_t* member_host, int64_t 
     SB_LAUNCH_CHECK(ctx);
     const int64_t jgroups = sb_ceil_div(n_cols, 8);
     SB_CHECK(jgroups <= 65535, "sb_attr_jaccard: %lld attributes are too many for one launch", (long long)n_cols);
-    k_jaccard<<<dim3(static_cast<unsigned>(n_cols), static_cast<unsigned>(jgroups)), 256, 0, st>>>(bits.p, n_cols, words,
-                                                                                                  out.p);
-    SB_LAUNCH_CHECK(ctx);
+    {
+        KernelTimer kt(ctx, SB_K_JACCARD);
+        k_jaccard<<<dim3(static_cast<unsigned>(n_cols), static_cast<unsigned>(jgroups)), 256, 0, st>>>(bits.p, n_cols,
+                                                                                                      words, out.p);
+        SB_LAUNCH_CHECK(ctx);
+    }
     copy_out(ctx, condensed_out_host, out.p, pairs * sizeof(double));
     SB_CUDA(cudaStreamSynchronize(st));
     SB_API_END

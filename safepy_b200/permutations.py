@@ -31,55 +31,70 @@ def make_perm_rows(node2attribute, num_permutations, random_seed, out=None):
     return rows
 
 
-def iter_perm_rows(node2attribute, num_permutations, random_seed, piece=128, depth=4):
-    """The same stream as make_perm_rows, produced `piece` permutations at a time by a background thread, so that
-    the GPU counts piece k (the C call releases the GIL) while the host replays the RNG for piece k + 1.
-    Yields int32 [<= piece, n] arrays that together equal make_perm_rows(...)."""
-    import queue
-    import threading
+class iter_perm_rows:
+    """The same stream as make_perm_rows, produced piece by piece by a background thread that starts at once, so that
+    the GPU counts piece k (the C call releases the GIL) while the host replays the RNG for piece k + 1.  Pieces
+    start small (the device gets work after a few permutations) and double up to `piece`.  Iterating yields int32
+    [<= piece, n] arrays that together equal make_perm_rows(...); close() (or exhausting it) stops the thread."""
 
-    n = node2attribute.shape[0]
-    indx_vals = rows_with_data(node2attribute)
-    out = queue.Queue(maxsize=depth)
-    stop = threading.Event()
+    def __init__(self, node2attribute, num_permutations, random_seed, piece=128, depth=4, first=16):
+        import queue
+        import threading
+        self._queue = queue.Queue(maxsize=depth)
+        self._stop = threading.Event()
+        self._done = False
+        n = node2attribute.shape[0]
+        indx_vals = rows_with_data(node2attribute)
+        piece = max(1, int(piece))
 
-    def put(item):
-        while not stop.is_set():
+        def put(item):
+            while not self._stop.is_set():
+                try:
+                    self._queue.put(item, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
+        def produce():
             try:
-                out.put(item, timeout=0.1)
-                return True
-            except queue.Full:
-                continue
-        return False
+                np.random.seed(random_seed)
+                cur = np.arange(n, dtype=np.int32)
+                p0, size = 0, max(1, min(int(first), piece))
+                while p0 < num_permutations:
+                    rows = np.empty((min(size, num_permutations - p0), n), dtype=np.int32)
+                    for k in range(rows.shape[0]):
+                        cur[indx_vals] = cur[np.random.permutation(indx_vals)]
+                        rows[k] = cur
+                    if not put(rows):
+                        return
+                    p0 += rows.shape[0]
+                    size = min(piece, size * 2)
+                put(None)
+            except BaseException as exc:  # noqa: BLE001  (handed to the consumer)
+                put(exc)
 
-    def produce():
-        try:
-            np.random.seed(random_seed)
-            cur = np.arange(n, dtype=np.int32)
-            for p0 in range(0, num_permutations, piece):
-                rows = np.empty((min(piece, num_permutations - p0), n), dtype=np.int32)
-                for k in range(rows.shape[0]):
-                    cur[indx_vals] = cur[np.random.permutation(indx_vals)]
-                    rows[k] = cur
-                if not put(rows):
-                    return
-            put(None)
-        except BaseException as exc:  # noqa: BLE001  (handed to the consumer)
-            put(exc)
+        self._worker = threading.Thread(target=produce, name="safe-b200-perm-replay", daemon=True)
+        self._worker.start()
 
-    worker = threading.Thread(target=produce, name="safe-b200-perm-replay", daemon=True)
-    worker.start()
-    try:
-        while True:
-            item = out.get()
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._done:
+            raise StopIteration
+        item = self._queue.get()
+        if item is None or isinstance(item, BaseException):
+            self.close()
             if item is None:
-                break
-            if isinstance(item, BaseException):
-                raise item
-            yield item
-    finally:
-        stop.set()
-        worker.join()
+                raise StopIteration
+            raise item
+        return item
+
+    def close(self):
+        self._done = True
+        self._stop.set()
+        self._worker.join()
 
 
 def shard_bounds(num_permutations, world_size, rank):

@@ -12,6 +12,7 @@ below, which takes graphs / arrays / DataFrames directly.
 
 There is no CPU fallback: the methods raise `SafeB200Error` when the CUDA library or a B200 is missing.
 """
+import contextlib
 import logging
 import time
 
@@ -100,6 +101,7 @@ class SafeB200Mixin:
     """The four hot-path methods; the host class supplies graph / node2attribute / attributes / settings."""
 
     device = -1
+    _plan = None  # enrichment plan of the compute_pvalues call in progress
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
     # ---------------------------------------------------------------------------------- stage 1
@@ -154,22 +156,18 @@ class SafeB200Mixin:
             logging.info("Setting all null attribute values to 0. Using the network as background for enrichment.")
             self.node2attribute[np.isnan(self.node2attribute)] = 0
 
-        b = self.node2attribute
-        nan_mask = np.isnan(b)
-        if np.any(np.sum(nan_mask, axis=0) / b.shape[0] > 0.5):
-            logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored for "
-                            "calculating enrichment.\n'Consider setting sf.background = ''network''.'")
-        binary = False
-        if self.enrichment_type == "auto":
-            # safe.py:458: no value other than 0, 1 and NaN (NaN != 0 and NaN != 1 hold, hence the mask)
-            binary = np.count_nonzero((b != 0) & (b != 1) & ~nan_mask) == 0
-        del nan_mask
-
+        # The attribute matrix goes to the device once; the look at its values (NaN share per attribute, anything
+        # other than 0 / 1 / NaN -- safe.py:453-458) happens there, and the same plan serves the chosen test.
         self._tail = None
-        if self.enrichment_type == "hypergeometric" or binary:
-            self.compute_pvalues_by_hypergeom(**kwargs)
-        else:
-            self.compute_pvalues_by_randomization(**kwargs)
+        with self._plan_scope() as plan:
+            nans, num_other_values = plan.attr_summary()
+            if np.any(nans / plan.n > 0.5):
+                logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored "
+                                "for calculating enrichment.\n'Consider setting sf.background = ''network''.'")
+            if self.enrichment_type == "hypergeometric" or (self.enrichment_type == "auto" and num_other_values == 0):
+                self.compute_pvalues_by_hypergeom(**kwargs)
+            else:
+                self.compute_pvalues_by_randomization(**kwargs)
 
         if self._tail is not None:
             # nes_binary and the per-attribute sums came out of the same kernel pass as the NES (safe.py:466-472)
@@ -181,6 +179,21 @@ class SafeB200Mixin:
             self.nes_binary[idx] = np.abs(self.nes[idx]) > -np.log10(self.enrichment_threshold)
             enriched = np.sum(self.nes_binary, axis=0)
         self.attributes["num_neighborhoods_enriched"] = enriched
+
+    @contextlib.contextmanager
+    def _plan_scope(self):
+        """The enrichment plan of the enclosing compute_pvalues call, or a fresh one when a branch method is called
+        on its own (both are public upstream)."""
+        if self._plan is not None:
+            yield self._plan
+            return
+        plan = self._enrichment_plan()
+        self._plan = plan
+        try:
+            yield plan
+        finally:
+            self._plan = None
+            plan.close()
 
     def _enrichment_plan(self):
         ctx = get_context(self.device)
@@ -215,11 +228,11 @@ class SafeB200Mixin:
         # the previous piece; counts -> p-values -> (FDR) -> NES -> nes_binary happen on the device in one tail
         # pass (safe.py:526-554, 466-472), so the count arrays never visit the host.
         t0 = time.perf_counter()
-        plan = self._enrichment_plan()
-        try:
+        perm_rows = iter_perm_rows(self.node2attribute, self.num_permutations, self.random_seed)  # replay starts now
+        with contextlib.closing(perm_rows), self._plan_scope() as plan:
             t1 = time.perf_counter()
             plan.null_begin(self.neighborhood_score_type, getattr(self, "engine", "auto"))
-            for rows in iter_perm_rows(self.node2attribute, self.num_permutations, self.random_seed):
+            for rows in perm_rows:
                 plan.null_add(rows)
             t2 = time.perf_counter()
             if self.multiple_testing:
@@ -227,8 +240,6 @@ class SafeB200Mixin:
             out = plan.null_finalize(self.num_permutations, self.attribute_sign, self.enrichment_threshold,
                                      self.multiple_testing)
             self.last_enrichment_stats = plan.stats()
-        finally:
-            plan.close()
         # host wall clock of the three phases (upload + CSR view, streamed null, fused tail + result copies)
         self.last_enrichment_seconds = {"plan": t1 - t0, "null": t2 - t1, "tail": time.perf_counter() - t2}
         self.ns = out["ns"]
@@ -250,11 +261,8 @@ class SafeB200Mixin:
             logging.info("Using the hypergeometric test to calculate enrichment...")
         if self.multiple_testing and self.verbose:
             logging.info("Running FDR-adjustment of p-values...")
-        plan = self._enrichment_plan()
-        try:
+        with self._plan_scope() as plan:
             out = plan.hypergeom_finalize(self.enrichment_threshold, self.multiple_testing)
-        finally:
-            plan.close()
         self.pvalues_pos = out["pvalues_pos"]
         self.nes = out["nes"]
         self._tail = (out["nes_binary"], out["num_neighborhoods_enriched"])

@@ -217,3 +217,14 @@ def test_safe_api_with_multiple_testing(stage2_small):
     sf.compute_pvalues(how="hypergeometric", multiple_testing=True, verbose=False)
     assert np.array_equal(sf.pvalues_pos, orc.fdr_rows(g["hyper_p"]), equal_nan=True) or \
         np.allclose(sf.pvalues_pos, orc.fdr_rows(g["hyper_p"]), rtol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("kind", ["normal32", "binary", "normal64"])
+def test_attr_summary(small, kind):
+    """safe.py:453-458 on the device: NaNs per column, values other than 0 / 1 / NaN."""
+    g, n, nb = small
+    attrs = g["attr_" + kind]
+    nans, other = _lib.Enrichment(nb, attrs).attr_summary()
+    mask = np.isnan(attrs)
+    assert np.array_equal(nans, mask.sum(axis=0))
+    assert other == np.sum(~mask & ~np.isin(attrs, [0, 1]))

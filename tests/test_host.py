@@ -112,14 +112,16 @@ def test_streamed_perm_rows_equal_the_one_shot_replay():
     attrs[rng.random(57) < 0.2] = np.nan
     full = make_perm_rows(attrs, 23, 11)
     state_after = np.random.get_state()[1].copy()
-    pieces = list(iter_perm_rows(attrs, 23, 11, piece=5, depth=2))
-    assert [p.shape[0] for p in pieces] == [5, 5, 5, 5, 3]
+    pieces = list(iter_perm_rows(attrs, 23, 11, piece=8, depth=2, first=2))
+    assert [p.shape[0] for p in pieces] == [2, 4, 8, 8, 1]
     assert np.array_equal(np.concatenate(pieces), full)
     assert np.array_equal(np.random.get_state()[1], state_after)      # the global stream ends where upstream's does
     # abandoning the iterator must not leave the producer thread blocked
     it = iter_perm_rows(attrs, 1000, 11, piece=2, depth=1)
     next(it)
     it.close()
+    assert not it._worker.is_alive()
+    iter_perm_rows(attrs, 1000, 11, piece=2, depth=1).close()        # never iterated
 
 
 def test_packed_row_sums_on_the_host(stage1_small):

@@ -1,6 +1,6 @@
 """Device time and roofline bookkeeping of the non-GEMM kernels at the BASELINE.json shapes.
 
-    python tools/kernel_bench.py [--only sssp|euclid|hypergeom] [--small]
+    python tools/kernel_bench.py [--only sssp|euclid|hypergeom|components|tail] [--small]
 
 Algorithmic bytes follow SURVEY.md section 8(d):
   k_sssp      sum over sources s and settled nodes t of (8 + deg(t) * 12) + N*N/8   (computed exactly from the result)
@@ -116,6 +116,66 @@ def main():
         out.append(dict(kernel="k_components", workload="C3 nodes x %d candidate attributes" % len(cand), n=n,
                         call_wall_s=wall, attributes_per_s=len(cand) / wall,
                         cpu_scipy_s_per_attribute=cpu, mean_components=float(ncc.mean())))
+    if only in (None, "tail"):
+        # what follows the counts inside compute_pvalues at C3 size (20k x 2000): fused tail, row-wise FDR, and the
+        # Jaccard distances define_domains needs between 1000 top attributes
+        from safepy_b200.permutations import make_perm_rows
+        cfg = syn.make_config("C3", 0.1 if small else 1.0, shuffle=True)
+        net, n, m = cfg["net"], cfg["n"], cfg["m"]
+        nr = cfg["radius"] * (net["x"].max() - net["x"].min())
+        nb = _lib.Neighborhoods(ctx, n).shortpath(net["indptr"], net["indices"], net["csr_length"], nr)
+        plan = _lib.Enrichment(nb, cfg["attributes"])
+        plan.null_begin("sum", "auto")
+        plan.null_add(make_perm_rows(cfg["attributes"], 16, 7))
+        for fdr in (False, True):
+            plan.null_finalize(16, multiple_testing=fdr)
+            ctx.profile(True)
+            ctx.kernel_ms("tail"), ctx.kernel_ms("fdr")
+            t0 = time.perf_counter()
+            plan.null_finalize(16, multiple_testing=fdr)
+            wall = time.perf_counter() - t0
+            ms_tail, _ = ctx.kernel_ms("tail")
+            ms_fdr, _ = ctx.kernel_ms("fdr")
+            ctx.profile(False)
+            cells = float(n) * m
+            # tail: 2 x 4 B counts + 8 B observed score in, 4 x 8 B out per cell
+            alg = 48.0 * cells
+            rec = dict(kernel="k_null_tail", workload="C3 finalize, multiple_testing=%s" % fdr, n=n, m=m, ms=ms_tail,
+                       algorithmic_bytes=alg, achieved_gbs=alg / (ms_tail * 1e-3) / 1e9, peak_gbs=PEAK,
+                       frac=alg / (ms_tail * 1e-3) / 1e9 / PEAK, call_wall_s=wall,
+                       d2h_bytes=40.0 * cells, d2h_gbs_incl_kernels=40.0 * cells / wall / 1e9)
+            if fdr:
+                # per matrix: sort (8 B key + 4 B index in and out) + adjustment pass (12 B in, 8 B out); two matrices
+                rec.update(fdr_ms=ms_fdr, fdr_algorithmic_bytes=2 * 44.0 * cells,
+                           fdr_gbs=2 * 44.0 * cells / (ms_fdr * 1e-3) / 1e9)
+            out.append(rec)
+        plan.close()
+        nb.close()
+        rng = np.random.default_rng(5)
+        nbin = np.zeros((n, m), dtype=np.uint8)
+        for j in range(m):
+            c = rng.integers(0, n)
+            d = np.hypot(net["x"] - net["x"][c], net["y"] - net["y"][c])
+            nbin[d < rng.uniform(0.03, 0.12), j] = 1
+        cols = np.arange(0, m, 2)
+        _lib.jaccard(ctx, nbin, cols[:4])
+        ctx.profile(True)
+        ctx.kernel_ms("jaccard")
+        t0 = time.perf_counter()
+        dist = _lib.jaccard(ctx, nbin, cols)
+        wall = time.perf_counter() - t0
+        ms, _ = ctx.kernel_ms("jaccard")
+        ctx.profile(False)
+        from scipy.spatial.distance import pdist
+        t0 = time.perf_counter()
+        k = min(len(cols), 200)
+        ref = pdist(nbin[:, cols[:k]].T.astype(np.float64), metric="jaccard")
+        cpu = time.perf_counter() - t0
+        assert np.array_equal(_lib.jaccard(ctx, nbin, cols[:k]), ref)
+        pairs = len(dist)
+        out.append(dict(kernel="k_jaccard", workload="C3 nodes, %d top attributes" % len(cols), n=n, pairs=pairs, ms=ms,
+                        pairs_per_s=pairs / (ms * 1e-3), l2_bytes=pairs * 2.0 * ((n + 31) // 32) * 4,
+                        call_wall_s=wall, cpu_scipy_pairs_per_s=k * (k - 1) / 2 / cpu))
     for o in out:
         print(json.dumps(o))
 

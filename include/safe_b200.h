@@ -52,6 +52,7 @@ extern "C" {
 typedef struct sb_ctx sb_ctx;       /* one device + stream + workspaces */
 typedef struct sb_neigh sb_neigh;   /* bit-packed N x N neighborhood matrix on the device */
 typedef struct sb_enrich sb_enrich; /* stage-2 plan: neighborhoods x attribute matrix, prepared operands */
+typedef struct sb_perm_stream sb_perm_stream; /* host replay of run_permutations' RNG stream (no device involved) */
 
 /* ------------------------------------------------------------------ library / context */
 int sb_abi_version(void);
@@ -60,6 +61,8 @@ const char* sb_last_error(void);
 /* device < 0: use the current CUDA device. Fails unless the device is compute capability 10.x. */
 int sb_ctx_create(int device, sb_ctx** out);
 int sb_ctx_destroy(sb_ctx* ctx);
+/* CUDA device ordinal of the context (-1 for a NULL handle) */
+int sb_ctx_device(sb_ctx* ctx);
 /* run all subsequent work of this context on an existing cudaStream_t (e.g. torch's current stream) */
 int sb_ctx_set_stream(sb_ctx* ctx, void* cuda_stream);
 int sb_ctx_synchronize(sb_ctx* ctx);
@@ -167,6 +170,30 @@ int sb_enrich_null_begin(sb_enrich* e, int score_type, int engine);
 int sb_enrich_null_add(sb_enrich* e, const int32_t* perm_rows_host, int64_t num_perm);
 /* permutations counted so far and (optionally) the raw counts; any pointer may be NULL */
 int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_neg_host, uint32_t* counts_pos_host);
+
+/* Permutation shards on several GPUs (one process per GPU): the device addresses of the two count arrays of the open
+ * null ([n x m] uint32 each, neg immediately followed by pos), so that the host program can sum them across ranks in
+ * place (one NCCL all-reduce over 2 * n * m words), and the number of permutations they hold afterwards.  The caller
+ * orders the streams: sb_ctx_synchronize before the collective, its own stream before the next library call. */
+int sb_enrich_null_counts_dev(sb_enrich* e, uint32_t** counts_neg_dev, uint32_t** counts_pos_dev);
+int sb_enrich_null_set_perms(sb_enrich* e, int64_t num_perm);
+
+/* run_permutations' index stream (safe_extras.py:46-58) replayed natively on the host: np.random.seed(seed) of
+ * NumPy's legacy MT19937 generator, then per permutation np.random.permutation(rows_with_data) applied in place to
+ * the already permuted matrix; what comes out are the composed gather rows sb_enrich_perm_counts takes.
+ * has_seed == 0 mirrors np.random.seed(None) (OS entropy).  A stream is pure host state. */
+int sb_perm_stream_create(int64_t n, const int64_t* rows_with_data_host, int64_t n_with_data, int has_seed,
+                          uint32_t seed, sb_perm_stream** out);
+int sb_perm_stream_destroy(sb_perm_stream* s);
+/* the next num_perm permutations as gather rows [num_perm][n]; rows_out_host == NULL skips them (a rank that owns a
+ * later shard still has to draw the earlier ones: the stream cannot jump) */
+int sb_perm_stream_next(sb_perm_stream* s, int64_t num_perm, int32_t* rows_out_host);
+/* generator state (624 key words + position, as np.random.get_state() reports it) and permutations drawn so far, so
+ * that the caller can leave NumPy's global generator where the reference would have left it */
+int sb_perm_stream_state(sb_perm_stream* s, uint32_t* key624_out, int32_t* pos_out, int64_t* drawn_out);
+/* sb_enrich_null_add for the next num_perm permutations of a stream, in one call: a producer thread replays piece
+ * k + 1 into pinned memory while the device counts piece k */
+int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm);
 
 /* Tail of SAFE.compute_pvalues_by_randomization (safe.py:526-554) and of SAFE.compute_pvalues (safe.py:466-472):
  *   p = counts / P (NaN where the observed score is NaN); optional Benjamini-Hochberg adjustment of every row across

@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_last_error": (C.c_char_p, []),
     "sb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "sb_ctx_destroy": (C.c_int, [_vp]),
+    "sb_ctx_device": (C.c_int, [_vp]),
     "sb_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "sb_ctx_synchronize": (C.c_int, [_vp]),
     "sb_ctx_release_memory": (C.c_int, [_vp]),
@@ -65,6 +66,13 @@ SIGNATURES = {
     "sb_enrich_null_begin": (C.c_int, [_vp, C.c_int, C.c_int]),
     "sb_enrich_null_add": (C.c_int, [_vp, _vp, _i64]),
     "sb_enrich_null_counts": (C.c_int, [_vp, C.POINTER(_i64), _vp, _vp]),
+    "sb_enrich_null_counts_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb_enrich_null_set_perms": (C.c_int, [_vp, _i64]),
+    "sb_perm_stream_create": (C.c_int, [_i64, _vp, _i64, C.c_int, C.c_uint32, C.POINTER(_vp)]),
+    "sb_perm_stream_destroy": (C.c_int, [_vp]),
+    "sb_perm_stream_next": (C.c_int, [_vp, _i64, _vp]),
+    "sb_perm_stream_state": (C.c_int, [_vp, _vp, C.POINTER(_i32), C.POINTER(_i64)]),
+    "sb_enrich_null_add_stream": (C.c_int, [_vp, _vp, _i64]),
     "sb_enrich_null_finalize": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_double, C.c_int, C.c_double,
                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_enrich_hypergeom_finalize": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
@@ -132,6 +140,11 @@ class Context:
         self.h = h
         if stream is not None:
             self.set_stream(stream)
+
+    @property
+    def device(self):
+        """CUDA device ordinal this context runs on."""
+        return int(self.lib.sb_ctx_device(self.h))
 
     def set_stream(self, stream):
         _check(self.lib, self.lib.sb_ctx_set_stream(self.h, _vp(int(stream))))
@@ -364,6 +377,11 @@ class Enrichment:
         _check(self.lib, self.lib.sb_enrich_null_add(self.h, _ptr(perm_rows), perm_rows.shape[0]))
         return self
 
+    def null_add_stream(self, stream, num_perm):
+        """Count the next `num_perm` permutations of a PermStream (replay and device work overlap inside the call)."""
+        _check(self.lib, self.lib.sb_enrich_null_add_stream(self.h, stream.h, int(num_perm)))
+        return self
+
     def null_counts(self, want_counts=True):
         """(permutations counted so far, counts_neg, counts_pos)"""
         num = _i64()
@@ -371,6 +389,15 @@ class Enrichment:
         cpos = np.empty((self.n, self.m), dtype=np.uint32) if want_counts else None
         _check(self.lib, self.lib.sb_enrich_null_counts(self.h, C.byref(num), _ptr(cneg), _ptr(cpos)))
         return num.value, cneg, cpos
+
+    def null_counts_dev(self):
+        """Device addresses (neg, pos) of the open null's count arrays; pos == neg + 4 * n * m."""
+        neg, pos = _vp(), _vp()
+        _check(self.lib, self.lib.sb_enrich_null_counts_dev(self.h, C.byref(neg), C.byref(pos)))
+        return int(neg.value), int(pos.value)
+
+    def null_set_perms(self, num_perm):
+        _check(self.lib, self.lib.sb_enrich_null_set_perms(self.h, int(num_perm)))
 
     def null_finalize(self, num_permutations, attribute_sign="both", enrichment_threshold=0.05,
                       multiple_testing=False, want=("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")):
@@ -419,6 +446,54 @@ class Enrichment:
     def close(self):
         if getattr(self, "h", None):
             self.lib.sb_enrich_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PermStream:
+    """run_permutations' RNG stream (np.random.seed + np.random.permutation per iteration, applied cumulatively)
+    replayed by the library on the host.  seed: int in [0, 2**32) or None (OS entropy, like np.random.seed(None))."""
+
+    def __init__(self, n, rows_with_data, seed):
+        self.lib = load_library()
+        self.n = int(n)
+        idx = _as(rows_with_data, np.int64)
+        if seed is not None and not (0 <= int(seed) < 2 ** 32):
+            raise ValueError("Seed must be between 0 and 2**32 - 1")     # numpy's message
+        h = _vp()
+        _check(self.lib, self.lib.sb_perm_stream_create(self.n, _ptr(idx), idx.shape[0], int(seed is not None),
+                                                        int(seed or 0), C.byref(h)))
+        self.h = h
+
+    def next(self, num_perm, out=None):
+        """Gather rows int32 [num_perm, n] of the next permutations."""
+        rows = out if out is not None else np.empty((int(num_perm), self.n), dtype=np.int32)
+        _check(self.lib, self.lib.sb_perm_stream_next(self.h, int(num_perm), _ptr(rows)))
+        return rows
+
+    def skip(self, num_perm):
+        _check(self.lib, self.lib.sb_perm_stream_next(self.h, int(num_perm), None))
+
+    def state(self):
+        """(key[624] uint32, pos, permutations drawn)"""
+        key = np.empty(624, dtype=np.uint32)
+        pos, drawn = _i32(), _i64()
+        _check(self.lib, self.lib.sb_perm_stream_state(self.h, _ptr(key), C.byref(pos), C.byref(drawn)))
+        return key, pos.value, drawn.value
+
+    def sync_numpy(self):
+        """Leave NumPy's legacy global generator where the reference's calls would have left it."""
+        key, pos, _ = self.state()
+        np.random.set_state(("MT19937", key, pos, 0, 0.0))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb_perm_stream_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsafe_b200.so")
 STAMP = os.path.join(HERE, ".libsafe_b200.stamp")
-SOURCES = ["neigh.cu", "enrich.cu", "gemm_tc.cu", "graph.cu", "finalize.cu"]
+SOURCES = ["neigh.cu", "enrich.cu", "gemm_tc.cu", "graph.cu", "finalize.cu", "permstream.cu"]
 HEADERS = ["common.cuh", "enrich.cuh", "sm100_ptx.cuh", os.path.join("..", "..", "include", "safe_b200.h")]
 
 NVCC_FLAGS = [

@@ -453,6 +453,23 @@ int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_
     SB_API_END
 }
 
+int sb_enrich_null_counts_dev(sb_enrich* e, uint32_t** counts_neg_dev, uint32_t** counts_pos_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e && counts_neg_dev && counts_pos_dev, "sb_enrich_null_counts_dev: NULL argument");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_counts_dev: no null has been started on this plan");
+    *counts_neg_dev = e->null_cnt.p;
+    *counts_pos_dev = e->null_cnt.p + static_cast<size_t>(e->n) * e->m;
+    SB_API_END
+}
+
+int sb_enrich_null_set_perms(sb_enrich* e, int64_t num_perm) {
+    SB_API_BEGIN
+    SB_CHECK(e && num_perm >= 0, "sb_enrich_null_set_perms: bad argument");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_set_perms: no null has been started on this plan");
+    e->null_perms = num_perm;
+    SB_API_END
+}
+
 int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, const double* nes_of_count_host,
                             int64_t table_len, int multiple_testing, double zero_pvalue_floor, int attribute_sign,
                             double nes_threshold, double* ns_host, double* pvalues_neg_host, double* pvalues_pos_host,

@@ -424,6 +424,8 @@ int sb_ctx_kernel_ms(sb_ctx* ctx, int kernel_class, double* ms_out, int64_t* cou
     SB_API_END
 }
 
+int sb_ctx_device(sb_ctx* ctx) { return ctx ? ctx->device : -1; }
+
 int sb_host_register(void* ptr, int64_t bytes) {
     SB_API_BEGIN
     SB_CUDA(cudaHostRegister(ptr, static_cast<size_t>(bytes), cudaHostRegisterDefault));

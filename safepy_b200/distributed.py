@@ -5,9 +5,50 @@ sequential) index stream: rank r scores permutations [lo, hi) against the full n
 add up (safepy/safe.py:518-519 does the same reduction with np.sum over its worker results).  This module holds the
 backend-independent part so that it can be exercised with gloo on CPU; bench.py uses it with NCCL on device buffers.
 """
+import sys
+
 import numpy as np
 
 from .permutations import make_perm_rows, shard_bounds
+
+
+def active_group(enabled=True):
+    """torch.distributed if the calling program runs one process per GPU -- it has imported torch itself, initialised
+    a process group and the world is larger than one -- else None.  (This package never imports torch on its own.)"""
+    td = sys.modules.get("torch.distributed")
+    if not enabled or td is None or not td.is_available() or not td.is_initialized() or td.get_world_size() < 2:
+        return None
+    return td
+
+
+class DeviceArray:
+    """Zero-copy view of library-owned device memory for torch.as_tensor (the CUDA array interface, version 2)."""
+
+    def __init__(self, ptr, count, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def shard_stream(stream, num_permutations, world_size, rank, add):
+    """Drive one rank's share of a permutation stream: permutations before the shard are drawn and dropped (the RNG
+    cannot jump), `add(stream, count)` consumes the shard, the rest is drawn so that every rank leaves the generator
+    where the reference would.  Returns (lo, hi)."""
+    lo, hi = shard_bounds(num_permutations, world_size, rank)
+    stream.skip(lo)
+    if hi > lo:
+        add(stream, hi - lo)
+    stream.skip(num_permutations - hi)
+    return lo, hi
+
+
+def broadcast_row_shards(dist, rows_tensor, n):
+    """All ranks end up with every rank's block of rows of `rows_tensor` ([n, ld], in place): one broadcast per shard
+    (shards are unequal when world does not divide n, which all_gather_into_tensor cannot express in place)."""
+    world = dist.get_world_size()
+    for src in range(world):
+        r0, r1 = row_shard(n, world, src)
+        if r1 > r0:
+            dist.broadcast(rows_tensor[r0:r1], src=src)
 
 
 def row_shard(n, world_size, rank):

@@ -14,15 +14,36 @@ def rows_with_data(node2attribute):
     return np.nonzero(np.sum(~np.isnan(node2attribute), axis=1))[0]
 
 
+def native_seed(random_seed):
+    """True when the library's native replay (sb_perm_stream_*) covers this seed: None or an int in [0, 2**32) --
+    what SAFE.random_seed holds (safe.py:102, 180-184).  Other seeds (arrays, ...) take NumPy's own seeding path."""
+    if random_seed is None:
+        return True
+    return isinstance(random_seed, (int, np.integer)) and not isinstance(random_seed, bool) \
+        and 0 <= int(random_seed) < 2 ** 32
+
+
+def perm_stream(node2attribute, random_seed):
+    """The library's host replay of the reference's RNG calls for this attribute matrix (see _lib.PermStream)."""
+    from . import _lib
+    return _lib.PermStream(node2attribute.shape[0], rows_with_data(node2attribute), random_seed)
+
+
 def make_perm_rows(node2attribute, num_permutations, random_seed, out=None):
     """Replay the reference's RNG calls and compose them. Returns int32 [num_permutations, n].
 
-    Consumes the global NumPy RNG exactly like the reference does, so interleaving with reference code keeps both
+    Leaves the global NumPy RNG exactly where the reference leaves it, so interleaving with reference code keeps both
     streams aligned.  random_seed=None seeds from OS entropy (np.random.seed(None)), as upstream."""
     n = node2attribute.shape[0]
+    rows = out if out is not None else np.empty((num_permutations, n), dtype=np.int32)
+    if native_seed(random_seed):
+        stream = perm_stream(node2attribute, random_seed)
+        stream.next(num_permutations, rows)
+        stream.sync_numpy()
+        stream.close()
+        return rows
     np.random.seed(random_seed)
     indx_vals = rows_with_data(node2attribute)
-    rows = out if out is not None else np.empty((num_permutations, n), dtype=np.int32)
     cur = np.arange(n, dtype=np.int32)
     for p in range(num_permutations):
         # n2a[indx_vals, :] = n2a[np.random.permutation(indx_vals), :]

@@ -21,7 +21,8 @@ import numpy as np
 from . import _lib
 from .neighborhood_matrix import PackedNeighborhoods, as_packed
 from .ordering import kd_order
-from .permutations import iter_perm_rows
+from .distributed import DeviceArray, active_group, broadcast_row_shards, row_shard, shard_stream
+from .permutations import iter_perm_rows, native_seed, perm_stream
 
 DEFAULTS = {
     # safepy/safe_default.ini:1-24 and safepy/safe.py:57-107
@@ -67,15 +68,22 @@ def _node_coordinates(graph):
     return x, y
 
 
-def graph_csr(graph, weight):
+def graph_csr(graph, weight, ctx=None):
     """Symmetric CSR of the graph with the cost rule of networkx's Dijkstra: data.get(weight, 1)
-    (what safe.py:406-410 hands to all_pairs_dijkstra_path_length).  Cached on the graph object."""
+    (what safe.py:406-410 hands to all_pairs_dijkstra_path_length).  Cached on the graph object.  With a device
+    context, a graph that SAFE.load_network built from edge arrays gets its CSR from sb_graph_csr."""
     key = (weight, graph.number_of_nodes(), graph.number_of_edges())
     cache = graph.graph.get("_safe_b200_csr")
     if cache is not None and cache[0] == key:
         return cache[1]
     n = graph.number_of_nodes()
     ne = graph.number_of_edges()
+    arrays = graph.graph.get("_safe_b200_edges")
+    if ctx is not None and weight == "length" and arrays is not None and arrays[0] == ne:
+        # the graph came from SAFE.load_network(edges=..., x=..., y=...): sort the edge arrays on the device
+        csr = _lib.build_csr(ctx, n, arrays[1][:, 0], arrays[1][:, 1], arrays[2])
+        graph.graph["_safe_b200_csr"] = (key, csr)
+        return csr
     eu = np.empty(ne, dtype=np.int64)
     ev = np.empty(ne, dtype=np.int64)
     w = np.empty(ne, dtype=np.float64)
@@ -101,6 +109,7 @@ class SafeB200Mixin:
     """The four hot-path methods; the host class supplies graph / node2attribute / attributes / settings."""
 
     device = -1
+    multi_gpu = True  # follow torch.distributed when the caller has initialised it (one process per GPU)
     _plan = None  # enrichment plan of the compute_pvalues call in progress
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
@@ -116,20 +125,30 @@ class SafeB200Mixin:
         x, y = _node_coordinates(self.graph)
         n = x.shape[0]
         dev = _lib.Neighborhoods(ctx, n)
+        # one process per GPU (torch.distributed initialised by the caller): every rank searches its block of
+        # sources and the packed rows are exchanged once
+        dist = active_group(self.multi_gpu)
+        r0, r1 = row_shard(n, dist.get_world_size(), dist.get_rank()) if dist else (0, n)
         metric = self.node_distance_metric
         if metric == "euclidean":
             nr = self.neighborhood_radius * (np.max(x) - np.min(x))          # safe.py:390-391 (x extent only)
-            dev.euclid(x, y, nr)
+            dev.euclid(x, y, nr, r0, r1)
         else:
             if metric == "shortpath_weighted_layout":
                 nr = self.neighborhood_radius * (np.max(x) - np.min(x))      # safe.py:404-405
-                indptr, indices, cost = graph_csr(self.graph, "length")
+                indptr, indices, cost = graph_csr(self.graph, "length", ctx)
             else:
                 nr = self.neighborhood_radius                                # safe.py:409
                 indptr, indices, cost = graph_csr(self.graph, "weight")
-            dev.shortpath(indptr, indices, cost, nr)
+            dev.shortpath(indptr, indices, cost, nr, r0, r1)
             # safe.py:417 stores the dict-of-dicts of distances; nothing in safepy reads it
             self.node_distances = None
+        if dist:
+            import torch
+            ctx.synchronize()
+            words = torch.as_tensor(DeviceArray(dev.words_dev, n * dev.ld), device=torch.device("cuda", ctx.device))
+            broadcast_row_shards(dist, words.view(n, dev.ld), n)
+            torch.cuda.synchronize(ctx.device)
 
         packed = PackedNeighborhoods(None, n, device=dev)    # host copy of the words is fetched on first use
         # locality hint for stage 2 (nodes sorted spatially); results do not depend on it
@@ -228,12 +247,44 @@ class SafeB200Mixin:
         # the previous piece; counts -> p-values -> (FDR) -> NES -> nes_binary happen on the device in one tail
         # pass (safe.py:526-554, 466-472), so the count arrays never visit the host.
         t0 = time.perf_counter()
-        perm_rows = iter_perm_rows(self.node2attribute, self.num_permutations, self.random_seed)  # replay starts now
-        with contextlib.closing(perm_rows), self._plan_scope() as plan:
+        with self._plan_scope() as plan:
             t1 = time.perf_counter()
             plan.null_begin(self.neighborhood_score_type, getattr(self, "engine", "auto"))
-            for rows in perm_rows:
-                plan.null_add(rows)
+            dist = active_group(self.multi_gpu)
+            if dist and not native_seed(self.random_seed):
+                raise ValueError("permutation shards over several GPUs need random_seed to be an int in [0, 2**32); "
+                                 "got %r" % (self.random_seed,))
+            if dist and self.random_seed is None:
+                raise ValueError("permutation shards over several GPUs need a random_seed: with None every rank "
+                                 "would draw its own stream")
+            if dist:
+                # permutations sharded over the ranks; ONE sum all-reduce of the device count arrays (safe.py:518-519
+                # sums its worker results the same way), then every rank runs the tail on the full counts
+                import torch
+                stream = perm_stream(self.node2attribute, self.random_seed)
+                shard_stream(stream, self.num_permutations, dist.get_world_size(), dist.get_rank(),
+                             plan.null_add_stream)
+                stream.sync_numpy()
+                stream.close()
+                plan.ctx.synchronize()
+                neg, _ = plan.null_counts_dev()
+                counts = torch.as_tensor(DeviceArray(neg, 2 * plan.n * plan.m),
+                                         device=torch.device("cuda", plan.ctx.device))
+                dist.all_reduce(counts)
+                torch.cuda.synchronize(plan.ctx.device)
+                plan.null_set_perms(self.num_permutations)
+            elif native_seed(self.random_seed):
+                # one C call: a producer thread replays the RNG stream piece by piece into pinned memory while the
+                # device counts the previous piece
+                stream = perm_stream(self.node2attribute, self.random_seed)
+                plan.null_add_stream(stream, self.num_permutations)
+                stream.sync_numpy()          # the global generator ends where upstream's would
+                stream.close()
+            else:
+                with contextlib.closing(iter_perm_rows(self.node2attribute, self.num_permutations,
+                                                       self.random_seed)) as perm_rows:
+                    for rows in perm_rows:
+                        plan.null_add(rows)
             t2 = time.perf_counter()
             if self.multiple_testing:
                 logging.info("Running FDR-adjustment of p-values...")
@@ -461,8 +512,16 @@ class SAFE(SafeB200Mixin):
             graph.add_nodes_from((i, {"key": i, "x": float(x[i]), "y": float(y[i]), "label": str(i),
                                       self.node_key_attribute: str(i)}) for i in range(x.shape[0]))
             if len(edges):
+                length = np.asarray(length, dtype=np.float64)
                 graph.add_edges_from((int(u), int(v), {} if w != w else {"length": float(w)})
                                      for (u, v), w in zip(edges, length))
+                lo, hi = np.minimum(edges[:, 0], edges[:, 1]), np.maximum(edges[:, 0], edges[:, 1])
+                if len(np.unique(lo * x.shape[0] + hi)) == len(edges):
+                    # no repeated edge (nx.Graph would keep only the last): define_neighborhoods can build its CSR
+                    # on the device from these arrays instead of walking the graph object edge by edge.
+                    # An edge without 'length' costs Dijkstra's default 1 (safe.py:406-407).
+                    graph.graph["_safe_b200_edges"] = (graph.number_of_edges(), edges.copy(),
+                                                       np.where(np.isnan(length), 1.0, length))
         self.graph = graph
 
     def load_attributes(self, attribute_file=None, **kwargs):

@@ -77,6 +77,26 @@ def test_tail_signs_and_nan_scores(small, sign, score_type):
     assert np.array_equal(out["num_neighborhoods_enriched"], enriched)
 
 
+@pytest.mark.parametrize("kind,perms", [("normal32", 60), ("single", 300), ("binary", 7)])
+def test_null_from_native_stream(small, kind, perms):
+    """sb_enrich_null_add_stream (RNG replay on a producer thread inside the C call) against the explicit rows."""
+    from safepy_b200.permutations import perm_stream
+    g, n, nb = small
+    attrs = g["attr_" + kind]
+    plan = _lib.Enrichment(nb, attrs)
+    cneg0, cpos0 = plan.perm_counts(make_perm_rows(attrs, perms, 3))
+    plan.null_begin("sum", "auto")
+    stream = perm_stream(attrs, 3)
+    plan.null_add_stream(stream, perms // 3)
+    plan.null_add_stream(stream, perms - perms // 3)          # a stream can be drained in several calls
+    num, cneg, cpos = plan.null_counts()
+    assert num == perms and stream.state()[2] == perms
+    assert np.array_equal(cneg, cneg0) and np.array_equal(cpos, cpos0)
+    other = _lib.PermStream(n + 1, np.arange(n + 1), 3)
+    with pytest.raises(_lib.SafeB200Error, match="the stream permutes"):
+        plan.null_add_stream(other, 1)
+
+
 def test_tail_needs_a_table_entry_per_count(small):
     g, n, nb = small
     attrs = g["attr_dyadic"]

@@ -170,3 +170,48 @@ def test_kd_order_and_relabelling():
     assert np.allclose(d, c1["net"]["length"])
     g = graph_order(c1["net"]["indptr"], c1["net"]["indices"], n)
     assert np.array_equal(np.sort(g), np.arange(n))
+
+
+@pytest.mark.parametrize("n,perms,seed", [(57, 23, 11), (1, 3, 0), (2, 5, 5), (5, 4, 2 ** 32 - 1), (300, 10, 7),
+                                          (5000, 6, 20240), (700, 9, None)])
+def test_native_perm_stream_replays_numpy(n, perms, seed):
+    """sb_perm_stream_* (MT19937 + legacy shuffle in C++) against the oracle's NumPy replay of safe_extras.py:46-58:
+    same gather rows, and the same generator state afterwards."""
+    from safepy_b200 import _lib
+    rng = np.random.default_rng(n)
+    attrs = rng.standard_normal((n, 2)).astype(np.float32)
+    attrs[rng.random(n) < 0.25] = np.nan
+    idx = np.nonzero(np.sum(~np.isnan(attrs), axis=1))[0]
+    stream = _lib.PermStream(n, idx, seed)
+    if seed is None:                                   # OS entropy: only the structure can be checked
+        rows = stream.next(perms)
+        assert all(sorted(r) == list(range(n)) for r in rows)
+        moved = np.setdiff1d(np.arange(n), idx)
+        assert np.array_equal(rows[:, moved], np.tile(moved, (perms, 1)))
+        return
+    ref = orc.perm_gather_rows(attrs, perms, seed)
+    state = np.random.get_state()
+    first = stream.next(perms // 2)
+    stream.skip(1)                                     # a skipped permutation still advances the stream
+    rest = stream.next(perms - perms // 2 - 1)
+    assert np.array_equal(first, ref[:perms // 2]) and np.array_equal(rest, ref[perms // 2 + 1:])
+    key, pos, drawn = stream.state()
+    assert drawn == perms and pos == state[2] and np.array_equal(key, state[1])
+    np.random.seed(12345)
+    stream.sync_numpy()
+    assert np.array_equal(np.random.get_state()[1], state[1]) and np.random.get_state()[2] == state[2]
+    # make_perm_rows goes through the same stream and leaves NumPy's generator where upstream would
+    np.random.seed(999)
+    assert np.array_equal(make_perm_rows(attrs, perms, seed), ref)
+    assert np.array_equal(np.random.get_state()[1], state[1])
+
+
+def test_perm_stream_rejects_bad_input():
+    from safepy_b200 import _lib
+    with pytest.raises(ValueError):
+        _lib.PermStream(10, np.arange(10), -1)
+    with pytest.raises(_lib.SafeB200Error, match="out of range"):
+        _lib.PermStream(10, np.array([3, 10]), 1)
+    from safepy_b200.permutations import native_seed
+    assert native_seed(None) and native_seed(7) and native_seed(np.int64(7))
+    assert not native_seed(2 ** 32) and not native_seed([1, 2]) and not native_seed(True)

@@ -100,3 +100,21 @@ def test_gpu_define_top_attributes_api(ctx):
     assert np.array_equal(sf.attributes["top"].values.astype(bool), g["top"])
     assert np.array_equal(sf.attributes["num_connected_components"].values, g["num_cc"])
     assert np.array_equal(sf.attributes["num_large_connected_components"].values, g["num_large_cc"])
+
+
+@pytest.mark.gpu
+def test_gpu_network_from_arrays_uses_the_device_csr(ctx, stage1_small):
+    """load_network(edges, x, y): edge lengths and the CSR come from the device; same neighborhoods as the reference
+    computed from its networkx graph."""
+    from safepy_b200 import SAFE
+    from safepy_b200.safe import graph_csr
+    g = stage1_small
+    sf = SAFE(verbose=False)
+    sf.load_network(edges=g["edges"], x=g["x"], y=g["y"])
+    walked = graph_csr(sf.graph, "length")                       # host walk over the graph object
+    sf.graph.graph.pop("_safe_b200_csr")
+    built = graph_csr(sf.graph, "length", ctx)                   # sb_graph_csr on the stored arrays
+    for a, b in zip(walked, built):
+        assert np.array_equal(a, b)
+    sf.define_neighborhoods(neighborhood_radius=float(g["r_layout"]))
+    assert np.array_equal(sf.neighborhoods.words, g["nb_layout"])

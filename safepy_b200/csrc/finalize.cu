@@ -267,6 +267,10 @@ __global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys
     for (int64_t i = b; i < e; ++i) mn = fmin(mn, __ddiv_rn(k[i], __ddiv_rn(static_cast<double>(i + 1), dm)));
     part[t] = mn;
     const bool has_nan = __syncthreads_or(nan_here);
+    if (has_nan) {  // not through idx: with a NaN among the keys the sort may not even return a permutation
+        for (int64_t i = t; i < m; i += 256) o[i] = qnan();
+        return;
+    }
     for (int off = 1; off < 256; off <<= 1) {  // inclusive suffix minimum
         const double v = t + off < 256 ? part[t + off] : __longlong_as_double(0x7FF0000000000000ll);
         __syncthreads();
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys
     double run = t + 1 < 256 ? part[t + 1] : __longlong_as_double(0x7FF0000000000000ll);
     for (int64_t i = e - 1; i >= b; --i) {
         run = fmin(run, __ddiv_rn(k[i], __ddiv_rn(static_cast<double>(i + 1), dm)));
-        o[ix[i]] = has_nan ? qnan() : fmin(run, 1.0);
+        o[ix[i]] = fmin(run, 1.0);
     }
 }
 

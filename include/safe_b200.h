@@ -194,6 +194,11 @@ int sb_perm_stream_state(sb_perm_stream* s, uint32_t* key624_out, int32_t* pos_o
 /* sb_enrich_null_add for the next num_perm permutations of a stream, in one call: a producer thread replays piece
  * k + 1 into pinned memory while the device counts piece k */
 int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm);
+/* The same for rank `rank` of `world` processes that each hold the same stream: the next num_perm permutations are
+ * dealt round-robin in equal pieces, this rank counts its pieces and draws-and-drops the others (the RNG cannot jump),
+ * so the foreign draws overlap with its own device work.  The ranks' counts add up to the full null
+ * (sb_enrich_null_counts_dev + one all-reduce, then sb_enrich_null_set_perms). */
+int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num_perm, int world, int rank);
 
 /* Tail of SAFE.compute_pvalues_by_randomization (safe.py:526-554) and of SAFE.compute_pvalues (safe.py:466-472):
  *   p = counts / P (NaN where the observed score is NaN); optional Benjamini-Hochberg adjustment of every row across

@@ -73,6 +73,7 @@ SIGNATURES = {
     "sb_perm_stream_next": (C.c_int, [_vp, _i64, _vp]),
     "sb_perm_stream_state": (C.c_int, [_vp, _vp, C.POINTER(_i32), C.POINTER(_i64)]),
     "sb_enrich_null_add_stream": (C.c_int, [_vp, _vp, _i64]),
+    "sb_enrich_null_add_stream_shard": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int]),
     "sb_enrich_null_finalize": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_double, C.c_int, C.c_double,
                                           _vp, _vp, _vp, _vp, _vp, _vp]),
     "sb_enrich_hypergeom_finalize": (C.c_int, [_vp, C.c_int, C.c_double, _vp, _vp, _vp, _vp]),
@@ -377,9 +378,12 @@ class Enrichment:
         _check(self.lib, self.lib.sb_enrich_null_add(self.h, _ptr(perm_rows), perm_rows.shape[0]))
         return self
 
-    def null_add_stream(self, stream, num_perm):
-        """Count the next `num_perm` permutations of a PermStream (replay and device work overlap inside the call)."""
-        _check(self.lib, self.lib.sb_enrich_null_add_stream(self.h, stream.h, int(num_perm)))
+    def null_add_stream(self, stream, num_perm, world=1, rank=0):
+        """Count the next `num_perm` permutations of a PermStream (replay and device work overlap inside the call).
+        With world > 1 the permutations are dealt round-robin in pieces and only this rank's pieces are counted; the
+        others are drawn and dropped so that every rank's stream stays aligned."""
+        _check(self.lib, self.lib.sb_enrich_null_add_stream_shard(self.h, stream.h, int(num_perm), int(world),
+                                                                  int(rank)))
         return self
 
     def null_counts(self, want_counts=True):

@@ -187,21 +187,35 @@ int sb_perm_stream_state(sb_perm_stream* s, uint32_t* key624_out, int32_t* pos_o
     SB_API_END
 }
 
-int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm) {
+int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num_perm, int world, int rank) {
     SB_API_BEGIN
     SB_CHECK(e && s, "sb_enrich_null_add_stream: NULL argument");
     SB_CHECK(e->null_score >= 0, "sb_enrich_null_add_stream: call sb_enrich_null_begin first");
     SB_CHECK(s->n == e->n, "sb_enrich_null_add_stream: the stream permutes %lld rows, the plan has %lld",
              (long long)s->n, (long long)e->n);
     SB_CHECK(num_perm >= 0, "sb_enrich_null_add_stream: num_perm < 0");
+    SB_CHECK(world >= 1 && rank >= 0 && rank < world, "sb_enrich_null_add_stream: rank %d of %d", rank, world);
     if (num_perm == 0) return 0;
     sb_ctx* ctx = e->ctx;
     ctx->bind();
     cudaStream_t st = ctx->stream;
     const int64_t n = e->n;
     const size_t cells = static_cast<size_t>(n) * e->m;
-    // pieces double from 16 permutations (the device gets work at once) up to `piece`
+    // Piece schedule.  One rank: pieces double from 16 permutations (the device gets work at once) up to `piece`.
+    // Several ranks: equal pieces dealt round-robin, ~4 per rank, so that drawing the other ranks' pieces (the RNG
+    // cannot jump) overlaps with counting one's own instead of preceding it.
     const int64_t piece = std::max<int64_t>(1, std::min<int64_t>(128, (64ll << 20) / n));
+    const int64_t dealt = std::max<int64_t>(1, std::min(piece, std::max<int64_t>(8, (num_perm + world * 4 - 1) / (world * 4))));
+    auto piece_size = [&](int64_t q) {
+        if (world > 1) return dealt;
+        return q < 4 ? std::min<int64_t>(piece, 16ll << q) : piece;
+    };
+    int64_t mine = 0;
+    for (int64_t q = 0, left = num_perm; left > 0; ++q) {
+        const int64_t np = std::min(piece_size(q), left);
+        if (q % world == rank) mine += np;
+        left -= np;
+    }
     constexpr int kRing = 3;
     RingLease lease(static_cast<size_t>(kRing) * piece * n * sizeof(int32_t));
     int32_t* ring = lease.p;
@@ -212,14 +226,19 @@ int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm)
     int64_t filled[kRing] = {0, 0, 0};  // permutations waiting in each slot (0 = free)
     bool abort = false;
     std::thread producer([&] {
-        int64_t left = num_perm, size = std::min<int64_t>(16, piece);
-        for (int slot = 0; left > 0; slot = (slot + 1) % kRing) {
+        int slot = 0;
+        for (int64_t q = 0, left = num_perm; left > 0; ++q) {
+            const int64_t np = std::min(piece_size(q), left);
+            left -= np;
+            if (q % world != rank) {  // another rank's piece: drawn and dropped
+                for (int64_t p = 0; p < np; ++p) s->next_into(nullptr);
+                continue;
+            }
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return filled[slot] == 0 || abort; });
                 if (abort) return;
             }
-            const int64_t np = std::min(size, left);
             int32_t* dst = ring + static_cast<size_t>(slot) * piece * n;
             for (int64_t p = 0; p < np; ++p) s->next_into(dst + p * n);
             {
@@ -227,14 +246,13 @@ int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm)
                 filled[slot] = np;
             }
             cv.notify_all();
-            left -= np;
-            size = std::min(piece, size * 2);
+            slot = (slot + 1) % kRing;
         }
     });
     std::string error;
     try {
         int64_t done = 0;
-        for (int slot = 0; done < num_perm; slot = (slot + 1) % kRing) {
+        for (int slot = 0; done < mine; slot = (slot + 1) % kRing) {
             int64_t np;
             {
                 std::unique_lock<std::mutex> lk(mu);
@@ -273,6 +291,10 @@ int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm)
     if (!error.empty()) fail("%s", error.c_str());
     for (int i = 0; i < 7; ++i) e->stats[i] = e->null_stats[i];
     SB_API_END
+}
+
+int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm) {
+    return sb_enrich_null_add_stream_shard(e, s, num_perm, 1, 0);
 }
 
 }  // extern "C"

@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 from .neighborhood_matrix import PackedNeighborhoods, as_packed
 from .ordering import kd_order
-from .distributed import DeviceArray, active_group, broadcast_row_shards, row_shard, shard_stream
+from .distributed import DeviceArray, active_group, broadcast_row_shards, row_shard
 from .permutations import iter_perm_rows, native_seed, perm_stream
 
 DEFAULTS = {
@@ -110,6 +110,7 @@ class SafeB200Mixin:
 
     device = -1
     multi_gpu = True  # follow torch.distributed when the caller has initialised it (one process per GPU)
+    results_rank = None  # with several ranks: None = every rank receives the [N, M] result arrays, r = only rank r
     _plan = None  # enrichment plan of the compute_pvalues call in progress
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
@@ -262,8 +263,7 @@ class SafeB200Mixin:
                 # sums its worker results the same way), then every rank runs the tail on the full counts
                 import torch
                 stream = perm_stream(self.node2attribute, self.random_seed)
-                shard_stream(stream, self.num_permutations, dist.get_world_size(), dist.get_rank(),
-                             plan.null_add_stream)
+                plan.null_add_stream(stream, self.num_permutations, dist.get_world_size(), dist.get_rank())
                 stream.sync_numpy()
                 stream.close()
                 plan.ctx.synchronize()
@@ -288,16 +288,19 @@ class SafeB200Mixin:
             t2 = time.perf_counter()
             if self.multiple_testing:
                 logging.info("Running FDR-adjustment of p-values...")
+            want = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
+            if dist and self.results_rank is not None and dist.get_rank() != self.results_rank:
+                want = ()            # this rank keeps only the per-attribute sums
             out = plan.null_finalize(self.num_permutations, self.attribute_sign, self.enrichment_threshold,
-                                     self.multiple_testing)
+                                     self.multiple_testing, want=want)
             self.last_enrichment_stats = plan.stats()
         # host wall clock of the three phases (upload + CSR view, streamed null, fused tail + result copies)
         self.last_enrichment_seconds = {"plan": t1 - t0, "null": t2 - t1, "tail": time.perf_counter() - t2}
-        self.ns = out["ns"]
-        self.pvalues_neg = out["pvalues_neg"]
-        self.pvalues_pos = out["pvalues_pos"]
-        self.nes = out["nes"]
-        self._tail = (out["nes_binary"], out["num_neighborhoods_enriched"])
+        self.ns = out.get("ns")
+        self.pvalues_neg = out.get("pvalues_neg")
+        self.pvalues_pos = out.get("pvalues_pos")
+        self.nes = out.get("nes")
+        self._tail = (out.get("nes_binary"), out["num_neighborhoods_enriched"])
 
     def compute_pvalues_by_hypergeom(self, **kwargs):
         if kwargs:

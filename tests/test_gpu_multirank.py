@@ -53,6 +53,14 @@ def _worker(rank, world, port, out_dir):
     st = sf.last_enrichment_stats
     share = st["decided"] + st["fixups"]
     assert 0 < share < n * 6 * P                      # this rank counted only its shard
+    sf.results_rank = 1                               # only rank 1 receives the [N, M] arrays
+    sf.compute_pvalues(how="randomization", num_permutations=P, verbose=False)
+    assert np.array_equal(sf.attributes["num_neighborhoods_enriched"].values, g["rand_enriched_normal32"])
+    if rank == 1:
+        assert np.array_equal(sf.nes, g["rand_nes_normal32"], equal_nan=True)
+    else:
+        assert sf.nes is None and sf.nes_binary is None and sf.pvalues_pos is None
+    sf.results_rank = None
     sf.multi_gpu = False                              # opt out: the rank does everything itself
     sf.define_neighborhoods(node_distance_metric="euclidean", neighborhood_radius=0.1)
     assert np.array_equal(sf.neighborhoods.words, euclid)

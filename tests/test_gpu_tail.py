@@ -97,6 +97,28 @@ def test_null_from_native_stream(small, kind, perms):
         plan.null_add_stream(other, 1)
 
 
+@pytest.mark.parametrize("world,perms", [(2, 60), (3, 100), (8, 37)])
+def test_round_robin_shards_add_up(small, world, perms):
+    """sb_enrich_null_add_stream_shard: every rank draws the whole stream and counts the pieces dealt to it; here the
+    ranks run one after the other into the same count arrays."""
+    from safepy_b200.permutations import perm_stream
+    g, n, nb = small
+    attrs = g["attr_normal32"]
+    plan = _lib.Enrichment(nb, attrs)
+    cneg0, cpos0 = plan.perm_counts(make_perm_rows(attrs, perms, 5))
+    plan.null_begin("sum", "auto")
+    shares = []
+    for rank in range(world):
+        stream = perm_stream(attrs, 5)
+        before = plan.null_counts(False)[0]
+        plan.null_add_stream(stream, perms, world, rank)
+        shares.append(plan.null_counts(False)[0] - before)
+        assert stream.state()[2] == perms                       # the whole stream was drawn
+    assert sum(shares) == perms and (world > perms // 8 or min(shares) > 0)
+    _, cneg, cpos = plan.null_counts()
+    assert np.array_equal(cneg, cneg0) and np.array_equal(cpos, cpos0)
+
+
 def test_tail_needs_a_table_entry_per_count(small):
     g, n, nb = small
     attrs = g["attr_dyadic"]

@@ -174,6 +174,9 @@ namespace sb {
 // speed and worker threads move them into the caller's buffer, so that the first-touch page faults of a freshly
 // allocated destination are taken in parallel.  Returns after the whole copy has landed.
 void copy_out(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+// The other direction: worker threads fill the pinned ring from pageable memory, the caller's thread uploads the
+// slots in order.  Both fall back to one cudaMemcpyAsync for small or already pinned buffers.
+void copy_in(sb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
 }  // namespace sb
 
 static inline int64_t sb_ld_words(int64_t n) { return ((n + 31) / 32 + 3) / 4 * 4; }

@@ -534,7 +534,7 @@ int sb_enrich_create(sb_ctx* ctx, sb_neigh* a, const void* b_host, int dtype, in
         void* d = dev_alloc(bytes);
         e->b = d;
         e->b_owned = true;
-        SB_CUDA(cudaMemcpyAsync(d, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        copy_in(ctx, d, b_host, bytes);
         build_csr(e);
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
     } catch (...) {
@@ -590,9 +590,7 @@ int sb_enrich_score(sb_enrich* e, int score_type, double* out_host) {
     SB_CHECK(e && out_host, "sb_enrich_score: NULL argument");
     e->ctx->bind();
     const double* s = enrich_observed(e, score_type);
-    SB_CUDA(cudaMemcpyAsync(out_host, s, static_cast<size_t>(e->n) * e->m * sizeof(double), cudaMemcpyDeviceToHost,
-                            e->ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(e->ctx->stream));
+    copy_out(e->ctx, out_host, s, static_cast<size_t>(e->n) * e->m * sizeof(double));
     SB_API_END
 }
 
@@ -640,10 +638,8 @@ int sb_enrich_perm_counts(sb_enrich* e, int score_type, int engine, const int32_
         if (rc) fail("%s", sb_last_error());
         SB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
-    SB_CUDA(cudaMemcpyAsync(counts_neg_host, cnt.p, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SB_CUDA(cudaMemcpyAsync(counts_pos_host, cnt.p + cells, cells * sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                            ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(ctx->stream));
+    copy_out(ctx, counts_neg_host, cnt.p, cells * sizeof(uint32_t));
+    copy_out(ctx, counts_pos_host, cnt.p + cells, cells * sizeof(uint32_t));
     SB_API_END
 }
 
@@ -703,10 +699,8 @@ int sb_enrich_hypergeom(sb_enrich* e, double* pvalues_host, double* nes_host) {
     if (pvalues_host) pv.reserve(cells);
     if (nes_host) nes.reserve(cells);
     hypergeom_dev(e, pv.p, nes.p);
-    if (pvalues_host)
-        SB_CUDA(cudaMemcpyAsync(pvalues_host, pv.p, cells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (nes_host)
-        SB_CUDA(cudaMemcpyAsync(nes_host, nes.p, cells * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (pvalues_host) copy_out(ctx, pvalues_host, pv.p, cells * sizeof(double));
+    if (nes_host) copy_out(ctx, nes_host, nes.p, cells * sizeof(double));
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     SB_API_END
 }

@@ -12,6 +12,8 @@
 //   k_jaccard           pairwise Jaccard distances between nes_binary columns of the top attributes, the metric
 //                       evaluation inside define_domains' linkage(..., metric='jaccard') (safe.py:672-675)
 //   copy_out            large device -> host result copies through a pinned ring drained by worker threads
+#include <sys/mman.h>
+
 #include <algorithm>
 #include <condition_variable>
 #include <deque>
@@ -25,33 +27,38 @@
 
 namespace sb {
 
-// ================================================================================================ copy_out
+// ================================================================================================ copy_out / copy_in
 namespace {
 
-struct OutRing {
+// Pinned ring + worker threads shared by the two directions.  Large transfers between the device and PAGEABLE host
+// memory are otherwise bound by one thread: the driver stages them through its own pinned buffer with a
+// single-threaded memcpy, and for a freshly allocated destination that thread also takes every first-touch page fault.
+struct HostRing {
     static constexpr int kSlots = 16;
     static constexpr size_t kSlot = 4u << 20;
     struct Task {
         int slot;
-        int device;
-        void* dst;
+        int device;      // >= 0: device -> host piece (wait for the slot's event, then copy out of the ring)
+        void* host;      //  < 0: host -> device piece (copy into the ring, then flag the slot ready)
         size_t bytes;
     };
     char* pinned = nullptr;
     cudaEvent_t ev[kSlots];
-    bool busy[kSlots];
-    std::mutex mu;                 // queue + busy flags
+    bool busy[kSlots];   // a worker still owns the slot
+    bool used[kSlots];   // the slot's event has been recorded by an upload of this call
+    std::mutex mu;       // queue + flags
     std::condition_variable cv_work, cv_done;
     std::deque<Task> queue;
     int pending = 0;
-    std::mutex call_mu;            // one copy_out at a time
+    std::mutex call_mu;  // one transfer at a time
     int workers = 0;
 
     void start() {
-        SB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pinned), kSlots * kSlot, cudaHostAllocDefault));
+        SB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&pinned), kSlots * kSlot, cudaHostAllocPortable));
         for (int i = 0; i < kSlots; ++i) {
             SB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
             busy[i] = false;
+            used[i] = false;
         }
         const unsigned hw = std::thread::hardware_concurrency();
         workers = static_cast<int>(std::max(2u, std::min(8u, hw ? hw : 2u)));
@@ -66,9 +73,14 @@ struct OutRing {
                 t = queue.front();
                 queue.pop_front();
             }
-            cudaSetDevice(t.device);
-            cudaEventSynchronize(ev[t.slot]);
-            memcpy(t.dst, pinned + static_cast<size_t>(t.slot) * kSlot, t.bytes);
+            char* ring = pinned + static_cast<size_t>(t.slot) * kSlot;
+            if (t.device >= 0) {
+                cudaSetDevice(t.device);
+                cudaEventSynchronize(ev[t.slot]);
+                memcpy(t.host, ring, t.bytes);
+            } else {
+                memcpy(ring, t.host, t.bytes);
+            }
             {
                 std::lock_guard<std::mutex> lk(mu);
                 busy[t.slot] = false;
@@ -77,18 +89,46 @@ struct OutRing {
             cv_done.notify_all();
         }
     }
+    void push(const Task& t) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            busy[t.slot] = true;
+            ++pending;
+            queue.push_back(t);
+        }
+        cv_work.notify_one();
+    }
+    void wait_slot(int slot) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return !busy[slot]; });
+    }
+    void wait_all() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+    }
 };
 
-OutRing* out_ring() {
-    static OutRing* ring = nullptr;  // leaked on purpose: detached workers may outlive static destruction
+// one ring per device (its events belong to that device's context); created with the device current
+HostRing* host_ring(int device) {
+    static HostRing* rings[64] = {};  // leaked on purpose: detached workers may outlive static destruction
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
-    if (!ring) {
-        OutRing* r = new OutRing;
+    SB_CHECK(device >= 0 && device < 64, "device ordinal %d out of range", device);
+    if (!rings[device]) {
+        HostRing* r = new HostRing;
         r->start();
-        ring = r;
+        rings[device] = r;
     }
-    return ring;
+    return rings[device];
+}
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
 }
 
 }  // namespace
@@ -96,40 +136,72 @@ OutRing* out_ring() {
 void copy_out(sb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
     if (bytes == 0) return;
     cudaStream_t st = ctx->stream;
-    if (bytes < 2 * OutRing::kSlot) {
+    if (bytes < 2 * HostRing::kSlot || !is_pageable(dst_host)) {
         SB_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
         return;
     }
     PhaseTrace tr(ctx, "copy_out");
-    OutRing* r = out_ring();
+    {
+        // a fresh NumPy buffer is untouched anonymous memory: ask for huge pages on its 2 MB-aligned interior so the
+        // first-touch faults below come 512x fewer (no-op where transparent huge pages are off)
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(dst_host) + (1u << 21) - 1) & ~((uintptr_t(1) << 21) - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(dst_host) + bytes) & ~((uintptr_t(1) << 21) - 1);
+        if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+    }
+    HostRing* r = host_ring(ctx->device);
     std::lock_guard<std::mutex> call(r->call_mu);
     const char* src = static_cast<const char*>(src_dev);
     char* dst = static_cast<char*>(dst_host);
     int slot = 0;
     cudaError_t err = cudaSuccess;
-    for (size_t off = 0; off < bytes && err == cudaSuccess; off += OutRing::kSlot, slot = (slot + 1) % OutRing::kSlots) {
-        const size_t len = std::min(OutRing::kSlot, bytes - off);
-        {
-            std::unique_lock<std::mutex> lk(r->mu);
-            r->cv_done.wait(lk, [&] { return !r->busy[slot]; });
-            r->busy[slot] = true;
-            ++r->pending;
-        }
-        err = cudaMemcpyAsync(r->pinned + static_cast<size_t>(slot) * OutRing::kSlot, src + off, len,
+    for (size_t off = 0; off < bytes && err == cudaSuccess; off += HostRing::kSlot, slot = (slot + 1) % HostRing::kSlots) {
+        const size_t len = std::min(HostRing::kSlot, bytes - off);
+        r->wait_slot(slot);
+        err = cudaMemcpyAsync(r->pinned + static_cast<size_t>(slot) * HostRing::kSlot, src + off, len,
                               cudaMemcpyDeviceToHost, st);
         if (err == cudaSuccess) err = cudaEventRecord(r->ev[slot], st);
-        {
-            // even after a failed launch the slot goes through a worker (the event then refers to earlier work)
-            std::lock_guard<std::mutex> lk(r->mu);
-            r->queue.push_back({slot, ctx->device, dst + off, err == cudaSuccess ? len : 0});
+        if (err == cudaSuccess) r->push({slot, ctx->device, dst + off, len});
+    }
+    r->wait_all();
+    SB_CUDA(err);
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+void copy_in(sb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    if (bytes == 0) return;
+    cudaStream_t st = ctx->stream;
+    if (bytes < 2 * HostRing::kSlot || !is_pageable(src_host)) {
+        SB_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    PhaseTrace tr(ctx, "copy_in");
+    HostRing* r = host_ring(ctx->device);
+    std::lock_guard<std::mutex> call(r->call_mu);
+    char* src = static_cast<char*>(const_cast<void*>(src_host));
+    char* dst = static_cast<char*>(dst_dev);
+    const size_t pieces = (bytes + HostRing::kSlot - 1) / HostRing::kSlot;
+    for (int i = 0; i < HostRing::kSlots; ++i) r->used[i] = false;
+    cudaError_t err = cudaSuccess;
+    size_t enq = 0;
+    for (size_t iss = 0; iss < pieces && err == cudaSuccess; ++iss) {
+        // keep the workers a ring ahead of the uploads
+        for (; enq < pieces && enq - iss < static_cast<size_t>(HostRing::kSlots); ++enq) {
+            const int slot = static_cast<int>(enq % HostRing::kSlots);
+            if (r->used[slot]) cudaEventSynchronize(r->ev[slot]);  // the slot's previous upload has left the ring
+            const size_t off = enq * HostRing::kSlot;
+            r->push({slot, -1, src + off, std::min(HostRing::kSlot, bytes - off)});
         }
-        r->cv_work.notify_one();
+        const int slot = static_cast<int>(iss % HostRing::kSlots);
+        const size_t off = iss * HostRing::kSlot;
+        r->wait_slot(slot);
+        err = cudaMemcpyAsync(dst + off, r->pinned + static_cast<size_t>(slot) * HostRing::kSlot,
+                              std::min(HostRing::kSlot, bytes - off), cudaMemcpyHostToDevice, st);
+        if (err == cudaSuccess) err = cudaEventRecord(r->ev[slot], st);
+        r->used[slot] = true;
     }
-    {
-        std::unique_lock<std::mutex> lk(r->mu);
-        r->cv_done.wait(lk, [&] { return r->pending == 0; });
-    }
+    r->wait_all();
     SB_CUDA(err);
     SB_CUDA(cudaStreamSynchronize(st));
 }
@@ -621,7 +693,7 @@ int sb_fdr_rows(sb_ctx* ctx, int64_t n, int64_t m, const double* pvalues_host, d
     for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
         const int64_t rows = std::min(rows_per, n - r0);
         const size_t at = static_cast<size_t>(r0) * m, len = static_cast<size_t>(rows) * m;
-        SB_CUDA(cudaMemcpyAsync(p.p, pvalues_host + at, len * sizeof(double), cudaMemcpyHostToDevice, st));
+        copy_in(ctx, p.p, pvalues_host + at, len * sizeof(double));
         bh_rows(ctx, bh, p.p, rows, m);
         copy_out(ctx, adjusted_host + at, p.p, len * sizeof(double));
     }
@@ -651,7 +723,7 @@ int sb_attr_jaccard(sb_ctx* ctx, int64_t n, const uint8_t* member_host, int64_t 
     cols.reserve(n_cols);
     bits.reserve(static_cast<size_t>(n_cols) * words);
     out.reserve(pairs);
-    SB_CUDA(cudaMemcpyAsync(member.p, member_host, static_cast<size_t>(n) * m, cudaMemcpyHostToDevice, st));
+    copy_in(ctx, member.p, member_host, static_cast<size_t>(n) * m);
     SB_CUDA(cudaMemcpyAsync(cols.p, cols_host, n_cols * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     k_pack_columns<<<dim3(static_cast<unsigned>(sb_ceil_div(n_cols, 128)), static_cast<unsigned>(words)), 128, 0, st>>>(
         member.p, n, m, cols.p, n_cols, words, bits.p);

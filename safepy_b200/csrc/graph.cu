@@ -307,7 +307,7 @@ int sb_graph_components(sb_ctx* ctx, int64_t n, const int64_t* indptr_host, cons
     mem.reserve(static_cast<size_t>(n) * m);
     SB_CUDA(cudaMemcpyAsync(ptr.p, indptr_host, (n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
     if (nnz) SB_CUDA(cudaMemcpyAsync(idx.p, indices_host, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    SB_CUDA(cudaMemcpyAsync(mem.p, member_host, static_cast<size_t>(n) * m, cudaMemcpyHostToDevice, st));
+    copy_in(ctx, mem.p, member_host, static_cast<size_t>(n) * m);
     // candidates are processed in chunks so that the label / size scratch stays below ~2 GiB
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_cand, (1ll << 28) / n));
     labels.reserve(static_cast<size_t>(chunk) * n);

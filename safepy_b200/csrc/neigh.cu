@@ -618,9 +618,7 @@ int sb_neigh_upload_packed(sb_neigh* a, const uint32_t* words_host, int64_t row0
     check_rows(a, row0, row1, "sb_neigh_upload_packed");
     SB_CHECK(words_host, "sb_neigh_upload_packed: words_host is NULL");
     a->ctx->bind();
-    SB_CUDA(cudaMemcpyAsync(a->words + row0 * a->ld, words_host, (row1 - row0) * a->ld * sizeof(uint32_t),
-                            cudaMemcpyHostToDevice, a->ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    copy_in(a->ctx, a->words + row0 * a->ld, words_host, (row1 - row0) * a->ld * sizeof(uint32_t));
     SB_API_END
 }
 
@@ -629,9 +627,7 @@ int sb_neigh_download_packed(sb_neigh* a, uint32_t* words_host, int64_t row0, in
     check_rows(a, row0, row1, "sb_neigh_download_packed");
     SB_CHECK(words_host, "sb_neigh_download_packed: words_host is NULL");
     a->ctx->bind();
-    SB_CUDA(cudaMemcpyAsync(words_host, a->words + row0 * a->ld, (row1 - row0) * a->ld * sizeof(uint32_t),
-                            cudaMemcpyDeviceToHost, a->ctx->stream));
-    SB_CUDA(cudaStreamSynchronize(a->ctx->stream));
+    copy_out(a->ctx, words_host, a->words + row0 * a->ld, (row1 - row0) * a->ld * sizeof(uint32_t));
     SB_API_END
 }
 

@@ -36,13 +36,18 @@ def import_reference():
             def __getattr__(self, name):
                 return _Anything()
 
+        def anything(name):
+            if name.startswith("__"):       # inspect / importlib probe modules for __file__, __path__, ...
+                raise AttributeError(name)
+            return _Anything()
+
         mpl = _stub("matplotlib", use=lambda *a, **k: None, rcParams={})
-        mpl.pyplot = _stub("matplotlib.pyplot", __getattr__=lambda name: _Anything())
+        mpl.pyplot = _stub("matplotlib.pyplot", __getattr__=anything)
         mpl.colors = _stub("matplotlib.colors", Normalize=_Anything, LinearSegmentedColormap=_Anything,
-                           __getattr__=lambda name: _Anything())
-        mpl.cm = _stub("matplotlib.cm", __getattr__=lambda name: _Anything())
-        mpl.patches = _stub("matplotlib.patches", __getattr__=lambda name: _Anything())
-        mpl.collections = _stub("matplotlib.collections", __getattr__=lambda name: _Anything())
+                           __getattr__=anything)
+        mpl.cm = _stub("matplotlib.cm", __getattr__=anything)
+        mpl.patches = _stub("matplotlib.patches", __getattr__=anything)
+        mpl.collections = _stub("matplotlib.collections", __getattr__=anything)
     try:
         import statsmodels.stats.multitest  # noqa: F401
     except ImportError:

@@ -315,11 +315,12 @@ __global__ void k_bh_prepare(int64_t rows, int64_t m, int32_t* __restrict__ idx,
     for (; i < cells; i += step) idx[i] = static_cast<int32_t>(i % m);
 }
 
-// One CTA per row.  keys = the row's p-values ascending, idx = their columns, out = the row itself (overwritten).  statsmodels' fdrcorrection:
+// One CTA per row.  keys = the row's p-values ascending, idx = their columns, out = the row itself (overwritten).
+// statsmodels' fdrcorrection:
 //   ecdf[k] = (k + 1) / m;  raw[k] = p_sorted[k] / ecdf[k];  adj = reverse running minimum of raw, capped at 1,
 // scattered back to the original columns.  A NaN anywhere in the row propagates through np.minimum.accumulate from
-// the end (argsort puts NaNs last), so the whole row becomes NaN.  Tied p-values all receive the value of the last of them
-// (the quotient is monotone in k), so the order a sort leaves ties in does not matter.
+// the end (argsort puts NaNs last), so the whole row becomes NaN.  Tied p-values all receive the value of the last
+// of them (the quotient is monotone in k), so the order a sort leaves ties in does not matter.
 __global__ void __launch_bounds__(256) k_bh_rows(const double* __restrict__ keys, const int32_t* __restrict__ idx,
                                                  int64_t m, double* __restrict__ out) {
     const int64_t row = blockIdx.x;

@@ -518,7 +518,8 @@ def run_ours(args):
                     sf.compute_pvalues(num_permutations=P)
                     t_cp = time.perf_counter() - t0
                 out["stages"]["safe_api"] = {
-                    "define_neighborhoods_s": t_dn, "compute_pvalues_s": t_cp,
+                    "define_neighborhoods_s": t_dn, "compute_pvalues_s": t_cp, "total_s": t_dn + t_cp,
+                    "metric": "define_neighborhoods+compute_pvalues sec (BASELINE.json's second metric)",
                     "compute_pvalues_phases_s": getattr(sf, "last_enrichment_seconds", None),
                     "note": "safepy_b200.SAFE.define_neighborhoods() + compute_pvalues(num_permutations=%d) on the "
                             "same workload, wall clock of the second call (graph object already built)" % P}

@@ -64,7 +64,7 @@ struct sb_perm_stream {
     //   1. which draw each position accepts: inside a run of positions with the same mask the only loop-carried value
     //      is i itself (i -= accepted), a rejected draw is simply overwritten by the next one;
     //   2. the swaps, in the same descending order, with all indices known up front.
-    // 1.75x the single-loop version, 5x NumPy, same permutation bit for bit.
+    // 1.75x the single-loop version, 4x NumPy's shuffle, same permutation bit for bit.
     void shuffle(int32_t* a, int64_t k) {
         uint32_t* js = draws.data();
         int64_t i = k - 1;

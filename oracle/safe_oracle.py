@@ -293,7 +293,9 @@ def fdrcorrection(pvals):
     restatement of its published algorithm, not a replay:
         sortind = argsort(p); ps = p[sortind]; ecdf = arange(1, n + 1) / float(n)
         raw = ps / ecdf; adj = minimum.accumulate(raw[::-1])[::-1]; adj[adj > 1] = 1; out[sortind] = adj
-    NaNs sort last and np.minimum propagates them, so one NaN turns the whole vector into NaN."""
+    NaNs sort last and np.minimum propagates them, so one NaN turns the whole vector into NaN.
+    tests/test_oracle_golden.py cross-checks it against scipy.stats.false_discovery_control(method='bh'), an
+    independent implementation in an installed library (equal to the last bit or one ulp: SciPy multiplies by m / k)."""
     pvals = np.asarray(pvals, dtype=np.float64)
     nobs = len(pvals)
     sortind = np.argsort(pvals)

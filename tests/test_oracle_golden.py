@@ -138,6 +138,14 @@ def test_fdr_restatement_is_benjamini_hochberg():
         assert np.allclose(adj[r], expect, rtol=0, atol=1e-15)
     assert np.all(adj >= p - 1e-18) and np.all(adj <= 1)
     assert len(set(adj[1, 4:9])) == 1
+    # an independent implementation in an installed library: SciPy's Benjamini-Hochberg (p * m / k instead of
+    # statsmodels' p / (k / m): equal up to the last bit)
+    from scipy.stats import false_discovery_control
+    big = rng.uniform(size=(20, 300))
+    big[rng.uniform(size=big.shape) < 0.2] = 0.0
+    big = np.where(rng.uniform(size=big.shape) < 0.3, np.round(big, 2), big)
+    scipy_bh = np.stack([false_discovery_control(r, method="bh") for r in big])
+    assert np.allclose(orc.fdr_rows(big), scipy_bh, rtol=1e-15, atol=1e-16)
     q = p.copy()
     q[3, 7] = np.nan
     adj2 = orc.fdr_rows(q)

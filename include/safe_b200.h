@@ -61,6 +61,8 @@ const char* sb_last_error(void);
 /* device < 0: use the current CUDA device. Fails unless the device is compute capability 10.x. */
 int sb_ctx_create(int device, sb_ctx** out);
 int sb_ctx_destroy(sb_ctx* ctx);
+/* ordinal of the calling thread's current CUDA device (what device < 0 resolves to), -1 without a usable device */
+int sb_current_device(void);
 /* CUDA device ordinal of the context (-1 for a NULL handle) */
 int sb_ctx_device(sb_ctx* ctx);
 /* run all subsequent work of this context on an existing cudaStream_t (e.g. torch's current stream) */

@@ -359,7 +359,10 @@ def define_domains(nes, nes_binary_matrix, top, attribute_distance_threshold, at
     domain[top] = domains
     ids = np.unique(domain)                                    # groupby sorts its keys
     counts = np.stack([nb[:, domain == d].sum(axis=1) for d in ids], axis=1)
-    maxnes = np.stack([nes[:, domain == d].max(axis=1) for d in ids], axis=1)
+    import warnings
+    with warnings.catch_warnings():                            # groupby(...).max() skips NaN; all-NaN stays NaN
+        warnings.simplefilter("ignore", RuntimeWarning)
+        maxnes = np.stack([np.nanmax(nes[:, domain == d], axis=1) for d in ids], axis=1)
     real = ids >= 1                                            # .loc[:, 1:]
     t_max = counts[:, real].max(axis=1)
     primary = ids[real][np.argmax(counts[:, real], axis=1)]    # idxmax: first maximum

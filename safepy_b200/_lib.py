@@ -30,6 +30,7 @@ SIGNATURES = {
     "sb_last_error": (C.c_char_p, []),
     "sb_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "sb_ctx_destroy": (C.c_int, [_vp]),
+    "sb_current_device": (C.c_int, []),
     "sb_ctx_device": (C.c_int, [_vp]),
     "sb_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "sb_ctx_synchronize": (C.c_int, [_vp]),
@@ -139,6 +140,9 @@ class Context:
         h = _vp()
         _check(self.lib, self.lib.sb_ctx_create(int(device), C.byref(h)))
         self.h = h
+        # one context = one caller thread at a time (include/safe_b200.h): callers that share a context between
+        # threads (safepy_b200.get_context hands out one per device) serialise on this lock
+        self.lock = threading.RLock()
         if stream is not None:
             self.set_stream(stream)
 
@@ -180,6 +184,11 @@ class Context:
             self.close()
         except Exception:
             pass
+
+
+def current_device():
+    """Ordinal of the calling thread's current CUDA device (-1 without one)."""
+    return int(load_library().sb_current_device())
 
 
 def neigh_ld(n):

@@ -350,6 +350,15 @@ int sb_ctx_create(int device, sb_ctx** out) {
     SB_API_END
 }
 
+int sb_current_device(void) {
+    int device = -1;
+    if (cudaGetDevice(&device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return device;
+}
+
 int sb_ctx_destroy(sb_ctx* ctx) {
     SB_API_BEGIN
     if (ctx) {

@@ -14,7 +14,9 @@ There is no CPU fallback: the methods raise `SafeB200Error` when the CUDA librar
 """
 import contextlib
 import logging
+import threading
 import time
+import warnings
 
 import numpy as np
 
@@ -45,15 +47,41 @@ DEFAULTS = {
 }
 
 _CONTEXTS = {}
+_CONTEXTS_LOCK = threading.Lock()
 
 
 def get_context(device=-1):
-    """Process-wide libsafe_b200 context per device (created on first use)."""
-    ctx = _CONTEXTS.get(device)
-    if ctx is None or ctx.h is None:
-        ctx = _lib.Context(device)
-        _CONTEXTS[device] = ctx
+    """Process-wide libsafe_b200 context per CUDA device (created on first use).  device < 0 means the calling
+    thread's CURRENT device, resolved to its ordinal on every call (so a later torch.cuda.set_device is honoured).
+    A context serves one caller thread at a time (include/safe_b200.h); the SAFE methods hold `ctx.lock` while they
+    run, so SAFE objects on different Python threads take turns instead of sharing scratch buffers."""
+    if device is None or device < 0:
+        device = _lib.current_device()
+        if device < 0:
+            device = -1                     # no usable device: let sb_ctx_create produce the error message
+    with _CONTEXTS_LOCK:
+        ctx = _CONTEXTS.get(device)
+        if ctx is None or ctx.h is None:
+            ctx = _lib.Context(device)
+            _CONTEXTS[ctx.device] = ctx
     return ctx
+
+
+def _locked(method):
+    """Run a SAFE method under its device context's lock (re-entrant: compute_pvalues calls the branch methods)."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        try:
+            lock = getattr(get_context(self.device), "lock", None)
+        except _lib.SafeB200Error:
+            lock = None     # no device: the method validates its arguments first, then fails where it needs the GPU
+        if lock is None:
+            return method(self, *args, **kwargs)
+        with lock:
+            return method(self, *args, **kwargs)
+    return wrapper
 
 
 # ------------------------------------------------------------------------------------------------ graph -> arrays
@@ -68,41 +96,32 @@ def _node_coordinates(graph):
     return x, y
 
 
-def graph_csr(graph, weight, ctx=None):
+def graph_csr(graph, weight):
     """Symmetric CSR of the graph with the cost rule of networkx's Dijkstra: data.get(weight, 1)
-    (what safe.py:406-410 hands to all_pairs_dijkstra_path_length).  Cached on the graph object.  With a device
-    context, a graph that SAFE.load_network built from edge arrays gets its CSR from sb_graph_csr."""
-    key = (weight, graph.number_of_nodes(), graph.number_of_edges())
-    cache = graph.graph.get("_safe_b200_csr")
-    if cache is not None and cache[0] == key:
-        return cache[1]
+    (what safe.py:406-410 hands to all_pairs_dijkstra_path_length).
+
+    Rebuilt from the graph object on EVERY call, like the reference, which re-reads the edge data every time
+    define_neighborhoods runs (safe.py:406-407): safe_io.apply_network_layout / calculate_edge_lengths (and users)
+    edit 'length' / 'weight' in place, and networkx keeps no modification counter that a cache could be checked
+    against.  The walk goes straight over the adjacency dicts with C-level iterators (the rows of the adjacency ARE
+    the CSR rows, so nothing is sorted): ~0.1 s for 145k edges."""
+    import operator
+    from itertools import chain
     n = graph.number_of_nodes()
-    ne = graph.number_of_edges()
-    arrays = graph.graph.get("_safe_b200_edges")
-    if ctx is not None and weight == "length" and arrays is not None and arrays[0] == ne:
-        # the graph came from SAFE.load_network(edges=..., x=..., y=...): sort the edge arrays on the device
-        csr = _lib.build_csr(ctx, n, arrays[1][:, 0], arrays[1][:, 1], arrays[2])
-        graph.graph["_safe_b200_csr"] = (key, csr)
-        return csr
-    eu = np.empty(ne, dtype=np.int64)
-    ev = np.empty(ne, dtype=np.int64)
-    w = np.empty(ne, dtype=np.float64)
-    if weight is None:  # structure only
-        for k, (u, v) in enumerate(graph.edges()):
-            eu[k], ev[k], w[k] = u, v, 1.0
-    else:
-        for k, (u, v, c) in enumerate(graph.edges(data=weight, default=1)):
-            eu[k], ev[k], w[k] = u, v, c
-    loop = eu == ev
-    src = np.concatenate([eu, ev[~loop]])
-    dst = np.concatenate([ev, eu[~loop]])
-    ww = np.concatenate([w, w[~loop]])
-    order = np.lexsort((dst, src))
+    adj = graph._adj if hasattr(graph, "_adj") else dict(graph.adjacency())
+    deg = np.fromiter(map(len, adj.values()), dtype=np.int64, count=n)
+    nnz = int(deg.sum())
     indptr = np.zeros(n + 1, dtype=np.int64)
-    np.add.at(indptr, src + 1, 1)
-    csr = (np.cumsum(indptr), dst[order].astype(np.int32), np.ascontiguousarray(ww[order]))
-    graph.graph["_safe_b200_csr"] = (key, csr)
-    return csr
+    np.cumsum(deg, out=indptr[1:])
+    indices = np.fromiter(chain.from_iterable(adj.values()), dtype=np.int32, count=nnz)
+    if weight is None:  # structure only
+        return indptr, indices, np.ones(nnz, dtype=np.float64)
+    data = list(chain.from_iterable(map(dict.values, adj.values())))
+    try:  # every edge carries the attribute (the common case): plain item lookups
+        cost = np.fromiter(map(operator.itemgetter(weight), data), dtype=np.float64, count=nnz)
+    except KeyError:
+        cost = np.fromiter(map(operator.methodcaller("get", weight, 1), data), dtype=np.float64, count=nnz)
+    return indptr, indices, cost
 
 
 class SafeB200Mixin:
@@ -115,6 +134,7 @@ class SafeB200Mixin:
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
     # ---------------------------------------------------------------------------------- stage 1
+    @_locked
     def define_neighborhoods(self, **kwargs):
         # sticky keyword overrides, safe.py:374-381
         for k in ("node_distance_metric", "neighborhood_radius_type", "neighborhood_radius"):
@@ -137,7 +157,7 @@ class SafeB200Mixin:
         else:
             if metric == "shortpath_weighted_layout":
                 nr = self.neighborhood_radius * (np.max(x) - np.min(x))      # safe.py:404-405
-                indptr, indices, cost = graph_csr(self.graph, "length", ctx)
+                indptr, indices, cost = graph_csr(self.graph, "length")
             else:
                 nr = self.neighborhood_radius                                # safe.py:409
                 indptr, indices, cost = graph_csr(self.graph, "weight")
@@ -164,6 +184,7 @@ class SafeB200Mixin:
         self.neighborhoods = packed
 
     # ---------------------------------------------------------------------------------- stage 2
+    @_locked
     def compute_pvalues(self, **kwargs):
         if "how" in kwargs:
             self.enrichment_type = kwargs["how"]
@@ -227,6 +248,7 @@ class SafeB200Mixin:
             plan.set_node_order(order)
         return plan
 
+    @_locked
     def compute_pvalues_by_randomization(self, **kwargs):
         if kwargs:
             logging.warning("Current settings (possibly overwriting global ones):")
@@ -302,6 +324,7 @@ class SafeB200Mixin:
         self.nes = out.get("nes")
         self._tail = (out.get("nes_binary"), out["num_neighborhoods_enriched"])
 
+    @_locked
     def compute_pvalues_by_hypergeom(self, **kwargs):
         if kwargs:
             if "verbose" in kwargs:
@@ -322,6 +345,7 @@ class SafeB200Mixin:
         self._tail = (out["nes_binary"], out["num_neighborhoods_enriched"])
 
     # ---------------------------------------------------------------------------------- next call of the workflow
+    @_locked
     def define_top_attributes(self, **kwargs):
         """safe.py:610-661.  The connectivity test (connected components of the subgraph induced by the enriched
         nodes, one attribute after the other through networkx upstream) runs batched over attributes on the GPU."""
@@ -360,6 +384,7 @@ class SafeB200Mixin:
             logging.info("Number of top attributes: %d" % np.sum(self.attributes["top"]))
 
 
+    @_locked
     def define_domains(self, **kwargs):
         """safe.py:661-716.  The pairwise Jaccard distances between the nes_binary columns of the top attributes
         (the metric evaluation inside the reference's linkage(m, 'average', metric='jaccard')) are computed on the
@@ -390,7 +415,10 @@ class SafeB200Mixin:
         domain = self.attributes["domain"].values
         ids = np.unique(domain)
         counts = np.stack([self.nes_binary[:, domain == d].sum(axis=1) for d in ids], axis=1)
-        maxnes = np.stack([self.nes[:, domain == d].max(axis=1) for d in ids], axis=1)
+        # pandas' groupby(...).max() skips NaN (z-score / invalid hypergeometric cells); an all-NaN group stays NaN
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            maxnes = np.stack([np.nanmax(self.nes[:, domain == d], axis=1) for d in ids], axis=1)
         self.node2domain = pd.DataFrame(counts, columns=pd.Index(ids, name="domain"))
         real = ids >= 1
         t_max = counts[:, real].max(axis=1)
@@ -500,7 +528,8 @@ class SAFE(SafeB200Mixin):
         """Either an nx.Graph in the reference's conventions (nodes 0..N-1 with 'x', 'y'; edges with 'length'), or
         arrays: edges [E, 2], coordinates x, y and either edge lengths or adjacency weights (default 1): lengths are
         then computed on the device as safe_io.calculate_edge_lengths does (layout distance x weight,
-        safe_io.py:311-333; an edge with weight 0 gets no 'length', like upstream)."""
+        safe_io.py:311-333; an edge with weight 0 gets no 'length', like upstream).  The graph object is the single
+        source of truth afterwards: define_neighborhoods re-reads its edge data on every call."""
         import networkx as nx
         if "node_key_attribute" in kwargs:
             self.node_key_attribute = kwargs["node_key_attribute"]
@@ -518,13 +547,6 @@ class SAFE(SafeB200Mixin):
                 length = np.asarray(length, dtype=np.float64)
                 graph.add_edges_from((int(u), int(v), {} if w != w else {"length": float(w)})
                                      for (u, v), w in zip(edges, length))
-                lo, hi = np.minimum(edges[:, 0], edges[:, 1]), np.maximum(edges[:, 0], edges[:, 1])
-                if len(np.unique(lo * x.shape[0] + hi)) == len(edges):
-                    # no repeated edge (nx.Graph would keep only the last): define_neighborhoods can build its CSR
-                    # on the device from these arrays instead of walking the graph object edge by edge.
-                    # An edge without 'length' costs Dijkstra's default 1 (safe.py:406-407).
-                    graph.graph["_safe_b200_edges"] = (graph.number_of_edges(), edges.copy(),
-                                                       np.where(np.isnan(length), 1.0, length))
         self.graph = graph
 
     def load_attributes(self, attribute_file=None, **kwargs):

@@ -16,6 +16,28 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` on the GPU box)")
 
 
+def _gpu_visible():
+    try:
+        from safepy_b200 import _lib
+        return _lib.current_device() >= 0
+    except Exception:  # noqa: BLE001  (library not built, no driver, ...)
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest` on a box without a B200 skips the gpu-marked tests instead of drowning host-side regressions
+    in CUDA errors.  `pytest -m gpu` (what the GPU box runs) or SAFE_B200_REQUIRE_GPU=1 keeps them loud: there the
+    tests must FAIL, not skip, when the CUDA path is unavailable."""
+    expr = config.getoption("-m") or ""
+    loud = os.environ.get("SAFE_B200_REQUIRE_GPU") == "1" or ("gpu" in expr and "not gpu" not in expr)
+    if loud or _gpu_visible():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible (run `pytest -m gpu` on a B200 to make this an error)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name)) as z:
         return {k: z[k] for k in z.files}

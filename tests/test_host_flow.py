@@ -163,6 +163,32 @@ def test_define_domains_flow(monkeypatch):
     assert np.array_equal(sf.attributes["domain"].values, ref_domain)
 
 
+def test_define_domains_primary_nes_skips_nan(monkeypatch):
+    """safe.py:687-701 takes the per-domain maximum with pandas' groupby(...).max(), which skips NaN (z-score scores
+    and invalid hypergeometric cells are NaN); an all-NaN group stays NaN.  Checked against pandas itself."""
+    g = load_golden("domains_small.npz")
+    monkeypatch.setattr(safe_mod, "get_context", lambda device=-1: None)
+    monkeypatch.setattr(_lib, "jaccard", lambda ctx, member, cols: orc.jaccard_condensed(member, cols))
+    nes = g["nes"].copy()
+    rng = np.random.default_rng(3)
+    nes[rng.uniform(size=nes.shape) < 0.3] = np.nan
+    nes[5, :] = np.nan                                                  # a node without any finite NES
+    m = nes.shape[1]
+    sf = SAFE(verbose=False)
+    sf.nes, sf.nes_binary = nes, g["nes_binary"]
+    sf.attributes = pd.DataFrame({"id": np.arange(m), "name": [str(j) for j in range(m)], "top": g["top"]})
+    sf.define_domains()
+    domain = sf.attributes["domain"].values
+    ref = pd.DataFrame(nes.T, index=pd.Index(domain, name="domain")).groupby(level="domain").max().T
+    primary = sf.node2domain["primary_domain"].values
+    want = np.array([ref.loc[i, d] for i, d in enumerate(primary)])
+    assert np.array_equal(sf.node2domain["primary_nes"].values, want, equal_nan=True)
+    assert np.isnan(sf.node2domain["primary_nes"].values[5])
+    assert np.isfinite(want).sum() > 0.9 * len(want)
+    _, _, _, _, oracle_nes = orc.define_domains(nes, g["nes_binary"], g["top"], sf.attribute_distance_threshold)
+    assert np.array_equal(oracle_nes, want, equal_nan=True)
+
+
 def test_define_top_attributes_flow(monkeypatch):
     g = load_golden("top_small.npz")
     n, m = g["nes_binary"].shape

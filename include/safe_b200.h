@@ -147,6 +147,15 @@ int sb_enrich_perm_counts(sb_enrich* e, int score_type, int engine, const int32_
                           uint32_t* counts_neg_host, uint32_t* counts_pos_host);
 int sb_enrich_perm_counts_dev(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_dev,
                               int64_t num_perm, uint32_t* counts_neg_dev, uint32_t* counts_pos_dev);
+/* The same counts ACCUMULATED into ONE word per cell, (counts_pos << 16) | counts_neg -- the array a permutation-
+ * sharded run sums over the ranks with a single all-reduce (the reduction safe.py:518-519 does with np.sum over its
+ * worker results; half the bytes of the two separate arrays).  The caller zeroes the buffer and keeps the number of
+ * permutations summed into a word (over all calls and ranks) below 65536.  sb_counts_unpack_dev STORES the two
+ * halves into separate arrays ([cells] each), e.g. after the all-reduce. */
+int sb_enrich_perm_counts_packed_dev(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_dev,
+                                     int64_t num_perm, uint32_t* counts_packed_dev);
+int sb_counts_unpack_dev(sb_ctx* ctx, const uint32_t* counts_packed_dev, int64_t cells, uint32_t* counts_neg_dev,
+                         uint32_t* counts_pos_dev);
 
 /* statistics of the last perm_counts call on this plan:
  * [0] comparisons decided by the GEMM, [1] comparisons sent to the exact fix-up, [2] A tiles stored,

@@ -216,6 +216,26 @@ def hypergeom_pvalues(neighborhoods, node2attribute):
     return pvalues_pos, nes
 
 
+def hypergeom_pvalues_block(neighborhood_rows, node2attribute, cols):
+    """The cells [rows, cols] of hypergeom_pvalues for a block of source rows (neighborhood_rows = those rows of the
+    neighborhood matrix, [R, N]) and attribute columns `cols`: the same statements (safe.py:573-608), with the
+    node-level quantities (which nodes carry data, n) still taken from the WHOLE attribute matrix as upstream.
+    Lets the full-size configurations be checked on a sample -- scipy's hypergeom.sf runs at ~6e4 cells/s."""
+    nodes_not_nan = np.any(~np.isnan(node2attribute), axis=1)
+    n = np.sum(nodes_not_nan)
+    sub = node2attribute[:, cols]
+    r, c = neighborhood_rows.shape[0], sub.shape[1]
+    N = np.zeros([r, c]) + n
+    N_in_group = np.tile(np.nansum(sub, axis=0), (r, 1))
+    neighborhood_size = np.dot(neighborhood_rows, nodes_not_nan.astype(int))[:, np.newaxis]
+    N_in_neighborhood = np.tile(neighborhood_size, (1, c))
+    N_in_neighborhood_in_group = np.dot(neighborhood_rows, np.where(~np.isnan(sub), sub, 0))
+    pvalues_pos = hypergeom.sf(N_in_neighborhood_in_group - 1, N, N_in_group, N_in_neighborhood)
+    with np.errstate(divide="ignore"):
+        nes = -np.log10(pvalues_pos)
+    return pvalues_pos, nes
+
+
 def nes_binary(nes, enrichment_threshold):
     """safe.py:468-470."""
     idx = ~np.isnan(nes)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "sb_enrich_score_dev": (C.c_int, [_vp, C.c_int, _vp]),
     "sb_enrich_perm_counts": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
     "sb_enrich_perm_counts_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp, _vp]),
+    "sb_enrich_perm_counts_packed_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _i64, _vp]),
+    "sb_counts_unpack_dev": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "sb_enrich_stats": (C.c_int, [_vp, _vp]),
     "sb_enrich_hypergeom": (C.c_int, [_vp, _vp, _vp]),
     "sb_enrich_hypergeom_dev": (C.c_int, [_vp, _vp, _vp]),
@@ -368,6 +370,17 @@ class Enrichment:
                                                             _vp(int(perm_dev)), int(num_perm), _vp(int(cneg_dev)),
                                                             _vp(int(cpos_dev))))
 
+    def perm_counts_packed_dev(self, perm_dev, num_perm, packed_dev, score_type="sum", engine="auto"):
+        """Counts added to one uint32 word per cell, pos << 16 | neg (device array [n, m], zeroed by the caller)."""
+        _check(self.lib, self.lib.sb_enrich_perm_counts_packed_dev(self.h, SCORE_TYPES[score_type], ENGINES[engine],
+                                                                   _vp(int(perm_dev)), int(num_perm),
+                                                                   _vp(int(packed_dev))))
+
+    def unpack_counts_dev(self, packed_dev, cneg_dev, cpos_dev):
+        """packed [n, m] -> counts_neg, counts_pos (stored, device arrays)."""
+        _check(self.lib, self.lib.sb_counts_unpack_dev(self.ctx.h, _vp(int(packed_dev)), self.n * self.m,
+                                                       _vp(int(cneg_dev)), _vp(int(cpos_dev))))
+
     def attr_summary(self):
         """(NaNs per attribute column, number of values that are neither 0, 1 nor NaN) -- safe.py:453-458."""
         nans = np.empty(self.m, dtype=np.int64)
@@ -455,6 +468,11 @@ class Enrichment:
         nes = np.empty((self.n, self.m), dtype=np.float64) if want_nes else None
         _check(self.lib, self.lib.sb_enrich_hypergeom(self.h, _ptr(pv), _ptr(nes)))
         return pv, nes
+
+    def hypergeom_dev(self, pvalues_dev, nes_dev):
+        """Hypergeometric p-values / NES into device arrays ([n, m] fp64 each; either may be 0 = not wanted)."""
+        _check(self.lib, self.lib.sb_enrich_hypergeom_dev(self.h, _vp(int(pvalues_dev)) if pvalues_dev else None,
+                                                          _vp(int(nes_dev)) if nes_dev else None))
 
     def close(self):
         if getattr(self, "h", None):

@@ -99,7 +99,8 @@ struct sb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers[SB_K_CLASSES];
     // grow-only scratch shared by all plans of this context (used only inside one call at a time):
     // gathered operand tiles, fix-up list, packed count accumulators
-    sb::DevBuf<int8_t> ws_bcat;
+    sb::DevBuf<int8_t> ws_bcat;      // pre-gathered operand tiles (M < 64 only)
+    sb::DevBuf<int32_t> ws_src;      // source-row table of the batch in flight (in-kernel row gather)
     sb::DevBuf<uint64_t> ws_flag_ij;
     sb::DevBuf<uint32_t> ws_flag_p;
     sb::DevBuf<uint32_t> ws_cpk;

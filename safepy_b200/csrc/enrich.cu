@@ -121,8 +121,8 @@ __device__ __forceinline__ double score_one(const int64_t* __restrict__ row_ptr,
 template <class T, bool ZS>
 __global__ void __launch_bounds__(128) k_score(const int64_t* __restrict__ row_ptr,
                                                const int32_t* __restrict__ col_idx, const T* __restrict__ b,
-                                               int64_t n, int64_t m, double* __restrict__ out) {
-    const int64_t i = blockIdx.x;
+                                               int64_t n, int64_t m, int64_t row0, double* __restrict__ out) {
+    const int64_t i = row0 + blockIdx.x;
     const int64_t j = blockIdx.y * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= m) return;
     out[i * m + j] = score_one<T, ZS>(row_ptr, col_idx, b, nullptr, n, m, i, 0, j);
@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ 
                                                     const int32_t* __restrict__ col_idx, const T* __restrict__ b,
                                                     const int32_t* __restrict__ perm, int64_t n, int64_t m,
                                                     int64_t ncols, const double* __restrict__ s0,
-                                                    uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos) {
+                                                    uint32_t* __restrict__ cneg, uint32_t* __restrict__ cpos,
+                                                    uint32_t* __restrict__ packed) {
     const int64_t i = blockIdx.x;
     const int64_t c = blockIdx.y * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (c >= ncols) return;
@@ -141,6 +142,11 @@ __global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ 
     const double s = score_one<T, ZS>(row_ptr, col_idx, b, perm, n, m, i, p, j);
     const double o = s0[i * m + j];
     // safe_extras.py:65-66 (NaN compares false on both sides)
+    if (packed) {
+        const uint32_t inc = (s <= o ? 1u : 0u) + (s >= o ? 0x10000u : 0u);
+        if (inc) atomicAdd(&packed[i * m + j], inc);
+        return;
+    }
     if (s <= o) atomicAdd(&cneg[i * m + j], 1u);
     if (s >= o) atomicAdd(&cpos[i * m + j], 1u);
 }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
                                                int64_t m, const uint64_t* __restrict__ flag_ij,
                                                const uint32_t* __restrict__ flag_p,
                                                unsigned int total, uint32_t* __restrict__ cneg,
-                                               uint32_t* __restrict__ cpos) {
+                                               uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
     const int lane = threadIdx.x & 31;
     unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int step = (gridDim.x * blockDim.x) >> 5;
@@ -180,8 +186,13 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
             so += __shfl_xor_sync(0xffffffffu, so, o);
         }
         if (lane == 0) {
-            if (sp <= so) atomicAdd(&cneg[i * m + j], 1u);
-            if (sp >= so) atomicAdd(&cpos[i * m + j], 1u);
+            if (packed) {
+                const uint32_t inc = (sp <= so ? 1u : 0u) + (sp >= so ? 0x10000u : 0u);
+                if (inc) atomicAdd(&packed[i * m + j], inc);
+            } else {
+                if (sp <= so) atomicAdd(&cneg[i * m + j], 1u);
+                if (sp >= so) atomicAdd(&cpos[i * m + j], 1u);
+            }
         }
     }
 }
@@ -305,6 +316,18 @@ __global__ void k_sum_i32(const int32_t* __restrict__ v, int64_t n, unsigned lon
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
 }
 
+// packed word per cell (pos << 16 | neg) -> the two count arrays (stored, not added)
+__global__ void k_unpack_store(const uint32_t* __restrict__ packed, int64_t cells, uint32_t* __restrict__ cneg,
+                               uint32_t* __restrict__ cpos) {
+    int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < cells; i += step) {
+        const uint32_t v = packed[i];
+        cneg[i] = v & 0xffffu;
+        cpos[i] = v >> 16;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static void build_csr(sb_enrich* e) {
     sb_ctx* ctx = e->ctx;
@@ -327,26 +350,34 @@ static void build_csr(sb_enrich* e) {
     SB_LAUNCH_CHECK(ctx);
 }
 
-void enrich_score_into(sb_enrich* e, int score_type, double* out_dev) {
+void enrich_score_into(sb_enrich* e, int score_type, double* out_dev) { enrich_score_rows(e, score_type, out_dev, 0, e->n); }
+
+void enrich_score_rows(sb_enrich* e, int score_type, double* out_dev, int64_t row0, int64_t row1) {
     sb_ctx* ctx = e->ctx;
     SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
              score_type);
-    dim3 grid(static_cast<unsigned>(e->n), static_cast<unsigned>(sb_ceil_div(e->m, 128)));
+    SB_CHECK(row0 >= 0 && row0 <= row1 && row1 <= e->n, "score rows [%lld, %lld) out of range", (long long)row0,
+             (long long)row1);
+    if (row1 == row0) return;
+    dim3 grid(static_cast<unsigned>(row1 - row0), static_cast<unsigned>(sb_ceil_div(e->m, 128)));
     SB_CHECK(grid.y <= 65535, "attribute count %lld too large for one launch", (long long)e->m);
     const bool zs = score_type == SB_SCORE_ZSCORE;
     KernelTimer kt(ctx, SB_K_SCORE);
     if (e->dtype == SB_F32) {
         const float* b = static_cast<const float*>(e->b);
         if (zs)
-            k_score<float, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+            k_score<float, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, row0,
+                                                                out_dev);
         else
-            k_score<float, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+            k_score<float, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, row0,
+                                                                 out_dev);
     } else {
         const double* b = static_cast<const double*>(e->b);
         if (zs)
-            k_score<double, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, out_dev);
+            k_score<double, true><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, row0,
+                                                                 out_dev);
         else
-            k_score<double, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m,
+            k_score<double, false><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, b, e->n, e->m, row0,
                                                                   out_dev);
     }
     SB_LAUNCH_CHECK(ctx);
@@ -370,7 +401,7 @@ const double* enrich_observed(sb_enrich* e, int score_type) {
 }
 
 void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg,
-                      uint32_t* cpos) {
+                      uint32_t* cpos, uint32_t* packed) {
     sb_ctx* ctx = e->ctx;
     const double* s0 = enrich_observed(e, score_type);
     const bool zs = score_type == SB_SCORE_ZSCORE;
@@ -384,7 +415,7 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
         const int32_t* perm = perm_dev + p0 * e->n;
 #define SB_LAUNCH_PC(T, Z)                                                                                     \
     k_perm_count<T, Z><<<grid, 128, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const T*>(e->b), \
-                                                      perm, e->n, e->m, ncols, s0, cneg, cpos)
+                                                      perm, e->n, e->m, ncols, s0, cneg, cpos, packed)
         if (e->dtype == SB_F32) {
             if (zs)
                 SB_LAUNCH_PC(float, true);
@@ -436,7 +467,7 @@ static const void* transposed_b(sb_enrich* e) {
 }
 
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
-                 unsigned int count, uint32_t* cneg, uint32_t* cpos) {
+                 unsigned int count, uint32_t* cneg, uint32_t* cpos, uint32_t* packed) {
     sb_ctx* ctx = e->ctx;
     const void* bt = transposed_b(e);
     const unsigned blocks = static_cast<unsigned>(
@@ -444,10 +475,12 @@ void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij,
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
         k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt),
-                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos);
+                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos,
+                                                        packed);
     else
         k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt),
-                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos);
+                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos,
+                                                         packed);
     SB_LAUNCH_CHECK(ctx);
 }
 
@@ -585,6 +618,31 @@ int sb_enrich_score_dev(sb_enrich* e, int score_type, double* out_dev) {
     SB_API_END
 }
 
+int sb_enrich_observed_rows_dev(sb_enrich* e, int score_type, int64_t row0, int64_t row1, double** scores_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e && scores_dev, "sb_enrich_observed_rows_dev: NULL argument");
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    e->ctx->bind();
+    DevBuf<double>& buf = score_type == SB_SCORE_SUM ? e->s0_sum : e->s0_z;
+    buf.reserve(static_cast<size_t>(e->n) * e->m);
+    enrich_score_rows(e, score_type, buf.p, row0, row1);
+    *scores_dev = buf.p;
+    SB_API_END
+}
+
+int sb_enrich_observed_set_ready(sb_enrich* e, int score_type) {
+    SB_API_BEGIN
+    SB_CHECK(e, "sb_enrich_observed_set_ready: NULL handle");
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    DevBuf<double>& buf = score_type == SB_SCORE_SUM ? e->s0_sum : e->s0_z;
+    SB_CHECK(buf.p && buf.n >= static_cast<size_t>(e->n) * e->m,
+             "sb_enrich_observed_set_ready: call sb_enrich_observed_rows_dev first");
+    (score_type == SB_SCORE_SUM ? e->have_s0_sum : e->have_s0_z) = true;
+    SB_API_END
+}
+
 int sb_enrich_score(sb_enrich* e, int score_type, double* out_host) {
     SB_API_BEGIN
     SB_CHECK(e && out_host, "sb_enrich_score: NULL argument");
@@ -612,6 +670,41 @@ int sb_enrich_perm_counts_dev(sb_enrich* e, int score_type, int engine, const in
         tc_perm_counts(e, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
     else
         simt_perm_counts(e, score_type, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
+    SB_API_END
+}
+
+int sb_enrich_perm_counts_packed_dev(sb_enrich* e, int score_type, int engine, const int32_t* perm_rows_dev,
+                                     int64_t num_perm, uint32_t* counts_packed_dev) {
+    SB_API_BEGIN
+    SB_CHECK(e && perm_rows_dev && counts_packed_dev, "sb_enrich_perm_counts_packed_dev: NULL argument");
+    SB_CHECK(num_perm >= 0 && num_perm < 65536,
+             "sb_enrich_perm_counts_packed_dev: num_perm must be in [0, 65536) (16-bit fields)");
+    SB_CHECK(score_type == SB_SCORE_SUM || score_type == SB_SCORE_ZSCORE, "unknown neighborhood_score_type %d",
+             score_type);
+    SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
+             engine);
+    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
+             "the tensor-core engine implements neighborhood_score_type 'sum' only");
+    e->ctx->bind();
+    if (num_perm == 0) return 0;
+    const bool use_tc = engine == SB_ENGINE_TC || (engine == SB_ENGINE_AUTO && score_type == SB_SCORE_SUM);
+    if (use_tc)
+        tc_perm_counts(e, perm_rows_dev, num_perm, nullptr, nullptr, counts_packed_dev);
+    else
+        simt_perm_counts(e, score_type, perm_rows_dev, num_perm, nullptr, nullptr, counts_packed_dev);
+    SB_API_END
+}
+
+int sb_counts_unpack_dev(sb_ctx* ctx, const uint32_t* counts_packed_dev, int64_t cells, uint32_t* counts_neg_dev,
+                         uint32_t* counts_pos_dev) {
+    SB_API_BEGIN
+    SB_CHECK(ctx && counts_packed_dev && counts_neg_dev && counts_pos_dev && cells >= 0,
+             "sb_counts_unpack_dev: bad argument");
+    ctx->bind();
+    if (cells == 0) return 0;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(cells, 256), ctx->num_sms * 16));
+    k_unpack_store<<<blocks, 256, 0, ctx->stream>>>(counts_packed_dev, cells, counts_neg_dev, counts_pos_dev);
+    SB_LAUNCH_CHECK(ctx);
     SB_API_END
 }
 

@@ -35,6 +35,8 @@ struct sb_enrich {
 
     // streaming null (sb_enrich_null_*, finalize.cu): the two count arrays stay on the device between calls
     sb::DevBuf<uint32_t> null_cnt;   // [2][n * m]: neg, pos
+    sb::DevBuf<uint32_t> null_pk;    // [n * m]: pos << 16 | neg of the permutations not yet moved into null_cnt
+    int64_t null_pk_perms = 0;       // permutations summed into null_pk (16-bit fields: kept below 60000)
     sb::DevBuf<int32_t> null_perm;   // staging for one piece of permutation indices
     int null_score = -1;             // -1: no null open
     int null_engine = 0;
@@ -46,15 +48,24 @@ namespace sb {
 
 // enrich.cu
 void enrich_score_into(sb_enrich* e, int score_type, double* out_dev);
+// rows [row0, row1) only (out_dev is the whole [n x m] array)
+void enrich_score_rows(sb_enrich* e, int score_type, double* out_dev, int64_t row0, int64_t row1);
 const double* enrich_observed(sb_enrich* e, int score_type);
+// counts are ADDED to cneg / cpos, or (cneg == cpos == nullptr) to one packed word per cell, pos << 16 | neg
 void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg,
-                      uint32_t* cpos);
+                      uint32_t* cpos, uint32_t* packed = nullptr);
 // exact fp64 re-evaluation of flagged (i, j, p) comparisons; entries are (i << 32 | j) , p pairs
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
-                 unsigned int count, uint32_t* cneg, uint32_t* cpos);
+                 unsigned int count, uint32_t* cneg, uint32_t* cpos, uint32_t* packed = nullptr);
 
 // gemm_tc.cu
 void tc_plan_destroy(TcPlan* p);
-void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos);
+// cneg += packed & 0xffff, cpos += packed >> 16, packed = 0
+void unpack_add_counts(sb_ctx* ctx, uint32_t* packed, int64_t cells, uint32_t* cneg, uint32_t* cpos);
+// finalize.cu: permutations of an open streaming null (sb_enrich_null_*), counted into the packed accumulator
+void null_count_dev(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm);
+void null_flush(sb_enrich* e);
+void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
+                    uint32_t* packed = nullptr);
 
 }  // namespace sb

@@ -13,9 +13,13 @@
 // block of 256 rows of A (128 per CTA) and multiplies it with a gathered-operand tile whose 64*D columns are split
 // between the two CTAs' shared memories, so every byte of the gathered operand that leaves L2 feeds 256 rows.
 // A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row.  The masks ride along with the
-// gathered tiles through the smem ring, expander warps turn them into int8 0/1 in TMEM, and the MMA takes its A
-// operand from TMEM.  Gathered tiles are stored in HBM in the tensor core's canonical no-swizzle MN-major
-// core-matrix order, one half per CTA, so one 1-D bulk async copy (TMA engine, UBLKCP) lands a half tile MMA-ready.
+// operand tiles through the smem ring, expander warps turn them into int8 0/1 in TMEM, and the MMA takes its A
+// operand from TMEM.  The permuted operand B_p = B[perm_p] never exists in memory: two gather warps per CTA fetch
+// the 64 source rows of every k-tile straight from the digit records (one 64*D-byte record per (node, column
+// group), L2-resident: a column group's slab is N * 64 * D bytes) with 16-byte async copies (LDGSTS) whose
+// shared-memory destinations are the tensor core's canonical no-swizzle MN-major core-matrix positions, so the
+// tile lands MMA-ready.  (M < 64 packs several permutations into one 64-column slot byte by byte; those tiny
+// problems keep the pre-gathered tile + bulk-copy path.)
 #include <algorithm>
 #include <climits>
 #include <vector>
@@ -40,8 +44,11 @@ constexpr int TC_EXP_WARPS = 4;          // one per TMEM lane quarter
 // therefore sit above the epilogue and expander warps.
 constexpr int TC_EXP_WARP0 = TC_EPI_WARPS;
 constexpr int TC_PROD_WARP = TC_EPI_WARPS + TC_EXP_WARPS;
-constexpr int TC_MMA_WARP = TC_PROD_WARP + 1;
-constexpr int TC_THREADS = (TC_EPI_WARPS + TC_EXP_WARPS + 2) * 32;
+constexpr int TC_GATHER_WARPS = 2;       // row-gather warps (LDGSTS), k-tiles 2g and 2g+1 of every fill each
+constexpr int TC_GATHER_WARP0 = TC_PROD_WARP + 1;
+constexpr int TC_MMA_WARP = TC_GATHER_WARP0 + TC_GATHER_WARPS;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;  // 16 warps x 128 registers = the whole register file
+static_assert(TC_GATHER_WARPS * 2 == TC_TPS, "each gather warp owns two k-tiles of a fill");
 // TMEM columns: accumulator buffer b at [256 b, 256 b + 64 D); A slot s (TC_APS tiles x 16 columns) in the gaps
 // [192, 256) and [448, 512)
 __host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return (s >> 1) * 256u + 192u + (s & 1u) * 32u; }
@@ -58,9 +65,12 @@ struct GemmParams {
     const uint64_t* a_bits;   // [n_tiles / TPS][2 (CTA rank)][TPS][128]: bit k of a word = A[row][64 kt + k]
     const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
-    const int8_t* bcat;       // [slot][kt][2 (CTA rank)][64 x 32*D]
+    const int8_t* bcat;       // pre-gathered tiles (M < 64, self-tests): [slot][kt][2 (CTA rank)][64 x 32*D]
+    const int8_t* dig;        // GATHER: digit records [n_cg][n][64*D] (plane d of column c at byte d*64 + c)
+    const int32_t* src_idx;   // GATHER: [slot][n_kt*64] source row of internal position t (-1: zero row)
     int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;  // n_rb: blocks of TC_PROWS rows
     int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
+    int32_t rb0;              // first row block of this launch (units cover row blocks [rb0, rb0 + n_rb))
     unsigned int* unit_counter;  // dynamic scheduler (zeroed before the launch)
     int32_t mode;
     int64_t n, m, mpad;
@@ -159,8 +169,9 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb,
 // sempty barriers through shared::cluster; the leader's tcgen05.commit multicasts to the aempty / empty / tfull
 // barriers of both CTAs.
 // Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
-template <int D, int KIND, bool SMALL_M, bool PROF>
+template <int D, int KIND, bool SMALL_M, bool PROF, bool GATHER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
+    static_assert(!(GATHER && SMALL_M), "the in-kernel row gather needs whole 64-column groups");
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sB = smem;
@@ -185,7 +196,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            mbar_init(&full[s], 1);
+            // producer's expect_tx arrive (+ one arrival per gathering thread when its cp.async have landed)
+            mbar_init(&full[s], GATHER ? 1 + TC_GATHER_WARPS * 32 : 1);
             mbar_init(&empty[s], 1 + TC_EXP_WARPS);  // MMA commit + own expander warps (done reading the bit tiles)
         }
         for (int b = 0; b < 2; ++b) {
@@ -194,8 +206,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
         }
         for (int s = 0; s < TC_SCHED; ++s) {
             mbar_init(&sfull[s], 1);
-            // consumers: leader MMA + peer producer + epilogue and expander warps of both CTAs
-            mbar_init(&sempty[s], 2 * (TC_EPI_WARPS + TC_EXP_WARPS) + 2);
+            // consumers: leader MMA + peer producer + epilogue, expander (and gather) warps of both CTAs
+            mbar_init(&sempty[s], 2 * (TC_EPI_WARPS + TC_EXP_WARPS + (GATHER ? TC_GATHER_WARPS : 0)) + 2);
         }
         for (int s = 0; s < TC_ASLOTS; ++s) {
             mbar_init(&afull[s], 2 * TC_EXP_WARPS);
@@ -248,6 +260,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 if (!stop) {
                     if (lane == 0) next_u = atomicAdd(p.unit_counter, 1u);  // consumed at the top of the next iteration
                     decode_unit(p, u, rb, cg, q0, q1);
+                    rb += p.rb0;
                     t0 = p.tile_ptr[rb];
                     nfills = (p.tile_ptr[rb + 1] - t0) / C::TPS;
                 } else {
@@ -279,8 +292,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 if (rb < 0) break;
             }
             const int nk = nfills * C::TPS;
-            for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
-            __syncwarp();
+            if (!GATHER) {  // (with the in-kernel gather the k-tile ids are the gather warps' business)
+                for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
+                __syncwarp();
+            }
             // this CTA's half of every gathered tile and its own rows of the A bit tiles
             const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * (2 * C::HALF_B) + rank * C::HALF_B;
             const uint64_t* const a_unit =
@@ -292,7 +307,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 #pragma unroll
                     for (int t = 0; t < C::TPS; ++t) {
                         const int i = f * C::TPS + t;
-                        kts[t] = i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i];
+                        kts[t] = GATHER ? 0 : (i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i]);
                     }
                     TC_TIMED(KIND, pt_wait, mbar_wait(&empty[stage], phase ^ 1u));
                     if (PROF) ++pt_fills;
@@ -300,12 +315,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                         if (p.dbg & 2) {
                             mbar_arrive(&full[stage]);
                         } else {
-                            mbar_expect_tx(&full[stage], C::STAGE);
+                            mbar_expect_tx(&full[stage], GATHER ? C::STAGE_A : C::STAGE);
                             uint8_t* const st = sB + stage * C::STAGE;
+                            if (!GATHER) {
 #pragma unroll
-                            for (int t = 0; t < C::TPS; ++t)
-                                bulk_g2s(st + t * C::HALF_B, b_q + static_cast<size_t>(kts[t]) * (2 * C::HALF_B),
-                                         C::HALF_B, &full[stage]);
+                                for (int t = 0; t < C::TPS; ++t)
+                                    bulk_g2s(st + t * C::HALF_B, b_q + static_cast<size_t>(kts[t]) * (2 * C::HALF_B),
+                                             C::HALF_B, &full[stage]);
+                            }
                             bulk_g2s(st + C::STAGE_B, a_unit + static_cast<size_t>(f) * (2 * C::TPS * TC_ROWS),
                                      C::STAGE_A, &full[stage]);
                         }
@@ -325,6 +342,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 1), pt_wait);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), pt_fills);
             if (p.dbg & 4) p.prof[10] = static_cast<long long>(p.q_total) * (p.tile_ptr[1] / C::TPS);  // probe: n_rb = 1
+        }
+    } else if (warp >= TC_GATHER_WARP0 && warp < TC_MMA_WARP) {
+        // ------------------------------------------------------------ row gather: digit records -> MMA-ready tiles
+        // Gather warp g fills k-tiles 2g and 2g+1 of every stage.  One LDGSTS of the warp moves 16 source rows x two
+        // 16-byte chunks: lanes 0..15 / 16..31 take the even / odd chunk of a 32-byte piece of rows 16 rg + (lane & 15),
+        // so every 32-byte sector that leaves L2 is used whole, and the eight lanes of a quarter warp write eight
+        // consecutive 16-byte core-matrix rows (conflict-free).  The source row indices of fill i+1 are loaded
+        // before the copies of fill i are issued, so their L2 latency never sits between two stages.
+        if (GATHER) {
+            constexpr int HC = 2 * D;    // 16-byte chunks per row of this CTA's half tile
+            constexpr int REC = 64 * D;  // bytes of one (node, column group) record
+            const int gw = warp - TC_GATHER_WARP0;
+            const int klo = lane & 15, chi = lane >> 4;
+            // chunk (k = 16 rg + klo, c = 2 cp + chi) of a half tile sits at 16 * ((k >> 3) * HC * 8 + c * 8 + (k & 7))
+            const uint32_t lane_off = static_cast<uint32_t>(((klo >> 3) * HC * 8 + chi * 8 + (klo & 7)) * 16);
+            int32_t* const my_kt = s_kt + gw * (TC_KT_SMEM / TC_GATHER_WARPS);
+            constexpr int MY_KT = TC_KT_SMEM / TC_GATHER_WARPS;
+            const size_t src_stride = static_cast<size_t>(p.n_kt) * TC_KT;
+            uint32_t stage = 0, phase = 0, uit = 0;
+            while (true) {
+                const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
+                mbar_wait_cluster(&sfull[sl], spar);
+                const int rb = s_unit[sl].rb, cg = s_unit[sl].cg, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1,
+                          t0 = s_unit[sl].t0, nfills = s_unit[sl].nfills;
+                __syncwarp();
+                if (lane == 0) {
+                    if (leader)
+                        mbar_arrive(&sempty[sl]);
+                    else
+                        mbar_arrive_cluster(ld_sempty + sl * 8);
+                }
+                ++uit;
+                if (rb < 0) break;
+                if (p.dbg & 4) continue;
+                // this warp's k-tile ids of the unit: entry 2 f + t = k-tile of (fill f, tile 2 gw + t)
+                for (int i = lane; i < min(2 * nfills, MY_KT); i += 32)
+                    my_kt[i] = p.tile_kt[t0 + (i >> 1) * C::TPS + gw * 2 + (i & 1)];
+                __syncwarp();
+                const int8_t* const dcg =
+                    p.dig + static_cast<size_t>(cg) * p.n * REC + rank * (REC / 2) + chi * 16;
+                auto load_idx = [&](int q, int f, int32_t (&dst)[2][4]) {
+                    const int32_t* const sq = p.src_idx + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * src_stride);
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+                        const int i = 2 * f + t;
+                        const int kt = i < MY_KT ? my_kt[i] : p.tile_kt[t0 + f * C::TPS + gw * 2 + t];
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) dst[t][rg] = __ldg(sq + static_cast<size_t>(kt) * TC_KT + rg * 16 + klo);
+                    }
+                };
+                int32_t nxt[2][4];
+                int q = q0, f = 0;
+                load_idx(q, f, nxt);
+                const int total = (q1 - q0) * nfills;
+                for (int it = 0; it < total; ++it) {
+                    int32_t cur[2][4];
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) cur[t][rg] = nxt[t][rg];
+                    if (++f == nfills) {
+                        f = 0;
+                        ++q;
+                    }
+                    if (it + 1 < total) load_idx(q, f, nxt);
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    const uint32_t sbase = smem_u32(sB + stage * C::STAGE) + lane_off;
+#pragma unroll
+                    for (int t = 0; t < 2; ++t) {
+#pragma unroll
+                        for (int rg = 0; rg < 4; ++rg) {
+                            const int32_t src = cur[t][rg];
+                            const int8_t* const g = dcg + static_cast<size_t>(src < 0 ? 0 : src) * REC;
+                            const uint32_t nbytes = src < 0 ? 0u : 16u;
+                            const uint32_t dst = sbase + static_cast<uint32_t>((gw * 2 + t) * C::HALF_B +
+                                                                               rg * 2 * HC * 8 * 16);
+#pragma unroll
+                            for (int cp = 0; cp < D; ++cp) cp_async16(dst + cp * 16 * 16, g + cp * 32, nbytes);
+                        }
+                    }
+                    cp_async_mbar_arrive_noinc(&full[stage]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
         }
     } else if (warp >= TC_EXP_WARP0 && warp < TC_PROD_WARP) {
         // ------------------------------------------------------------ A expanders: bits -> int8 0/1 in TMEM
@@ -367,6 +471,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 for (int f = 0; f < nfills; ++f) {
                     // the bit tiles of this fill arrive in the smem stage together with the gathered operand
                     TC_TIMED(KIND, xt_full, mbar_wait(&full[stage], phase));
+                    // the gathered rows were written by LDGSTS (generic proxy); the MMA reads them through the async
+                    // proxy and is released by this warp's afull arrive below
+                    if (GATHER) fence_proxy_async_smem();
                     const uint64_t* const sbits =
                         reinterpret_cast<const uint64_t*>(sB + stage * C::STAGE + C::STAGE_B) + r;
                     uint64_t w[C::TPS];
@@ -837,8 +944,11 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     if (bad) atomicOr(flags, 1);
 }
 
-// fixed-point digits: q = rint(v * 2^shift[j]) as D balanced base-256 int8 digits, plane d at digits + d*n*mpad
-template <class T, int D>
+// fixed-point digits: q = rint(v * 2^shift[j]) as D balanced base-256 int8 digits.
+// RECORDS = false (M < 64): plane d at digits + d*n*mpad.
+// RECORDS = true: one 64*D-byte record per (column group, node), digits[(cg * n + r) * 64 D + d * 64 + (j & 63)] --
+// the unit the GEMM's gather warps fetch (a CTA of a pair takes one half of the record).
+template <class T, int D, bool RECORDS>
 __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_t mpad,
                            const int32_t* __restrict__ shift, int8_t* __restrict__ digits) {
     const int64_t total = n * mpad;
@@ -860,7 +970,9 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
                 dig = static_cast<int>(static_cast<int8_t>(q & 0xff));
                 q = (q - dig) >> 8;
             }
-            digits[static_cast<size_t>(d) * total + idx] = static_cast<int8_t>(dig);
+            const size_t at = RECORDS ? (static_cast<size_t>(j >> 6) * n + r) * (64 * D) + d * 64 + (j & 63)
+                                      : static_cast<size_t>(d) * total + idx;
+            digits[at] = static_cast<int8_t>(dig);
         }
     }
 }
@@ -875,56 +987,21 @@ __device__ __forceinline__ int gather_chunk_pos(int k, int nc) {
     return (nc / HC) * (TC_KT * HC) + (k >> 3) * (HC * 8) + (nc % HC) * 8 + (k & 7);
 }
 
-// M >= 64: one block builds the tiles of GCG consecutive column groups for one (permutation, k-tile).  The source
-// rows are resolved once per block; reads are 64*GCG contiguous bytes per (source row, digit plane); the tiles are
-// assembled in shared memory and written out linearly.
-template <int D>
-struct GatherCfg {
-    static constexpr int GCG = D == 1 ? 8 : (D == 2 ? 4 : 3);  // column groups per block (tiles <= 36 KB of smem)
-};
-template <int D>
-__global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ digits, const int32_t* __restrict__ perm,
-                                                const int32_t* __restrict__ order, int64_t n, int64_t mpad,
-                                                int32_t n_kt, int32_t n_cg, int8_t* __restrict__ bcat) {
-    constexpr int NC16 = 4 * D;
-    constexpr int CHUNKS = TC_KT * NC16;       // 16-byte chunks per tile
-    constexpr int GCG = GatherCfg<D>::GCG;
-    __shared__ uint4 s_tile[GCG * CHUNKS];
-    __shared__ int32_t s_src[TC_KT];
-    const int kt = blockIdx.x;
-    const int q = blockIdx.z;
-    const int cg0 = blockIdx.y * GCG, ncg = min(GCG, n_cg - cg0);
-    if (threadIdx.x < TC_KT) {
-        const int64_t t = static_cast<int64_t>(kt) * TC_KT + threadIdx.x;
-        int32_t src = -1;
+// Source rows of a batch in the internal node order: src[q][t] = perm[q][order[t]] (identity for perm == nullptr),
+// -1 for the padding positions t >= n of the last k-tile.  What the GEMM's gather warps index the digit records with.
+__global__ void __launch_bounds__(256) k_compose_src(const int32_t* __restrict__ perm,
+                                                     const int32_t* __restrict__ order, int64_t n, int64_t n_pad,
+                                                     int64_t total, int32_t* __restrict__ src) {
+    int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; idx < total; idx += step) {
+        const int64_t q = idx / n_pad, t = idx % n_pad;
+        int32_t v = -1;
         if (t < n) {
             const int64_t node = order ? order[t] : t;  // internal position t holds the caller's node `node`
-            src = perm ? perm[static_cast<int64_t>(q) * n + node] : static_cast<int32_t>(node);
+            v = perm ? perm[q * n + node] : static_cast<int32_t>(node);
         }
-        s_src[threadIdx.x] = src;
-    }
-    __syncthreads();
-    const size_t plane = static_cast<size_t>(n) * mpad;
-    const int per_row = ncg * 4;               // 16-byte chunks per (row, plane) in this block's column range
-    const int total = TC_KT * D * per_row;
-    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int c16 = idx % per_row, rest = idx / per_row;
-        const int d = rest % D, k = rest / D;
-        const int g = c16 >> 2, jc = c16 & 3;
-        const int32_t src = s_src[k];
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (src >= 0)
-            v = __ldg(reinterpret_cast<const uint4*>(digits + d * plane + static_cast<size_t>(src) * mpad +
-                                                     static_cast<size_t>(cg0) * 64 + c16 * 16));
-        s_tile[g * CHUNKS + gather_chunk_pos<D>(k, d * 4 + jc)] = v;
-    }
-    __syncthreads();
-    // streaming stores: the tiles are read once by the GEMM much later; they must not evict the digit planes (re-read
-    // by every permutation of the batch) from L2
-    for (int g = 0; g < ncg; ++g) {
-        const size_t slot = static_cast<size_t>(q) * n_cg + cg0 + g;
-        uint4* dst = reinterpret_cast<uint4*>(bcat + (slot * n_kt + kt) * (TC_KT * 64 * D));
-        for (int i = threadIdx.x; i < CHUNKS; i += blockDim.x) __stcs(dst + i, s_tile[g * CHUNKS + i]);
+        src[idx] = v;
     }
 }
 
@@ -995,7 +1072,9 @@ struct TcPlan {
     DevBuf<int64_t> s0fix;
     DevBuf<unsigned int> flag_count;
     int64_t cpk_perms = 0;  // permutations accumulated in the packed counters since the last unpack (16-bit fields)
+    uint32_t* cpk = nullptr;  // packed counters of the call in progress (context scratch or the caller's array)
     unsigned int flag_cap = 0;
+    bool any_inexact = false;
 };
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
@@ -1013,31 +1092,38 @@ static void print_prof(sb_ctx* ctx, const long long* d_prof, const char* what) {
             h[4] / fills, h[5] / fills, h[7] / fills, h[8] / fills, h[9] / fills);
 }
 
-template <int D, int KIND, bool SMALL_M, bool PROF>
+template <int D, int KIND, bool SMALL_M, bool PROF, bool GATHER>
 static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
     using C = TcCfg<D>;
     static bool configured = false;
     if (!configured) {
-        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     C::SMEM));
+        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M, PROF, GATHER>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
     KernelTimer kt(ctx, SB_K_GEMM);
     // `grid` counts CTA pairs; the kernel carries __cluster_dims__(2, 1, 1)
-    k_gemm<D, KIND, SMALL_M, PROF><<<2 * grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
+    k_gemm<D, KIND, SMALL_M, PROF, GATHER><<<2 * grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
     SB_LAUNCH_CHECK(ctx);
 }
 
+// in-kernel row gather (gp.dig set): whole column groups only; pre-gathered tiles (gp.bcat): M < 64 and self-tests
 template <int D, bool PROF>
 static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams& gp, int grid) {
+    const bool gather = gp.dig != nullptr;
+    SB_CHECK(!(gather && small_m), "internal error: row gather with M < 64");
     if (kind == TCK_RAW)
-        launch_gemm<D, TCK_RAW, false, PROF>(ctx, gp, grid);
-    else if (kind == TCK_STORE)
-        small_m ? launch_gemm<D, TCK_STORE, true, false>(ctx, gp, grid)
-                : launch_gemm<D, TCK_STORE, false, false>(ctx, gp, grid);
-    else
-        small_m ? launch_gemm<D, TCK_COUNT, true, PROF>(ctx, gp, grid)
-                : launch_gemm<D, TCK_COUNT, false, PROF>(ctx, gp, grid);
+        gather ? launch_gemm<D, TCK_RAW, false, PROF, true>(ctx, gp, grid)
+               : launch_gemm<D, TCK_RAW, false, PROF, false>(ctx, gp, grid);
+    else {
+        SB_CHECK(gather || small_m, "internal error: column groups of 64 take the in-kernel row gather");
+        if (kind == TCK_STORE)
+            small_m ? launch_gemm<D, TCK_STORE, true, false, false>(ctx, gp, grid)
+                    : launch_gemm<D, TCK_STORE, false, false, true>(ctx, gp, grid);
+        else
+            small_m ? launch_gemm<D, TCK_COUNT, true, PROF, false>(ctx, gp, grid)
+                    : launch_gemm<D, TCK_COUNT, false, PROF, true>(ctx, gp, grid);
+    }
 }
 
 static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid) {
@@ -1068,24 +1154,16 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
         launch_gemm_k<3, false>(ctx, kind, small_m, gp, grid);
 }
 
-static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
+// Operand of a batch of permutations.  Column groups of 64 (M >= 64): only the source-row table of the batch is
+// built (the GEMM gathers the rows itself).  M < 64: the packed tiles are assembled in HBM (tiny problems).
+static void prepare_operand(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
     KernelTimer kt(ctx, SB_K_GATHER);
     if (pl->mpad >= 64) {
-        const int nq = slots / pl->n_cg;
-        const int gcg = pl->D == 1 ? GatherCfg<1>::GCG : (pl->D == 2 ? GatherCfg<2>::GCG : GatherCfg<3>::GCG);
-        dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(sb_ceil_div(pl->n_cg, gcg)),
-                  static_cast<unsigned>(nq));
-        SB_CHECK(grid.y <= 65535 && grid.z <= 65535, "too many column groups / permutations in one batch");
-#define SB_G(DD) \
-    k_gather<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt, pl->n_cg, \
-                                                ctx->ws_bcat.p)
-        if (pl->D == 1)
-            SB_G(1);
-        else if (pl->D == 2)
-            SB_G(2);
-        else
-            SB_G(3);
-#undef SB_G
+        const int64_t n_pad = static_cast<int64_t>(pl->n_kt) * TC_KT;
+        const int64_t total = n_pad * batch_perms;
+        ctx->ws_src.reserve(static_cast<size_t>(total));
+        const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(total, 256), ctx->num_sms * 16));
+        k_compose_src<<<blocks, 256, 0, ctx->stream>>>(perm, pl->order, pl->n, n_pad, total, ctx->ws_src.p);
     } else {
         dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
         SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
@@ -1109,7 +1187,12 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.a_bits = pl->a_bits.p;
     gp.tile_ptr = pl->tile_ptr.p;
     gp.tile_kt = pl->tile_kt.p;
-    gp.bcat = ctx->ws_bcat.p;
+    if (pl->mpad >= 64) {
+        gp.dig = pl->digits.p;
+        gp.src_idx = ctx->ws_src.p;
+    } else {
+        gp.bcat = ctx->ws_bcat.p;
+    }
     gp.n_kt = pl->n_kt;
     gp.n_rb = pl->n_rb;
     gp.n_cg = pl->n_cg;
@@ -1126,7 +1209,7 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.flag_p = ctx->ws_flag_p.p;
     gp.flag_count = pl->flag_count.p;
     gp.flag_cap = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
-    gp.cpk = ctx->ws_cpk.p;
+    gp.cpk = pl->cpk;
     const uint32_t ncols = 64u * pl->D;
     gp.b_lbo = ncols / 2 * 8;  // MN-major B half tile: stride between 8-row K groups
     gp.b_sbo = 128;        //             stride between 16-column chunks
@@ -1296,8 +1379,15 @@ static TcPlan* build_plan(sb_enrich* e) {
         pl->digits.reserve(static_cast<size_t>(D) * n * pl->mpad);
         const unsigned qblocks =
             static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * pl->mpad, 256), ctx->num_sms * 32));
-#define SB_Q(T, DD) \
-    k_quantize<T, DD><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad, shift.p, pl->digits.p)
+#define SB_Q(T, DD)                                                                                              \
+    do {                                                                                                         \
+        if (pl->mpad >= 64)                                                                                      \
+            k_quantize<T, DD, true><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad, shift.p, \
+                                                             pl->digits.p);                                      \
+        else                                                                                                     \
+            k_quantize<T, DD, false><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad,       \
+                                                              shift.p, pl->digits.p);                            \
+    } while (0)
         if (e->dtype == SB_F32) {
             if (D == 1) SB_Q(float, 1);
             else if (D == 2) SB_Q(float, 2);
@@ -1313,22 +1403,29 @@ static TcPlan* build_plan(sb_enrich* e) {
 
         delete tr;
         tr = new PhaseTrace(ctx, "tc.plan.alloc_flags");
-        // ---- flag list (capacity >= one slot's worst case so that overflow recovery always terminates)
-        const int64_t worst_slot = static_cast<int64_t>(pl->n_rb) * TC_PROWS * 64 * (pl->mpad >= 64 ? pl->n_cg : 1);
-        pl->flag_cap = static_cast<unsigned int>(std::min<int64_t>(std::max<int64_t>(4ll << 20, worst_slot), 1ll << 31));
+        // ---- flag list.  Only inexact columns can flag (~3e-5 of their comparisons for N(0,1) data); the list is
+        // sized for a quarter of the cells per launch (4M .. 128M entries of 12 bytes) instead of the worst case, and
+        // an overflowing launch is redone in (slot, row-block range) pieces whose worst case fits (tc_perm_counts).
+        bool any_inexact = false;
+        for (int64_t j = 0; j < m; ++j) any_inexact |= h_inexact[j] != 0;
+        pl->any_inexact = any_inexact;
+        const int64_t padded_cells = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
+        int64_t cap = any_inexact ? std::min<int64_t>(std::max<int64_t>(padded_cells / 4, 4ll << 20), 128ll << 20) : 0;
+        if (getenv("SB_FLAG_CAP")) cap = atoll(getenv("SB_FLAG_CAP"));  // tests: force the overflow recovery
+        cap = std::max<int64_t>(cap, static_cast<int64_t>(TC_PROWS) * 64 * pl->n_cg);  // >= one row block per bucket
+        pl->flag_cap = static_cast<unsigned int>(sb_ceil_div(cap, pl->n_cg) * pl->n_cg);
         ctx->ws_flag_ij.reserve(pl->flag_cap);
         ctx->ws_flag_p.reserve(pl->flag_cap);
         pl->flag_count.reserve(pl->n_cg);
-        ctx->ws_cpk.reserve(static_cast<size_t>(n) * m);
 
         delete tr;
         tr = new PhaseTrace(ctx, "tc.plan.s0fix");
         // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
         const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
         const int64_t slots1 = slots_for(pl, 1);
-        ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
+        if (pl->mpad < 64) ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
         pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_PROWS * pl->mpad);
-        launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1);
+        prepare_operand(ctx, pl, nullptr, static_cast<int>(slots1), 1);
         GemmParams gp = base_params(e, pl);
         gp.mode = TCM_STORE;
         gp.q_total = 1;
@@ -1346,25 +1443,32 @@ static TcPlan* build_plan(sb_enrich* e) {
     return pl;
 }
 
-// one GEMM launch over slots [0, q_total) of the gathered batch
-static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int batch_perms) {
+// one GEMM launch over slots [q_first, q_first + q_total) of the prepared batch and row blocks [rb0, rb0 + n_rb)
+static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_first, int q_total, int batch_perms, int rb0,
+                           int n_rb) {
     sb_ctx* ctx = e->ctx;
     GemmParams gp = base_params(e, pl);
     gp.mode = mode;
     gp.q_total = q_total;
     gp.batch_perms = batch_perms;
-    // L2 blocking (see decode_unit; bands are chosen in build_plan).  The number of
-    // slots per unit (q_per) trades per-unit epilogue overhead (observed-score preload, count flush) against the
-    // gathered slab a band touches per (q chunk, column group): measured on C3, 13+ slots per unit (64 MB slabs, the
-    // default; SB_SLAB_MB overrides) run 20 % faster than 4 and the 5-stage ring still hides the L2 / HBM latency.
-    const double tile_b = static_cast<double>(TC_KT) * 64 * pl->D;
-    gp.band_rb = pl->band_rb;
-    gp.n_bands = pl->n_bands;
-    const double slab = std::max(1, pl->band_kt) * tile_b;  // gathered bytes a band touches per (slot, column group)
-    static const double slab_mb = getenv("SB_SLAB_MB") ? atof(getenv("SB_SLAB_MB")) : 64.0;
-    int q_per = static_cast<int>(std::max(1.0, std::min(64.0, slab_mb * (1 << 20) / slab)));
-    // enough units to keep every SM busy with a few units each
-    const int base_units = pl->n_rb * pl->n_cg;
+    gp.rb0 = rb0;
+    gp.n_rb = n_rb;
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
+    if (q_first) {  // slot offset into the operand of the batch
+        if (gp.src_idx) gp.src_idx += static_cast<size_t>(q_first) * pl->n_kt * TC_KT;
+        if (gp.bcat) gp.bcat += static_cast<size_t>(q_first) * pl->n_cg * pl->n_kt * tile_b;
+    }
+    // Unit order (decode_unit): band of row blocks, then q chunk, then column group, then row block -- the CTA pairs
+    // that run concurrently work on the same column group, whose digit records (N x 64 D bytes, 3.8 MB at C3) are
+    // what they all gather from: the slab stays L2-resident whatever the number of slots per unit.  Slots per unit
+    // (q_per) only trades per-unit epilogue overhead (observed-score preload, count flush) against load balance:
+    // up to 64 (SB_Q_PER overrides), fewer when the launch would not give every SM pair a few units.
+    const bool whole = rb0 == 0 && n_rb == pl->n_rb;
+    gp.band_rb = whole ? pl->band_rb : n_rb;
+    gp.n_bands = whole ? pl->n_bands : 1;
+    static const int q_per_max = getenv("SB_Q_PER") ? std::max(1, atoi(getenv("SB_Q_PER"))) : 64;
+    int q_per = q_per_max;
+    const int base_units = n_rb * pl->n_cg;
     const int want_chunks = static_cast<int>(sb_ceil_div(4 * (ctx->num_sms / 2), base_units));
     q_per = std::min<int>(q_per, std::max<int>(1, q_total / std::max(1, want_chunks)));
     q_per = std::max(1, std::min(q_per, q_total));
@@ -1379,77 +1483,93 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_total, int 
         SB_CUDA(cudaMemsetAsync(d_prof.p, 0, 16 * sizeof(long long), ctx->stream));
         gp.prof = d_prof.p;
         fprintf(stderr, "[sb_trace] gemm schedule: n_rb %d n_cg %d q_total %d q_per %d band_rb %d n_bands %d units %lld\n",
-                pl->n_rb, pl->n_cg, q_total, gp.q_per, gp.band_rb, gp.n_bands, (long long)units);
+                n_rb, pl->n_cg, q_total, gp.q_per, gp.band_rb, gp.n_bands, (long long)units);
     }
     launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms / 2)));
     if (trace) print_prof(ctx, d_prof.p, "batch gemm");
 }
 
-static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpos) {
-    sb_ctx* ctx = e->ctx;
-    const int64_t cells = e->n * e->m;
+void unpack_add_counts(sb_ctx* ctx, uint32_t* packed, int64_t cells, uint32_t* cneg, uint32_t* cpos) {
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(cells, 256), ctx->num_sms * 16));
-    k_unpack_counts<<<blocks, 256, 0, ctx->stream>>>(ctx->ws_cpk.p, cells, cneg, cpos);
+    k_unpack_counts<<<blocks, 256, 0, ctx->stream>>>(packed, cells, cneg, cpos);
     SB_LAUNCH_CHECK(ctx);
+}
+
+static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpos) {
+    unpack_add_counts(e->ctx, pl->cpk, e->n * e->m, cneg, cpos);
     pl->cpk_perms = 0;
 }
 
-void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos) {
+// Counts of `num_perm` permutations.  Either ADDED to the caller's two arrays (cneg / cpos), or, with `packed`
+// (cneg == cpos == nullptr), ADDED to one word per cell, pos << 16 | neg -- the form that crosses NVLink in the
+// multi-GPU all-reduce; the caller keeps the number of permutations summed into a word below 65536.
+void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
+                    uint32_t* packed) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
     PhaseTrace tr_all(ctx, "tc.perm_counts(total)");
     if (!e->tc) e->tc = build_plan(e);
     TcPlan* pl = e->tc;
-    if (!pl->usable) {  // +-inf in the data: fixed point cannot represent it
-        simt_perm_counts(e, SB_SCORE_SUM, perm_dev, num_perm, cneg, cpos);
+    if (!pl->usable) {  // +-inf in the data (or neighborhoods of 65536+ nodes): fixed point cannot represent it
+        simt_perm_counts(e, SB_SCORE_SUM, perm_dev, num_perm, cneg, cpos, packed);
         return;
     }
+    SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
     PhaseTrace* tr_ws = new PhaseTrace(ctx, "tc.workspace");
 
-    // batch size: Bcat workspace <= ~1/8 of free memory (at most 16 GiB), q per unit < 32768 (16-bit counters)
-    // (cudaMemGetInfo was seen to take hundreds of ms on a busy device: ask once per context)
-    if (ctx->bcat_budget == 0) {
-        size_t free_b = 0, total_b = 0;
-        SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
-    }
-    const size_t free_b = ctx->bcat_budget * 8;
+    // Permutations per launch.  Column groups of 64: the operand of a batch is only its source-row table
+    // (4 (N + pad) bytes per permutation, at most 1 GiB per launch).  M < 64: pre-gathered tiles, <= ~1/8 of the free
+    // memory seen at the first null of this context (cudaMemGetInfo was seen to take hundreds of ms on a busy device).
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
-    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(free_b / 8, slot_bytes * slots_for(pl, 1)), 16ull << 30),
-                                   ctx->ws_bcat.n);
-    int64_t max_slots = std::max<int64_t>(slots_for(pl, 1), static_cast<int64_t>(budget / slot_bytes));
-    max_slots = std::min<int64_t>(max_slots, 65535);
-    int64_t pb = pl->mpad >= 64 ? max_slots / pl->n_cg : max_slots * pl->pps;
+    int64_t pb;
+    if (pl->mpad >= 64) {
+        pb = std::max<int64_t>(1, (1ll << 30) / (static_cast<int64_t>(pl->n_kt) * TC_KT * 4));
+    } else {
+        if (ctx->bcat_budget == 0) {
+            size_t free_b = 0, total_b = 0;
+            SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
+        }
+        const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes), 16ull << 30),
+                                       ctx->ws_bcat.n);
+        const int64_t max_slots = std::min<int64_t>(std::max<int64_t>(1, static_cast<int64_t>(budget / slot_bytes)), 65535);
+        pb = max_slots * pl->pps;
+    }
     pb = std::max<int64_t>(1, std::min<int64_t>(pb, 16384));  // 16-bit per-unit counters
     pb = std::min(pb, num_perm);
-    const int64_t need_slots = slots_for(pl, pb);
-    ctx->ws_bcat.reserve(static_cast<size_t>(need_slots) * slot_bytes);
-    // the packed counters and the fix-up list live in context scratch: (re)claim them for this call
+    if (pl->mpad < 64) ctx->ws_bcat.reserve(static_cast<size_t>(slots_for(pl, pb)) * slot_bytes);
+    // the fix-up list (and, unless the caller supplies the packed array, the packed counters) live in context scratch
     ctx->ws_flag_ij.reserve(pl->flag_cap);
     ctx->ws_flag_p.reserve(pl->flag_cap);
-    ctx->ws_cpk.reserve(static_cast<size_t>(e->n) * e->m);
-    SB_CUDA(cudaMemsetAsync(ctx->ws_cpk.p, 0, static_cast<size_t>(e->n) * e->m * sizeof(uint32_t), st));
+    if (packed) {
+        pl->cpk = packed;
+    } else {
+        ctx->ws_cpk.reserve(static_cast<size_t>(e->n) * e->m);
+        SB_CUDA(cudaMemsetAsync(ctx->ws_cpk.p, 0, static_cast<size_t>(e->n) * e->m * sizeof(uint32_t), st));
+        pl->cpk = ctx->ws_cpk.p;
+    }
     pl->cpk_perms = 0;
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
-    int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;  // includes padding tiles
+    const int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;  // includes padding tiles
+    const unsigned int cap_cg = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
+    std::vector<unsigned int> h_flags(pl->n_cg);
     for (int64_t p0 = 0; p0 < num_perm; p0 += pb) {
         const int64_t np = std::min(pb, num_perm - p0);
         const int32_t* perm = perm_dev + p0 * e->n;
         const int slots = static_cast<int>(slots_for(pl, np));
         const int q_total = pl->mpad >= 64 ? static_cast<int>(np) : slots;
         {
-            PhaseTrace tr(ctx, "tc.batch.gather");
-            launch_gather(ctx, pl, perm, slots, static_cast<int>(np));
+            PhaseTrace tr(ctx, "tc.batch.operand");
+            prepare_operand(ctx, pl, perm, slots, static_cast<int>(np));
         }
         PhaseTrace tr_b(ctx, "tc.batch.gemm+fixup");
-        const unsigned int cap_cg = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
-        std::vector<unsigned int> h_flags(pl->n_cg);
         // fix-ups bucket by bucket: the flags of one column group touch 64 attribute columns only, so the scattered
         // row reads of the fix-up kernel stay L2-resident
         auto run_fixups = [&](const int32_t* perm_base) -> int64_t {
+            if (!pl->any_inexact) return 0;  // exactly representable columns never flag
             SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
                                     cudaMemcpyDeviceToHost, st));
             SB_CUDA(cudaStreamSynchronize(st));
@@ -1461,42 +1581,44 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
             for (int cg = 0; cg < pl->n_cg; ++cg)
                 if (h_flags[cg])
                     fixup_flags(e, perm_base, ctx->ws_flag_ij.p + static_cast<size_t>(cg) * cap_cg,
-                                ctx->ws_flag_p.p + static_cast<size_t>(cg) * cap_cg, h_flags[cg], cneg, cpos);
+                                ctx->ws_flag_p.p + static_cast<size_t>(cg) * cap_cg, h_flags[cg], cneg, cpos,
+                                packed);
             return total;
         };
         SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-        if (pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);
+        if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);
         pl->cpk_perms += np;
-        run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, q_total, static_cast<int>(np));
+        run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
         ktile_iters += tiles_per_pass * q_total;
         const int64_t got = run_fixups(perm);
         if (got >= 0) {
             flagged += got;
         } else {
-            // A bucket overflowed: nothing of the list is used.  Re-emit the flags slot by slot (one slot's worst case
-            // always fits) without re-adding the decided counts.
+            // A bucket overflowed: nothing of the list is used.  Re-emit the flags (without re-adding the decided
+            // counts) slot by slot and in row-block ranges whose worst case -- every cell of the range flagged --
+            // fits a bucket.
             ++overflow_batches;
+            const int rb_step = std::max<int>(1, static_cast<int>(cap_cg / (TC_PROWS * 64)));
             for (int q = 0; q < q_total; ++q) {
-                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-                GemmParams gp = base_params(e, pl);
-                gp.mode = TCM_FLAG;
-                gp.bcat = ctx->ws_bcat.p + static_cast<size_t>(q) * pl->n_cg * slot_bytes;
-                gp.q_total = 1;
-                gp.q_chunks = 1;
-                gp.q_per = 1;
-                // batch-local permutation index of column block q is recovered by offsetting perm instead
-                gp.batch_perms = static_cast<int32_t>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
-                if (pl->mpad >= 64) gp.batch_perms = 1;
-                launch_gemm_d(ctx, pl->D, gp, std::min(pl->n_rb * pl->n_cg, ctx->num_sms / 2));
-                ktile_iters += tiles_per_pass;
+                const int bp = pl->mpad >= 64
+                                   ? 1
+                                   : static_cast<int>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
+                // the batch-local permutation index of a flag is relative to slot q: offset the index base instead
                 const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
-                const int64_t gq = run_fixups(perm_q);
-                SB_CHECK(gq >= 0, "internal error: flag list overflow in single-slot recovery");
-                flagged += gq;
+                for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
+                    const int nrb = std::min(rb_step, pl->n_rb - rb0);
+                    SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
+                    run_batch_gemm(e, pl, TCM_FLAG, q, 1, bp, rb0, nrb);
+                    const int64_t gq = run_fixups(perm_q);
+                    SB_CHECK(gq >= 0, "internal error: flag list overflow in single-slot recovery");
+                    flagged += gq;
+                }
+                ktile_iters += tiles_per_pass;
             }
         }
     }
-    flush_counts(e, pl, cneg, cpos);
+    if (!packed) flush_counts(e, pl, cneg, cpos);
+    pl->cpk = nullptr;
     e->stats[0] = e->n * e->m * num_perm - flagged;
     e->stats[1] = flagged;
     e->stats[2] = pl->n_tiles_real;

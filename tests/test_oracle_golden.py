@@ -89,6 +89,24 @@ def test_hypergeom_matches_reference(stage2_small):
     assert np.array_equal(p, g["hyper_bgnet_p"], equal_nan=True)
 
 
+def test_hypergeom_block_equals_the_full_statement(stage2_small):
+    """The sampled-block form used for the full-size checks (bench.py parity gate, C2 test) reproduces the reference's
+    cells bit for bit, also when a sampled column subset alone would misjudge which nodes carry data."""
+    g = stage2_small
+    n = g["x"].shape[0]
+    nb = unpack_packed(g["neighborhoods"], n).astype(np.int64)
+    rows = np.array([0, 3, 17, n - 1])
+    cols = np.array([1, 4, 5])
+    p, nes = orc.hypergeom_pvalues_block(nb[rows], g["attr_binary"], cols)
+    assert np.array_equal(p, g["hyper_p"][np.ix_(rows, cols)], equal_nan=True)
+    assert np.array_equal(nes, g["hyper_nes"][np.ix_(rows, cols)], equal_nan=True)
+    attrs = g["attr_binary"].copy()
+    attrs[:, cols] = np.where(np.arange(n)[:, None] % 7 == 0, np.nan, attrs[:, cols])   # NaN only in these columns
+    pf, _ = orc.hypergeom_pvalues(nb, attrs)
+    pb, _ = orc.hypergeom_pvalues_block(nb[rows], attrs, cols)
+    assert np.array_equal(pb, pf[np.ix_(rows, cols)], equal_nan=True)
+
+
 def test_sparse_twin_equals_dense_dot(stage2_small):
     g = stage2_small
     n = g["x"].shape[0]

@@ -99,8 +99,7 @@ struct sb_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers[SB_K_CLASSES];
     // grow-only scratch shared by all plans of this context (used only inside one call at a time):
     // gathered operand tiles, fix-up list, packed count accumulators
-    sb::DevBuf<int8_t> ws_bcat;      // pre-gathered operand tiles (M < 64 only)
-    sb::DevBuf<int32_t> ws_src;      // source-row table of the batch in flight (in-kernel row gather)
+    sb::DevBuf<int8_t> ws_bcat;      // gathered operand tiles of the batch in flight
     sb::DevBuf<uint64_t> ws_flag_ij;
     sb::DevBuf<uint32_t> ws_flag_p;
     sb::DevBuf<uint32_t> ws_cpk;
@@ -118,15 +117,16 @@ struct KernelTimer {
     sb_ctx* ctx;
     int cls;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    KernelTimer(sb_ctx* c, int k) : ctx(c), cls(k) {
+    cudaStream_t st;
+    KernelTimer(sb_ctx* c, int k, cudaStream_t on = nullptr) : ctx(c), cls(k), st(on ? on : c->stream) {
         if (!ctx->profile) return;
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, ctx->stream);
+        cudaEventRecord(e0, st);
     }
     ~KernelTimer() {
         if (!e0) return;
-        cudaEventRecord(e1, ctx->stream);
+        cudaEventRecord(e1, st);
         ctx->timers[cls].emplace_back(e0, e1);
     }
 };

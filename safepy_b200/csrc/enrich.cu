@@ -158,14 +158,22 @@ __global__ void __launch_bounds__(128) k_perm_count(const int64_t* __restrict__ 
 // fp64, so the summation order is immaterial; for the rest the reference's own BLAS order is unspecified.)
 // b_t is the attribute matrix TRANSPOSED ([m][n]): the scattered reads of one comparison then fall into one
 // n-element column (a bucket of 64 columns stays L2-resident even at 100k nodes x 5000 attributes).
+// blockIdx.y selects a bucket of the list when count_dev is given.
 template <class T>
 __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
                                                const T* __restrict__ b_t, const int32_t* __restrict__ perm, int64_t n,
                                                int64_t m, const uint64_t* __restrict__ flag_ij,
                                                const uint32_t* __restrict__ flag_p,
-                                               unsigned int total, uint32_t* __restrict__ cneg,
+                                               unsigned int total, const unsigned int* __restrict__ count_dev,
+                                               unsigned int cap, uint32_t* __restrict__ cneg,
                                                uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
     const int lane = threadIdx.x & 31;
+    if (count_dev) {
+        total = count_dev[blockIdx.y];
+        if (total > cap) return;  // overflowed bucket: redone by the caller
+        flag_ij += static_cast<size_t>(blockIdx.y) * cap;
+        flag_p += static_cast<size_t>(blockIdx.y) * cap;
+    }
     unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int step = (gridDim.x * blockDim.x) >> 5;
     for (; k < total; k += step) {
@@ -449,7 +457,7 @@ __global__ void __launch_bounds__(256) k_transpose(const T* __restrict__ in, int
     }
 }
 
-static const void* transposed_b(sb_enrich* e) {
+const void* enrich_transposed(sb_enrich* e) {
     if (e->b_t) return e->b_t;
     sb_ctx* ctx = e->ctx;
     const size_t bytes = static_cast<size_t>(e->n) * e->m * (e->dtype == SB_F32 ? 4 : 8);
@@ -469,18 +477,38 @@ static const void* transposed_b(sb_enrich* e) {
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
                  unsigned int count, uint32_t* cneg, uint32_t* cpos, uint32_t* packed) {
     sb_ctx* ctx = e->ctx;
-    const void* bt = transposed_b(e);
+    const void* bt = enrich_transposed(e);
     const unsigned blocks = static_cast<unsigned>(
         std::min<int64_t>(sb_ceil_div(static_cast<int64_t>(count), 8), static_cast<int64_t>(ctx->num_sms) * 8));
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
         k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt),
-                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos,
-                                                        packed);
+                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0,
+                                                        cneg, cpos, packed);
     else
         k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt),
-                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, cneg, cpos,
-                                                         packed);
+                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0,
+                                                         cneg, cpos, packed);
+    SB_LAUNCH_CHECK(ctx);
+}
+
+void fixup_flag_buckets(sb_enrich* e, cudaStream_t st, const int32_t* perm_dev, const uint64_t* flag_ij,
+                        const uint32_t* flag_p, const unsigned int* count_dev, int n_buckets, unsigned int cap,
+                        uint32_t* cneg, uint32_t* cpos, uint32_t* packed) {
+    sb_ctx* ctx = e->ctx;
+    const void* bt = e->b_t;
+    SB_CHECK(bt, "internal error: transposed attribute matrix not built");
+    // blocks per bucket: the whole device, split over the buckets (a bucket usually holds a few thousand entries)
+    const int bx = std::max(1, std::min(64, (ctx->num_sms * 8) / std::max(1, n_buckets)));
+    dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_buckets));
+    SB_CHECK(grid.y <= 65535, "too many fix-up buckets");
+    KernelTimer kt(ctx, SB_K_FIXUP, st);
+    if (e->dtype == SB_F32)
+        k_fixup<float><<<grid, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt), perm_dev, e->n,
+                                             e->m, flag_ij, flag_p, 0, count_dev, cap, cneg, cpos, packed);
+    else
+        k_fixup<double><<<grid, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt), perm_dev,
+                                              e->n, e->m, flag_ij, flag_p, 0, count_dev, cap, cneg, cpos, packed);
     SB_LAUNCH_CHECK(ctx);
 }
 

@@ -57,6 +57,14 @@ void simt_perm_counts(sb_enrich* e, int score_type, const int32_t* perm_dev, int
 // exact fp64 re-evaluation of flagged (i, j, p) comparisons; entries are (i << 32 | j) , p pairs
 void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij, const uint32_t* flag_p,
                  unsigned int count, uint32_t* cneg, uint32_t* cpos, uint32_t* packed = nullptr);
+// [m x n] transposed copy of the attribute matrix (built on the context's stream on first use)
+const void* enrich_transposed(sb_enrich* e);
+// The same for a list bucketed by column group ([n_buckets][cap] entries, bucket b holding count_dev[b] of them), in
+// ONE launch on `st` with the counts read on the device; a bucket whose count exceeds `cap` overflowed and is skipped
+// as a whole (the caller redoes it).
+void fixup_flag_buckets(sb_enrich* e, cudaStream_t st, const int32_t* perm_dev, const uint64_t* flag_ij,
+                        const uint32_t* flag_p, const unsigned int* count_dev, int n_buckets, unsigned int cap,
+                        uint32_t* cneg, uint32_t* cpos, uint32_t* packed);
 
 // gemm_tc.cu
 void tc_plan_destroy(TcPlan* p);

@@ -13,13 +13,13 @@
 // block of 256 rows of A (128 per CTA) and multiplies it with a gathered-operand tile whose 64*D columns are split
 // between the two CTAs' shared memories, so every byte of the gathered operand that leaves L2 feeds 256 rows.
 // A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row.  The masks ride along with the
-// operand tiles through the smem ring, expander warps turn them into int8 0/1 in TMEM, and the MMA takes its A
-// operand from TMEM.  The permuted operand B_p = B[perm_p] never exists in memory: two gather warps per CTA fetch
-// the 64 source rows of every k-tile straight from the digit records (one 64*D-byte record per (node, column
-// group), L2-resident: a column group's slab is N * 64 * D bytes) with 16-byte async copies (LDGSTS) whose
-// shared-memory destinations are the tensor core's canonical no-swizzle MN-major core-matrix positions, so the
-// tile lands MMA-ready.  (M < 64 packs several permutations into one 64-column slot byte by byte; those tiny
-// problems keep the pre-gathered tile + bulk-copy path.)
+// gathered tiles through the smem ring, expander warps turn them into int8 0 / -1 in TMEM with byte permutes
+// (no table, no shared-memory traffic), and the MMA takes its A operand from TMEM; the digits are stored negated,
+// so the products come out with the right sign.  Gathered tiles are stored in HBM in the tensor core's canonical
+// no-swizzle MN-major core-matrix order, one half per CTA, so one 1-D bulk async copy (TMA engine, UBLKCP) lands a
+// half tile MMA-ready.  (A variant in which the kernel gathered the rows itself with 16-byte LDGSTS was measured at
+// 387 ms vs 226 ms for the C3 null -- 16 cache lines per instruction at ~2 cycles per L1TEX wavefront, on a shared
+// memory pipe the expanders already kept half busy; see profiles/r2a_bench_c3_fused_ldgsts_gather.json.)
 #include <algorithm>
 #include <climits>
 #include <vector>
@@ -44,16 +44,12 @@ constexpr int TC_EXP_WARPS = 4;          // one per TMEM lane quarter
 // therefore sit above the epilogue and expander warps.
 constexpr int TC_EXP_WARP0 = TC_EPI_WARPS;
 constexpr int TC_PROD_WARP = TC_EPI_WARPS + TC_EXP_WARPS;
-constexpr int TC_GATHER_WARPS = 2;       // row-gather warps (LDGSTS), k-tiles 2g and 2g+1 of every fill each
-constexpr int TC_GATHER_WARP0 = TC_PROD_WARP + 1;
-constexpr int TC_MMA_WARP = TC_GATHER_WARP0 + TC_GATHER_WARPS;
-constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;  // 16 warps x 128 registers = the whole register file
-static_assert(TC_GATHER_WARPS * 2 == TC_TPS, "each gather warp owns two k-tiles of a fill");
+constexpr int TC_MMA_WARP = TC_PROD_WARP + 1;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;
 // TMEM columns: accumulator buffer b at [256 b, 256 b + 64 D); A slot s (TC_APS tiles x 16 columns) in the gaps
 // [192, 256) and [448, 512)
 __host__ __device__ constexpr uint32_t tc_acol(uint32_t s) { return (s >> 1) * 256u + 192u + (s & 1u) * 32u; }
 static_assert(TC_APS * 16 == 32 && TC_ASLOTS == 4 && TC_TPS == 2 * TC_APS, "A slots must tile the TMEM gaps");
-constexpr int TC_LUT_REP = 8;            // replicas of the byte -> 8 x int8 expansion table (bank spreading)
 constexpr int TC_SCHED = 4;              // depth of the work-unit ring (scheduler -> all other roles of the pair)
 constexpr int TC_KT_SMEM = 1024;         // k-tile ids of the current row block cached in smem (tail: global)
 
@@ -65,9 +61,7 @@ struct GemmParams {
     const uint64_t* a_bits;   // [n_tiles / TPS][2 (CTA rank)][TPS][128]: bit k of a word = A[row][64 kt + k]
     const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
-    const int8_t* bcat;       // pre-gathered tiles (M < 64, self-tests): [slot][kt][2 (CTA rank)][64 x 32*D]
-    const int8_t* dig;        // GATHER: digit records [n_cg][n][64*D] (plane d of column c at byte d*64 + c)
-    const int32_t* src_idx;   // GATHER: [slot][n_kt*64] source row of internal position t (-1: zero row)
+    const int8_t* bcat;       // [slot][kt][2 (CTA rank)][64 x 32*D], K rows in the expanders' order (tc_kpos)
     int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;  // n_rb: blocks of TC_PROWS rows
     int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
     int32_t rb0;              // first row block of this launch (units cover row blocks [rb0, rb0 + n_rb))
@@ -120,28 +114,43 @@ struct TcCfg {
     static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
     static constexpr int OFF_S0LO = OFF_S0HI + 64 * TC_ROWS * 4;    // uint32 [16][128], 4 columns per word
     static constexpr int OFF_KT = OFF_S0LO + 16 * TC_ROWS * 4;      // int32 [TC_KT_SMEM]
-    static constexpr int OFF_LUT = OFF_KT + TC_KT_SMEM * 4;         // uint64 [256][TC_LUT_REP]
-    static constexpr int OFF_UNIT = OFF_LUT + 256 * TC_LUT_REP * 8; // UnitInfo [TC_SCHED]
+    static constexpr int OFF_UNIT = OFF_KT + TC_KT_SMEM * 4;        // UnitInfo [TC_SCHED]
     static constexpr int OFF_BAR = OFF_UNIT + TC_SCHED * 32;
     static constexpr int SMEM = OFF_BAR + 512;  // 34 mbarriers + the TMEM base address
 };
 
-// 64 membership bits -> 16 TMEM words of four 0/1 bytes (K elements 4c .. 4c+3 of a row sit in 32-bit column c).
-// One table lookup per byte of the mask: entry b of the table holds the eight 0/1 bytes of b.  The table is
-// replicated TC_LUT_REP times (lane l reads replica l % TC_LUT_REP) so that a warp's 32 random lookups spread over
-// the shared-memory banks.
-__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t lane_lut, uint32_t (&r)[16]) {
+// 64 membership bits -> 16 TMEM words of four int8 values 0 / -1, without a table and without shared memory.
+// One byte permute (PRMT) expands four bits.  Its four selector nibbles are four CONSECUTIVE nibbles of the mask, and
+// the 8-byte source it selects from is constant: {00,FF,00,FF,00,FF,00,FF} returns 0x00 / 0xFF by bit 0 of a
+// nibble, {00,00,FF,FF,00,00,FF,FF} by bit 1, {00,00,00,00,FF,FF,FF,FF} by bit 2, whatever the other bits are (bit 3
+// of a selector asks for the replicated sign of the selected byte -- 0x00 / 0xFF again).  Bit 3 itself takes one shift.
+// So word 4 g + j of a row comes from 16-bit group g of the mask with source j: 6 shifts + 16 permutes per 64 bits
+// (the lookup-table version cost 24 instructions, 8 of them shared-memory loads with bank conflicts: ~400 of the
+// shared-memory pipe's 768 cycles per fill, next to the tensor core's own operand reads).
+// Byte i of that word is mask bit 16 g + 4 i + j, i.e. the MMA sees the 64 entries of a tile in the order
+//   K position 16 g + 4 j + i  <->  tile entry 16 g + 4 i + j        (tc_kpos, an involution),
+// and the gathered operand tiles are written with their rows in the same order.  A = -1 where the reference has 1:
+// the digit planes hold the digits of -q (k_quantize), so A @ B is the reference's product.
+__host__ __device__ constexpr int tc_kpos(int p) { return (p & ~15) | ((p & 3) << 2) | ((p >> 2) & 3); }
+
+template <uint32_t LO, uint32_t HI>
+__device__ __forceinline__ uint32_t expand4(uint32_t ctl) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(LO), "r"(HI), "r"(ctl));
+    return d;
+}
+__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t (&r)[16]) {
     const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
-    // two instructions per lookup address: PRMT isolates byte b, one multiply-add scales it by the 64-byte entry
-    // stride and adds this lane's table address (replica included)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        const uint32_t byte = __byte_perm(b < 4 ? lo : hi, 0u, 0x4440u + (b & 3));
-        const uint32_t addr = byte * 64u + lane_lut;
-        asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2 * b]), "=r"(r[2 * b + 1]) : "r"(addr));
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t word = g < 2 ? lo : hi;
+        const uint32_t x = (g & 1) ? word >> 16 : word;  // PRMT reads the low 16 bits of its selector only
+        r[g * 4 + 0] = expand4<0xFF00FF00u, 0xFF00FF00u>(x);
+        r[g * 4 + 1] = expand4<0xFFFF0000u, 0xFFFF0000u>(x);
+        r[g * 4 + 2] = expand4<0x00000000u, 0xFFFFFFFFu>(x);
+        r[g * 4 + 3] = expand4<0xFF00FF00u, 0xFF00FF00u>(word >> (16 * (g & 1) + 3));
     }
 }
-static_assert(TC_LUT_REP * 8 == 64, "expand_bits assumes 64-byte table entries");
 
 // Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
 // tiles stay L2-resident) the q chunk is the slowest index, then the column group, then the row block -- CTA pairs
@@ -169,9 +178,8 @@ __device__ __forceinline__ void decode_unit(const GemmParams& p, int u, int& rb,
 // sempty barriers through shared::cluster; the leader's tcgen05.commit multicasts to the aempty / empty / tfull
 // barriers of both CTAs.
 // Epilogue warp w reads TMEM lane quarter (w & 3) and the 32-column half (w >> 2) of every digit plane.
-template <int D, int KIND, bool SMALL_M, bool PROF, bool GATHER>
+template <int D, int KIND, bool SMALL_M, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gemm(const GemmParams p) {
-    static_assert(!(GATHER && SMALL_M), "the in-kernel row gather needs whole 64-column groups");
     using C = TcCfg<D>;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sB = smem;
@@ -196,8 +204,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
-            // producer's expect_tx arrive (+ one arrival per gathering thread when its cp.async have landed)
-            mbar_init(&full[s], GATHER ? 1 + TC_GATHER_WARPS * 32 : 1);
+            mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1 + TC_EXP_WARPS);  // MMA commit + own expander warps (done reading the bit tiles)
         }
         for (int b = 0; b < 2; ++b) {
@@ -206,24 +213,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
         }
         for (int s = 0; s < TC_SCHED; ++s) {
             mbar_init(&sfull[s], 1);
-            // consumers: leader MMA + peer producer + epilogue, expander (and gather) warps of both CTAs
-            mbar_init(&sempty[s], 2 * (TC_EPI_WARPS + TC_EXP_WARPS + (GATHER ? TC_GATHER_WARPS : 0)) + 2);
+            // consumers: leader MMA + peer producer + epilogue and expander warps of both CTAs
+            mbar_init(&sempty[s], 2 * (TC_EPI_WARPS + TC_EXP_WARPS) + 2);
         }
         for (int s = 0; s < TC_ASLOTS; ++s) {
             mbar_init(&afull[s], 2 * TC_EXP_WARPS);
             mbar_init(&aempty[s], 1);
         }
         mbar_fence_init();
-    }
-    {
-        uint64_t* lut = reinterpret_cast<uint64_t*>(smem + C::OFF_LUT);
-        for (int i = threadIdx.x; i < 256 * TC_LUT_REP; i += blockDim.x) {
-            const uint32_t b = static_cast<uint32_t>(i) / TC_LUT_REP;
-            uint64_t v = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v |= static_cast<uint64_t>((b >> j) & 1u) << (8 * j);
-            lut[i] = v;
-        }
     }
     if (warp == TC_MMA_WARP) tmem_alloc2(tmem_slot, 512);
     tc_fence_before();
@@ -292,10 +289,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 if (rb < 0) break;
             }
             const int nk = nfills * C::TPS;
-            if (!GATHER) {  // (with the in-kernel gather the k-tile ids are the gather warps' business)
-                for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
-                __syncwarp();
-            }
+            for (int i = lane; i < min(nk, TC_KT_SMEM); i += 32) s_kt[i] = p.tile_kt[t0 + i];
+            __syncwarp();
             // this CTA's half of every gathered tile and its own rows of the A bit tiles
             const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * (2 * C::HALF_B) + rank * C::HALF_B;
             const uint64_t* const a_unit =
@@ -307,7 +302,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 #pragma unroll
                     for (int t = 0; t < C::TPS; ++t) {
                         const int i = f * C::TPS + t;
-                        kts[t] = GATHER ? 0 : (i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i]);
+                        kts[t] = i < TC_KT_SMEM ? s_kt[i] : p.tile_kt[t0 + i];
                     }
                     TC_TIMED(KIND, pt_wait, mbar_wait(&empty[stage], phase ^ 1u));
                     if (PROF) ++pt_fills;
@@ -315,14 +310,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                         if (p.dbg & 2) {
                             mbar_arrive(&full[stage]);
                         } else {
-                            mbar_expect_tx(&full[stage], GATHER ? C::STAGE_A : C::STAGE);
+                            mbar_expect_tx(&full[stage], C::STAGE);
                             uint8_t* const st = sB + stage * C::STAGE;
-                            if (!GATHER) {
 #pragma unroll
-                                for (int t = 0; t < C::TPS; ++t)
-                                    bulk_g2s(st + t * C::HALF_B, b_q + static_cast<size_t>(kts[t]) * (2 * C::HALF_B),
-                                             C::HALF_B, &full[stage]);
-                            }
+                            for (int t = 0; t < C::TPS; ++t)
+                                bulk_g2s(st + t * C::HALF_B, b_q + static_cast<size_t>(kts[t]) * (2 * C::HALF_B),
+                                         C::HALF_B, &full[stage]);
                             bulk_g2s(st + C::STAGE_B, a_unit + static_cast<size_t>(f) * (2 * C::TPS * TC_ROWS),
                                      C::STAGE_A, &full[stage]);
                         }
@@ -343,101 +336,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 10), pt_fills);
             if (p.dbg & 4) p.prof[10] = static_cast<long long>(p.q_total) * (p.tile_ptr[1] / C::TPS);  // probe: n_rb = 1
         }
-    } else if (warp >= TC_GATHER_WARP0 && warp < TC_MMA_WARP) {
-        // ------------------------------------------------------------ row gather: digit records -> MMA-ready tiles
-        // Gather warp g fills k-tiles 2g and 2g+1 of every stage.  One LDGSTS of the warp moves 16 source rows x two
-        // 16-byte chunks: lanes 0..15 / 16..31 take the even / odd chunk of a 32-byte piece of rows 16 rg + (lane & 15),
-        // so every 32-byte sector that leaves L2 is used whole, and the eight lanes of a quarter warp write eight
-        // consecutive 16-byte core-matrix rows (conflict-free).  The source row indices of fill i+1 are loaded
-        // before the copies of fill i are issued, so their L2 latency never sits between two stages.
-        if (GATHER) {
-            constexpr int HC = 2 * D;    // 16-byte chunks per row of this CTA's half tile
-            constexpr int REC = 64 * D;  // bytes of one (node, column group) record
-            const int gw = warp - TC_GATHER_WARP0;
-            const int klo = lane & 15, chi = lane >> 4;
-            // chunk (k = 16 rg + klo, c = 2 cp + chi) of a half tile sits at 16 * ((k >> 3) * HC * 8 + c * 8 + (k & 7))
-            const uint32_t lane_off = static_cast<uint32_t>(((klo >> 3) * HC * 8 + chi * 8 + (klo & 7)) * 16);
-            int32_t* const my_kt = s_kt + gw * (TC_KT_SMEM / TC_GATHER_WARPS);
-            constexpr int MY_KT = TC_KT_SMEM / TC_GATHER_WARPS;
-            const size_t src_stride = static_cast<size_t>(p.n_kt) * TC_KT;
-            uint32_t stage = 0, phase = 0, uit = 0;
-            while (true) {
-                const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
-                mbar_wait_cluster(&sfull[sl], spar);
-                const int rb = s_unit[sl].rb, cg = s_unit[sl].cg, q0 = s_unit[sl].q0, q1 = s_unit[sl].q1,
-                          t0 = s_unit[sl].t0, nfills = s_unit[sl].nfills;
-                __syncwarp();
-                if (lane == 0) {
-                    if (leader)
-                        mbar_arrive(&sempty[sl]);
-                    else
-                        mbar_arrive_cluster(ld_sempty + sl * 8);
-                }
-                ++uit;
-                if (rb < 0) break;
-                if (p.dbg & 4) continue;
-                // this warp's k-tile ids of the unit: entry 2 f + t = k-tile of (fill f, tile 2 gw + t)
-                for (int i = lane; i < min(2 * nfills, MY_KT); i += 32)
-                    my_kt[i] = p.tile_kt[t0 + (i >> 1) * C::TPS + gw * 2 + (i & 1)];
-                __syncwarp();
-                const int8_t* const dcg =
-                    p.dig + static_cast<size_t>(cg) * p.n * REC + rank * (REC / 2) + chi * 16;
-                auto load_idx = [&](int q, int f, int32_t (&dst)[2][4]) {
-                    const int32_t* const sq = p.src_idx + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * src_stride);
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-                        const int i = 2 * f + t;
-                        const int kt = i < MY_KT ? my_kt[i] : p.tile_kt[t0 + f * C::TPS + gw * 2 + t];
-#pragma unroll
-                        for (int rg = 0; rg < 4; ++rg) dst[t][rg] = __ldg(sq + static_cast<size_t>(kt) * TC_KT + rg * 16 + klo);
-                    }
-                };
-                int32_t nxt[2][4];
-                int q = q0, f = 0;
-                load_idx(q, f, nxt);
-                const int total = (q1 - q0) * nfills;
-                for (int it = 0; it < total; ++it) {
-                    int32_t cur[2][4];
-#pragma unroll
-                    for (int t = 0; t < 2; ++t)
-#pragma unroll
-                        for (int rg = 0; rg < 4; ++rg) cur[t][rg] = nxt[t][rg];
-                    if (++f == nfills) {
-                        f = 0;
-                        ++q;
-                    }
-                    if (it + 1 < total) load_idx(q, f, nxt);
-                    mbar_wait(&empty[stage], phase ^ 1u);
-                    const uint32_t sbase = smem_u32(sB + stage * C::STAGE) + lane_off;
-#pragma unroll
-                    for (int t = 0; t < 2; ++t) {
-#pragma unroll
-                        for (int rg = 0; rg < 4; ++rg) {
-                            const int32_t src = cur[t][rg];
-                            const int8_t* const g = dcg + static_cast<size_t>(src < 0 ? 0 : src) * REC;
-                            const uint32_t nbytes = src < 0 ? 0u : 16u;
-                            const uint32_t dst = sbase + static_cast<uint32_t>((gw * 2 + t) * C::HALF_B +
-                                                                               rg * 2 * HC * 8 * 16);
-#pragma unroll
-                            for (int cp = 0; cp < D; ++cp) cp_async16(dst + cp * 16 * 16, g + cp * 32, nbytes);
-                        }
-                    }
-                    cp_async_mbar_arrive_noinc(&full[stage]);
-                    if (++stage == C::STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
-                }
-            }
-        }
     } else if (warp >= TC_EXP_WARP0 && warp < TC_PROD_WARP) {
         // ------------------------------------------------------------ A expanders: bits -> int8 0/1 in TMEM
         const int quarter = warp - TC_EXP_WARP0;
         const int r = quarter * 32 + lane;
         const uint32_t t_lane = tbase + (static_cast<uint32_t>(quarter * 32) << 16);
-        const uint32_t lane_lut = smem_u32(smem + C::OFF_LUT) + (lane % TC_LUT_REP) * 8;
         uint32_t aslot = 0, aphase = 0, stage = 0, phase = 0, uit = 0;
-        long long xt_wait = 0, xt_st = 0, xt_full = 0;
+        long long xt_wait = 0, xt_st = 0, xt_full = 0, xt_alu = 0;
         const long long xt_start = PROF ? clock64() : 0;
         while (true) {
             const uint32_t sl = uit % TC_SCHED, spar = (uit / TC_SCHED) & 1u;
@@ -453,7 +358,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
             ++uit;
             if (rb < 0) break;
             // Software pipeline over half fills: the TMEM store of half h is in flight while half h+1 is expanded
-            // (table lookups), so neither the tcgen05.st latency nor the lookups sit on the critical path alone.
+            // (byte permutes), so neither the tcgen05.st latency nor the permutes sit on the critical path alone.
             auto publish = [&](uint32_t slot) {   // the store into `slot` was issued earlier
                 tmem_st_wait();
                 tc_fence_before();
@@ -471,9 +376,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 for (int f = 0; f < nfills; ++f) {
                     // the bit tiles of this fill arrive in the smem stage together with the gathered operand
                     TC_TIMED(KIND, xt_full, mbar_wait(&full[stage], phase));
-                    // the gathered rows were written by LDGSTS (generic proxy); the MMA reads them through the async
-                    // proxy and is released by this warp's afull arrive below
-                    if (GATHER) fence_proxy_async_smem();
                     const uint64_t* const sbits =
                         reinterpret_cast<const uint64_t*>(sB + stage * C::STAGE + C::STAGE_B) + r;
                     uint64_t w[C::TPS];
@@ -488,9 +390,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 #pragma unroll
                     for (int h = 0; h < C::TPS / TC_APS; ++h) {
                         uint32_t e[TC_APS][16];
+                        const long long xa0 = PROF ? clock64() : 0;
+                        if (p.dbg & 8) {  // timing experiment: no expansion work (results are garbage)
 #pragma unroll
-                        for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], lane_lut, e[t]);
-                        if (pending) publish(pending_slot);
+                            for (int t = 0; t < TC_APS; ++t)
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) e[t][c] = static_cast<uint32_t>(w[h * TC_APS + t]);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], e[t]);
+                        }
+                        if (PROF) {  // keep the permutes inside the timed window
+#pragma unroll
+                            for (int t = 0; t < TC_APS; ++t)
+#pragma unroll
+                                for (int c = 0; c < 16; ++c) asm volatile("" ::"r"(e[t][c]));
+                            xt_alu += clock64() - xa0;
+                        }
+                        if (pending) TC_TIMED(KIND, xt_st, publish(pending_slot));
                         TC_TIMED(KIND, xt_wait, mbar_wait(&aempty[aslot], aphase ^ 1u));
                         tc_fence_after();
                         const uint32_t ta = t_lane + tc_acol(aslot);
@@ -512,11 +429,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 3), xt_wait);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 11), xt_st);
             atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 12), xt_full);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 13), xt_alu);
         }
     } else if (warp == TC_MMA_WARP) {
         // ------------------------------------------------------------ MMA issuer (leader only; one elected lane)
         if (leader) {
-            const uint32_t idesc = idesc_i8(TC_PROWS, C::NCOLS, /*a_signed*/ 0, /*b_signed*/ 1, /*a MN*/ 0, /*b MN*/ 1);
+            const uint32_t idesc = idesc_i8(TC_PROWS, C::NCOLS, /*a_signed*/ 1, /*b_signed*/ 1, /*a MN*/ 0, /*b MN*/ 1);
             const uint64_t b_desc0 = smem_desc_noswz(smem_u32(sB), p.b_lbo, p.b_sbo);
             const uint32_t b_ks = p.b_kstep >> 4;
             uint32_t stage = 0, aslot = 0, aphase = 0, acc_it = 0, uit = 0;
@@ -643,7 +561,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 uint32_t flagmask = 0;
                 constexpr int CW = 8;  // columns per TMEM load: keeps the live accumulator set at 8 D registers
 #pragma unroll
-                for (int ch = 0; ch < 32 / CW; ++ch) {
+                for (int ch = 0; ch < ((p.dbg & 16) ? 0 : 32 / CW); ++ch) {  // dbg 16: timing experiment, no epilogue work
                     uint32_t acc[D][CW];
 #pragma unroll
                     for (int d = 0; d < D; ++d) tmem_ld8(t_addr + d * 64 + ch * CW, acc[d]);
@@ -944,10 +862,12 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     if (bad) atomicOr(flags, 1);
 }
 
-// fixed-point digits: q = rint(v * 2^shift[j]) as D balanced base-256 int8 digits.
+// fixed-point digits: q = rint(v * 2^shift[j]); stored are the D balanced base-256 int8 digits of -q (the expanded
+// neighborhood operand is 0 / -1, see expand_bits).
 // RECORDS = false (M < 64): plane d at digits + d*n*mpad.
 // RECORDS = true: one 64*D-byte record per (column group, node), digits[(cg * n + r) * 64 D + d * 64 + (j & 63)] --
-// the unit the GEMM's gather warps fetch (a CTA of a pair takes one half of the record).
+// what k_gather copies (192 contiguous bytes at D = 3), one column group's records being a compact N * 64 D byte
+// slab that stays L2-resident while the permutations of a batch are gathered from it.
 template <class T, int D, bool RECORDS>
 __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_t mpad,
                            const int32_t* __restrict__ shift, int8_t* __restrict__ digits) {
@@ -959,7 +879,7 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
         int q = 0;
         if (j < m) {
             const double v = static_cast<double>(b[r * m + j]);
-            if (v == v) q = static_cast<int>(rint(ldexp(v, shift[j])));
+            if (v == v) q = -static_cast<int>(rint(ldexp(v, shift[j])));
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -987,22 +907,47 @@ __device__ __forceinline__ int gather_chunk_pos(int k, int nc) {
     return (nc / HC) * (TC_KT * HC) + (k >> 3) * (HC * 8) + (nc % HC) * 8 + (k & 7);
 }
 
-// Source rows of a batch in the internal node order: src[q][t] = perm[q][order[t]] (identity for perm == nullptr),
-// -1 for the padding positions t >= n of the last k-tile.  What the GEMM's gather warps index the digit records with.
-__global__ void __launch_bounds__(256) k_compose_src(const int32_t* __restrict__ perm,
-                                                     const int32_t* __restrict__ order, int64_t n, int64_t n_pad,
-                                                     int64_t total, int32_t* __restrict__ src) {
-    int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
-    for (; idx < total; idx += step) {
-        const int64_t q = idx / n_pad, t = idx % n_pad;
-        int32_t v = -1;
+// M >= 64: one block builds the tile of one (column group, permutation slot, k-tile) from the 64 source records.
+// Tile row p (the MMA's K position) holds the record of tile entry tc_kpos(p).  The grid runs k-tiles fastest, then
+// permutation slots, then column groups: while the permutations of a batch are gathered, the only records touched
+// are those of one column group (N * 64 D bytes), i.e. the reads are L2 hits and DRAM sees the tile writes only.
+template <int D>
+__global__ void __launch_bounds__(256) k_gather(const int8_t* __restrict__ records, const int32_t* __restrict__ perm,
+                                                const int32_t* __restrict__ order, int64_t n, int32_t n_kt,
+                                                int32_t n_cg, int8_t* __restrict__ bcat) {
+    constexpr int NC16 = 4 * D;
+    constexpr int CHUNKS = TC_KT * NC16;       // 16-byte chunks per tile
+    // one pad chunk per 8 (a 128-byte core matrix becomes 144 bytes): the NC16 chunks of a record, which land 128
+    // bytes apart in the tile, then fall into different banks
+    __shared__ uint4 s_tile[CHUNKS + CHUNKS / 8];
+    __shared__ int32_t s_src[TC_KT];
+    const int kt = blockIdx.x;
+    const int q = blockIdx.y;
+    const int cg = blockIdx.z;
+    if (threadIdx.x < TC_KT) {
+        const int64_t t = static_cast<int64_t>(kt) * TC_KT + tc_kpos(threadIdx.x);
+        int32_t src = -1;
         if (t < n) {
             const int64_t node = order ? order[t] : t;  // internal position t holds the caller's node `node`
-            v = perm ? perm[q * n + node] : static_cast<int32_t>(node);
+            src = perm ? perm[static_cast<int64_t>(q) * n + node] : static_cast<int32_t>(node);
         }
-        src[idx] = v;
+        s_src[threadIdx.x] = src;
     }
+    __syncthreads();
+    const uint4* const rec = reinterpret_cast<const uint4*>(records + static_cast<size_t>(cg) * n * (64 * D));
+    for (int idx = threadIdx.x; idx < CHUNKS; idx += blockDim.x) {
+        const int k = idx / NC16, nc = idx % NC16;  // NC16 consecutive threads read one contiguous record
+        const int32_t src = s_src[k];
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (src >= 0) v = __ldg(rec + static_cast<size_t>(src) * NC16 + nc);
+        const int at = gather_chunk_pos<D>(k, nc);
+        s_tile[at + (at >> 3)] = v;
+    }
+    __syncthreads();
+    // streaming stores: the tiles are read by the GEMM much later; they must not evict the records from L2
+    const size_t slot = static_cast<size_t>(q) * n_cg + cg;
+    uint4* dst = reinterpret_cast<uint4*>(bcat + (slot * n_kt + kt) * (TC_KT * 64 * D));
+    for (int i = threadIdx.x; i < CHUNKS; i += blockDim.x) __stcs(dst + i, s_tile[i + (i >> 3)]);
 }
 
 // M < 64: a slot holds pps = 64 / mpad permutations of all attributes; byte-wise assembly (tiny problems only)
@@ -1020,7 +965,7 @@ __global__ void __launch_bounds__(256) k_gather_small(const int8_t* __restrict__
     const size_t plane = static_cast<size_t>(n) * mpad;
     for (int idx = threadIdx.x; idx < CHUNKS; idx += blockDim.x) {
         const int k = idx / NC16, nc = idx % NC16;
-        const int64_t t = static_cast<int64_t>(kt) * TC_KT + k;
+        const int64_t t = static_cast<int64_t>(kt) * TC_KT + tc_kpos(k);  // tile row k = the MMA's K position
         const int d = nc >> 2, jc = nc & 3;
         uint32_t w[4] = {0, 0, 0, 0};
         if (t < n) {
@@ -1086,44 +1031,38 @@ static void print_prof(sb_ctx* ctx, const long long* d_prof, const char* what) {
     const double fills = std::max<double>(1.0, static_cast<double>(h[10]));
     fprintf(stderr,
             "[sb_trace] %s: cycles per fill (%d k-tiles): producer %.0f (wait empty %.0f) | expander %.0f (wait full "
-            "%.0f, wait aempty %.0f, tmem st %.0f) | mma %.0f (wait A %.0f, wait tempty %.0f) | epilogue %.0f (wait "
-            "tfull %.0f)\n",
+            "%.0f, wait aempty %.0f, publish %.0f, expand alu %.0f) | mma %.0f (wait A %.0f, wait tempty %.0f) | "
+            "epilogue %.0f (wait tfull %.0f)\n",
             what, TC_TPS, h[0] / fills, h[1] / fills, h[2] / fills, h[12] / fills, h[3] / fills, h[11] / fills,
+            h[13] / fills,
             h[4] / fills, h[5] / fills, h[7] / fills, h[8] / fills, h[9] / fills);
 }
 
-template <int D, int KIND, bool SMALL_M, bool PROF, bool GATHER>
+template <int D, int KIND, bool SMALL_M, bool PROF>
 static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
     using C = TcCfg<D>;
     static bool configured = false;
     if (!configured) {
-        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M, PROF, GATHER>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        SB_CUDA(cudaFuncSetAttribute(k_gemm<D, KIND, SMALL_M, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     C::SMEM));
         configured = true;
     }
     KernelTimer kt(ctx, SB_K_GEMM);
     // `grid` counts CTA pairs; the kernel carries __cluster_dims__(2, 1, 1)
-    k_gemm<D, KIND, SMALL_M, PROF, GATHER><<<2 * grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
+    k_gemm<D, KIND, SMALL_M, PROF><<<2 * grid, TC_THREADS, C::SMEM, ctx->stream>>>(gp);
     SB_LAUNCH_CHECK(ctx);
 }
 
-// in-kernel row gather (gp.dig set): whole column groups only; pre-gathered tiles (gp.bcat): M < 64 and self-tests
 template <int D, bool PROF>
 static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams& gp, int grid) {
-    const bool gather = gp.dig != nullptr;
-    SB_CHECK(!(gather && small_m), "internal error: row gather with M < 64");
     if (kind == TCK_RAW)
-        gather ? launch_gemm<D, TCK_RAW, false, PROF, true>(ctx, gp, grid)
-               : launch_gemm<D, TCK_RAW, false, PROF, false>(ctx, gp, grid);
-    else {
-        SB_CHECK(gather || small_m, "internal error: column groups of 64 take the in-kernel row gather");
-        if (kind == TCK_STORE)
-            small_m ? launch_gemm<D, TCK_STORE, true, false, false>(ctx, gp, grid)
-                    : launch_gemm<D, TCK_STORE, false, false, true>(ctx, gp, grid);
-        else
-            small_m ? launch_gemm<D, TCK_COUNT, true, PROF, false>(ctx, gp, grid)
-                    : launch_gemm<D, TCK_COUNT, false, PROF, true>(ctx, gp, grid);
-    }
+        launch_gemm<D, TCK_RAW, false, PROF>(ctx, gp, grid);
+    else if (kind == TCK_STORE)
+        small_m ? launch_gemm<D, TCK_STORE, true, false>(ctx, gp, grid)
+                : launch_gemm<D, TCK_STORE, false, false>(ctx, gp, grid);
+    else
+        small_m ? launch_gemm<D, TCK_COUNT, true, PROF>(ctx, gp, grid)
+                : launch_gemm<D, TCK_COUNT, false, PROF>(ctx, gp, grid);
 }
 
 static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid) {
@@ -1154,22 +1093,29 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
         launch_gemm_k<3, false>(ctx, kind, small_m, gp, grid);
 }
 
-// Operand of a batch of permutations.  Column groups of 64 (M >= 64): only the source-row table of the batch is
-// built (the GEMM gathers the rows itself).  M < 64: the packed tiles are assembled in HBM (tiny problems).
-static void prepare_operand(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms) {
-    KernelTimer kt(ctx, SB_K_GATHER);
+// Gathered operand tiles of a batch of permutations -> bcat, on stream st
+static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms, int8_t* bcat,
+                          cudaStream_t st) {
+    KernelTimer kt(ctx, SB_K_GATHER, st);
     if (pl->mpad >= 64) {
-        const int64_t n_pad = static_cast<int64_t>(pl->n_kt) * TC_KT;
-        const int64_t total = n_pad * batch_perms;
-        ctx->ws_src.reserve(static_cast<size_t>(total));
-        const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(total, 256), ctx->num_sms * 16));
-        k_compose_src<<<blocks, 256, 0, ctx->stream>>>(perm, pl->order, pl->n, n_pad, total, ctx->ws_src.p);
+        const int nq = slots / pl->n_cg;
+        dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(nq), static_cast<unsigned>(pl->n_cg));
+        SB_CHECK(grid.y <= 65535 && grid.z <= 65535, "too many column groups / permutations in one batch");
+#define SB_G(DD) \
+    k_gather<DD><<<grid, 256, 0, st>>>(pl->digits.p, perm, pl->order, pl->n, pl->n_kt, pl->n_cg, bcat)
+        if (pl->D == 1)
+            SB_G(1);
+        else if (pl->D == 2)
+            SB_G(2);
+        else
+            SB_G(3);
+#undef SB_G
     } else {
         dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
         SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
 #define SB_G(DD)                                                                                                  \
-    k_gather_small<DD><<<grid, 256, 0, ctx->stream>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt,   \
-                                                      pl->pps, pl->log2_mpad, batch_perms, ctx->ws_bcat.p)
+    k_gather_small<DD><<<grid, 256, 0, st>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt, pl->pps,   \
+                                             pl->log2_mpad, batch_perms, bcat)
         if (pl->D == 1)
             SB_G(1);
         else if (pl->D == 2)
@@ -1187,12 +1133,7 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.a_bits = pl->a_bits.p;
     gp.tile_ptr = pl->tile_ptr.p;
     gp.tile_kt = pl->tile_kt.p;
-    if (pl->mpad >= 64) {
-        gp.dig = pl->digits.p;
-        gp.src_idx = ctx->ws_src.p;
-    } else {
-        gp.bcat = ctx->ws_bcat.p;
-    }
+    gp.bcat = ctx->ws_bcat.p;
     gp.n_kt = pl->n_kt;
     gp.n_rb = pl->n_rb;
     gp.n_cg = pl->n_cg;
@@ -1423,9 +1364,9 @@ static TcPlan* build_plan(sb_enrich* e) {
         // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
         const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
         const int64_t slots1 = slots_for(pl, 1);
-        if (pl->mpad < 64) ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
+        ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
         pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_PROWS * pl->mpad);
-        prepare_operand(ctx, pl, nullptr, static_cast<int>(slots1), 1);
+        launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1, ctx->ws_bcat.p, st);
         GemmParams gp = base_params(e, pl);
         gp.mode = TCM_STORE;
         gp.q_total = 1;
@@ -1454,20 +1395,18 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_first, int 
     gp.rb0 = rb0;
     gp.n_rb = n_rb;
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
-    if (q_first) {  // slot offset into the operand of the batch
-        if (gp.src_idx) gp.src_idx += static_cast<size_t>(q_first) * pl->n_kt * TC_KT;
-        if (gp.bcat) gp.bcat += static_cast<size_t>(q_first) * pl->n_cg * pl->n_kt * tile_b;
-    }
-    // Unit order (decode_unit): band of row blocks, then q chunk, then column group, then row block -- the CTA pairs
-    // that run concurrently work on the same column group, whose digit records (N x 64 D bytes, 3.8 MB at C3) are
-    // what they all gather from: the slab stays L2-resident whatever the number of slots per unit.  Slots per unit
-    // (q_per) only trades per-unit epilogue overhead (observed-score preload, count flush) against load balance:
-    // up to 64 (SB_Q_PER overrides), fewer when the launch would not give every SM pair a few units.
+    // slot offset into the gathered operand of the batch
+    gp.bcat += static_cast<size_t>(q_first) * pl->n_cg * pl->n_kt * tile_b;
+    // L2 blocking (see decode_unit; bands are chosen in build_plan).  The number of slots per unit (q_per) trades
+    // per-unit epilogue overhead (observed-score preload, count flush) against the gathered slab a band touches per
+    // (q chunk, column group): measured on C3, 13+ slots per unit (64 MB slabs, the default; SB_SLAB_MB overrides)
+    // run 20 % faster than 4 and the 5-stage ring still hides the L2 / HBM latency.
     const bool whole = rb0 == 0 && n_rb == pl->n_rb;
     gp.band_rb = whole ? pl->band_rb : n_rb;
     gp.n_bands = whole ? pl->n_bands : 1;
-    static const int q_per_max = getenv("SB_Q_PER") ? std::max(1, atoi(getenv("SB_Q_PER"))) : 64;
-    int q_per = q_per_max;
+    const double slab = std::max(1, pl->band_kt) * static_cast<double>(tile_b);  // gathered bytes per (slot, group)
+    static const double slab_mb = getenv("SB_SLAB_MB") ? atof(getenv("SB_SLAB_MB")) : 64.0;
+    int q_per = static_cast<int>(std::max(1.0, std::min(64.0, slab_mb * (1 << 20) / slab)));
     const int base_units = n_rb * pl->n_cg;
     const int want_chunks = static_cast<int>(sb_ceil_div(4 * (ctx->num_sms / 2), base_units));
     q_per = std::min<int>(q_per, std::max<int>(1, q_total / std::max(1, want_chunks)));
@@ -1485,6 +1424,8 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_first, int 
         fprintf(stderr, "[sb_trace] gemm schedule: n_rb %d n_cg %d q_total %d q_per %d band_rb %d n_bands %d units %lld\n",
                 n_rb, pl->n_cg, q_total, gp.q_per, gp.band_rb, gp.n_bands, (long long)units);
     }
+    static const int dbg = getenv("SB_DBG") ? atoi(getenv("SB_DBG")) : 0;  // timing experiments only (8, 16)
+    gp.dbg = dbg;
     launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms / 2)));
     if (trace) print_prof(ctx, d_prof.p, "batch gemm");
 }
@@ -1517,31 +1458,38 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
     PhaseTrace* tr_ws = new PhaseTrace(ctx, "tc.workspace");
 
-    // Permutations per launch.  Column groups of 64: the operand of a batch is only its source-row table
-    // (4 (N + pad) bytes per permutation, at most 1 GiB per launch).  M < 64: pre-gathered tiles, <= ~1/8 of the free
-    // memory seen at the first null of this context (cudaMemGetInfo was seen to take hundreds of ms on a busy device).
+    // Batches: the gathered tiles of a batch take <= ~1/8 of the free memory seen at the first null of this context (at
+    // most 16 GiB; cudaMemGetInfo was seen to take hundreds of ms on a busy device: ask once per context).  Per batch:
+    // gather -> GEMM -> fix-ups, all on the context's stream and without a host synchronisation in between (the fix-up
+    // kernel reads the bucket counters on the device; they are logged and looked at once, after the last batch).
+    // Measured and dropped: the gather of batch b + 1 and the fix-ups of batch b - 1 on a second stream under the GEMM
+    // of batch b (double-buffered operand and lists).  The kernels do overlap -- their small blocks fit next to a
+    // k_gemm CTA -- but the step does not get shorter (C3: 290 / 289 / 292 ms for none / fix-ups / both overlapped):
+    // the GEMM slows down by what the side work takes, because the chip runs at its 1 kW power cap (SM clock 1.6-1.7
+    // of 1.965 GHz, sw_power_cap active) and a step costs the same energy either way.
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
-    int64_t pb;
-    if (pl->mpad >= 64) {
-        pb = std::max<int64_t>(1, (1ll << 30) / (static_cast<int64_t>(pl->n_kt) * TC_KT * 4));
-    } else {
-        if (ctx->bcat_budget == 0) {
-            size_t free_b = 0, total_b = 0;
-            SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
-        }
-        const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes), 16ull << 30),
-                                       ctx->ws_bcat.n);
-        const int64_t max_slots = std::min<int64_t>(std::max<int64_t>(1, static_cast<int64_t>(budget / slot_bytes)), 65535);
-        pb = max_slots * pl->pps;
+    if (ctx->bcat_budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
     }
+    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes * slots_for(pl, 1)),
+                                                    16ull << 30),
+                                   ctx->ws_bcat.n);
+    int64_t max_slots = std::max<int64_t>(slots_for(pl, 1), static_cast<int64_t>(budget / slot_bytes));
+    max_slots = std::min<int64_t>(max_slots, 65535ll * (pl->mpad >= 64 ? pl->n_cg : 1));
+    int64_t pb = pl->mpad >= 64 ? max_slots / pl->n_cg : max_slots * pl->pps;
     pb = std::max<int64_t>(1, std::min<int64_t>(pb, 16384));  // 16-bit per-unit counters
     pb = std::min(pb, num_perm);
-    if (pl->mpad < 64) ctx->ws_bcat.reserve(static_cast<size_t>(slots_for(pl, pb)) * slot_bytes);
+    const int64_t n_batches = sb_ceil_div(num_perm, pb);
+    pb = sb_ceil_div(num_perm, n_batches);  // equal batches
+    ctx->ws_bcat.reserve(static_cast<size_t>(slots_for(pl, pb)) * slot_bytes);
     // the fix-up list (and, unless the caller supplies the packed array, the packed counters) live in context scratch
     ctx->ws_flag_ij.reserve(pl->flag_cap);
     ctx->ws_flag_p.reserve(pl->flag_cap);
+    DevBuf<unsigned int> count_log;  // bucket counters of every batch, read back once at the end
+    count_log.reserve(static_cast<size_t>(n_batches) * pl->n_cg);
     if (packed) {
         pl->cpk = packed;
     } else {
@@ -1550,71 +1498,100 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         pl->cpk = ctx->ws_cpk.p;
     }
     pl->cpk_perms = 0;
+    if (pl->any_inexact) enrich_transposed(e);
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
     const int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;  // includes padding tiles
     const unsigned int cap_cg = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
-    std::vector<unsigned int> h_flags(pl->n_cg);
-    for (int64_t p0 = 0; p0 < num_perm; p0 += pb) {
-        const int64_t np = std::min(pb, num_perm - p0);
-        const int32_t* perm = perm_dev + p0 * e->n;
-        const int slots = static_cast<int>(slots_for(pl, np));
-        const int q_total = pl->mpad >= 64 ? static_cast<int>(np) : slots;
+    auto batch_of = [&](int64_t b, const int32_t*& perm, int64_t& np, int& slots, int& q_total) {
+        const int64_t p0 = b * pb;
+        np = std::min(pb, num_perm - p0);
+        perm = perm_dev + p0 * e->n;
+        slots = static_cast<int>(slots_for(pl, np));
+        q_total = pl->mpad >= 64 ? static_cast<int>(np) : slots;
+    };
+    auto gather_batch = [&](int64_t b, cudaStream_t on) {
+        const int32_t* perm;
+        int64_t np;
+        int slots, q_total;
+        batch_of(b, perm, np, slots, q_total);
+        launch_gather(ctx, pl, perm, slots, static_cast<int>(np), ctx->ws_bcat.p, on);
+    };
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int32_t* perm;
+        int64_t np;
+        int slots, q_total;
+        batch_of(b, perm, np, slots, q_total);
         {
-            PhaseTrace tr(ctx, "tc.batch.operand");
-            prepare_operand(ctx, pl, perm, slots, static_cast<int>(np));
+            PhaseTrace tr(ctx, "tc.batch.gather");
+            gather_batch(b, st);
         }
         PhaseTrace tr_b(ctx, "tc.batch.gemm+fixup");
-        // fix-ups bucket by bucket: the flags of one column group touch 64 attribute columns only, so the scattered
-        // row reads of the fix-up kernel stay L2-resident
-        auto run_fixups = [&](const int32_t* perm_base) -> int64_t {
-            if (!pl->any_inexact) return 0;  // exactly representable columns never flag
-            SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
-                                    cudaMemcpyDeviceToHost, st));
-            SB_CUDA(cudaStreamSynchronize(st));
-            int64_t total = 0;
-            for (int cg = 0; cg < pl->n_cg; ++cg) {
-                if (h_flags[cg] > cap_cg) return -1;
-                total += h_flags[cg];
-            }
-            for (int cg = 0; cg < pl->n_cg; ++cg)
-                if (h_flags[cg])
-                    fixup_flags(e, perm_base, ctx->ws_flag_ij.p + static_cast<size_t>(cg) * cap_cg,
-                                ctx->ws_flag_p.p + static_cast<size_t>(cg) * cap_cg, h_flags[cg], cneg, cpos,
-                                packed);
-            return total;
-        };
-        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-        if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);
+        if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);  // 16-bit fields about to overflow
         pl->cpk_perms += np;
+        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
         run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
         ktile_iters += tiles_per_pass * q_total;
-        const int64_t got = run_fixups(perm);
-        if (got >= 0) {
-            flagged += got;
-        } else {
-            // A bucket overflowed: nothing of the list is used.  Re-emit the flags (without re-adding the decided
-            // counts) slot by slot and in row-block ranges whose worst case -- every cell of the range flagged --
-            // fits a bucket.
-            ++overflow_batches;
-            const int rb_step = std::max<int>(1, static_cast<int>(cap_cg / (TC_PROWS * 64)));
-            for (int q = 0; q < q_total; ++q) {
-                const int bp = pl->mpad >= 64
-                                   ? 1
-                                   : static_cast<int>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
-                // the batch-local permutation index of a flag is relative to slot q: offset the index base instead
-                const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
-                for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
-                    const int nrb = std::min(rb_step, pl->n_rb - rb0);
-                    SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-                    run_batch_gemm(e, pl, TCM_FLAG, q, 1, bp, rb0, nrb);
-                    const int64_t gq = run_fixups(perm_q);
-                    SB_CHECK(gq >= 0, "internal error: flag list overflow in single-slot recovery");
-                    flagged += gq;
-                }
-                ktile_iters += tiles_per_pass;
+        if (pl->any_inexact) {
+            SB_CUDA(cudaMemcpyAsync(count_log.p + b * pl->n_cg, pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
+                                    cudaMemcpyDeviceToDevice, st));
+            fixup_flag_buckets(e, st, perm, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->n_cg, cap_cg,
+                               cneg, cpos, packed);
+        }
+    }
+
+    // ---- bucket counters of all batches: statistics, and the (rare) overflowed buckets, which the fix-up kernel skipped
+    std::vector<unsigned int> h_log(static_cast<size_t>(n_batches) * pl->n_cg, 0u);
+    if (pl->any_inexact) {
+        SB_CUDA(cudaMemcpyAsync(h_log.data(), count_log.p, h_log.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<unsigned int> h_flags(pl->n_cg);
+    for (int64_t b = 0; b < n_batches; ++b) {
+        std::vector<char> redo(pl->n_cg, 0);
+        bool any = false;
+        for (int cg = 0; cg < pl->n_cg; ++cg) {
+            const unsigned int c = h_log[b * pl->n_cg + cg];
+            if (c > cap_cg) {
+                redo[cg] = 1;
+                any = true;
+            } else {
+                flagged += c;
             }
+        }
+        if (!any) continue;
+        // Overflowed buckets: re-emit the flags of this batch (without re-adding the decided counts) slot by slot and
+        // in row-block ranges whose worst case -- every cell of the range flagged -- fits a bucket, and fix up the
+        // overflowed buckets only (the others are already done).
+        ++overflow_batches;
+        const int32_t* perm;
+        int64_t np;
+        int slots, q_total;
+        batch_of(b, perm, np, slots, q_total);
+        gather_batch(b, st);
+        const int rb_step = std::max<int>(1, static_cast<int>(cap_cg / (TC_PROWS * 64)));
+        for (int q = 0; q < q_total; ++q) {
+            const int bp = pl->mpad >= 64 ? 1
+                                          : static_cast<int>(std::min<int64_t>(pl->pps, np - static_cast<int64_t>(q) * pl->pps));
+            // the batch-local permutation index of a flag is relative to slot q: offset the index base instead
+            const int32_t* perm_q = perm + static_cast<int64_t>(q) * pl->pps * e->n;
+            for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
+                const int nrb = std::min(rb_step, pl->n_rb - rb0);
+                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
+                run_batch_gemm(e, pl, TCM_FLAG, q, 1, bp, rb0, nrb);
+                SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
+                                        cudaMemcpyDeviceToHost, st));
+                SB_CUDA(cudaStreamSynchronize(st));
+                for (int cg = 0; cg < pl->n_cg; ++cg) {
+                    if (!redo[cg] || !h_flags[cg]) continue;
+                    SB_CHECK(h_flags[cg] <= cap_cg, "internal error: flag list overflow in single-slot recovery");
+                    fixup_flags(e, perm_q, ctx->ws_flag_ij.p + static_cast<size_t>(cg) * cap_cg,
+                                ctx->ws_flag_p.p + static_cast<size_t>(cg) * cap_cg, h_flags[cg], cneg, cpos, packed);
+                    flagged += h_flags[cg];
+                }
+            }
+            ktile_iters += tiles_per_pass;
         }
     }
     if (!packed) flush_counts(e, pl, cneg, cpos);
@@ -1656,13 +1633,15 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
             for (int rank = 0; rank < 2; ++rank)
                 at[((static_cast<size_t>(kt / TC_TPS) * 2 + rank) * TC_TPS + kt % TC_TPS) * TC_ROWS + r] = w;
         }
+    // tile row k (the MMA's K position) holds operand row tc_kpos(k); the expanded A is 0 / -1, so the raw
+    // accumulators are the NEGATED product (production stores the digits of -q instead) and are negated below
     const int hc = ncols / 32;  // 16-column chunks per half tile
     for (int kt = 0; kt < ktiles; ++kt)
         for (int k = 0; k < TC_KT; ++k)
             for (int c = 0; c < ncols; ++c) {
                 const int nc = c >> 4;
                 bt[static_cast<size_t>(kt) * tile_b + (nc / hc) * (tile_b / 2) + (k >> 3) * (hc * 128) + (nc % hc) * 128 +
-                   (k & 7) * 16 + (c & 15)] = b_host[static_cast<size_t>(kt * TC_KT + k) * ncols + c];
+                   (k & 7) * 16 + (c & 15)] = b_host[static_cast<size_t>(kt * TC_KT + tc_kpos(k)) * ncols + c];
             }
     std::vector<int32_t> ptr = {0, kt_pad}, kts(kt_pad);
     for (int i = 0; i < kt_pad; ++i) kts[i] = std::min(i, ktiles - 1);
@@ -1708,7 +1687,7 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     SB_CUDA(cudaMemcpyAsync(both.data(), d_out.p, both.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     const size_t half_elems = static_cast<size_t>(TC_ROWS) * ncols;
-    memcpy(d_host, both.data(), half_elems * sizeof(int32_t));
+    for (size_t i = 0; i < half_elems; ++i) d_host[i] = -both[i];
     if (!(variant & 2))
         SB_CHECK(memcmp(both.data(), both.data() + half_elems, half_elems * sizeof(int32_t)) == 0,
                  "sb_selftest_mma_i8: the two CTAs of the pair disagree");

@@ -375,7 +375,6 @@ int sb_ctx_release_memory(sb_ctx* ctx) {
     ctx->bind();
     SB_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->ws_bcat.release();
-    ctx->ws_src.release();
     ctx->ws_flag_ij.release();
     ctx->ws_flag_p.release();
     ctx->ws_cpk.release();

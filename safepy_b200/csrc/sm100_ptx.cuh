@@ -124,20 +124,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-// ---------------------------------------------------------------- 16-byte async copies (LDGSTS)
-// global -> shared without a register round trip, L1 bypassed (.cg); the destination of every 16-byte piece is
-// free, which is what lets a row gather land directly in the tensor core's core-matrix order.  src_bytes = 0 writes
-// 16 zero bytes (the global address must still be valid).
-__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gmem_src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gmem_src), "r"(src_bytes)
-                 : "memory");
-}
-// One arrival on `bar` once every cp.async this thread has issued so far has landed; .noinc: the arrival is one of
-// the barrier's expected count (the barrier is initialised with one arrival per copying thread).
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

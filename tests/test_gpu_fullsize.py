@@ -163,7 +163,7 @@ nb = _lib.Neighborhoods(ctx, n).upload_packed(g["nb_layout"])
 # values on a coarse non-dyadic grid: many near-ties, i.e. many flagged comparisons
 rng = np.random.default_rng(1)
 attrs = (np.round(rng.standard_normal((n, 70)) * 3) * 0.1).astype(np.float32)
-rows = make_perm_rows(attrs, 12, 3)
+rows = make_perm_rows(attrs, 150, 3)
 plan = _lib.Enrichment(nb, attrs)
 tneg, tpos = plan.perm_counts(rows, "sum", "tc")
 st = plan.stats()

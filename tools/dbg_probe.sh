@@ -1,0 +1,9 @@
+#!/bin/bash
+# timing experiments on the production null (C3).  Results with SB_DBG != 0 are garbage.
+run() {
+  env "$@" python bench.py --no-cpu-baseline --no-safe-api --no-parity --steps 3 --warmup 1 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print('$*', round(d['ms_per_step'],1), {k: round(v,1) for k,v in d['roofline']['kernel_ms_per_step'].items()}, d['clocks']['sm_mhz'])"
+}
+for ov in 0 1 2; do run SB_OVERLAP=$ov; done
+run SB_OVERLAP=1 SB_SLAB_MB=128
+run SB_OVERLAP=1 SB_SLAB_MB=32

@@ -137,6 +137,11 @@ int sb_enrich_set_node_order(sb_enrich* e, const int32_t* order_host);
 /* compute_neighborhood_score(A, B, type), safe_extras.py:6-33 -> fp64 [n x m] */
 int sb_enrich_score(sb_enrich* e, int score_type, double* out_host);
 int sb_enrich_score_dev(sb_enrich* e, int score_type, double* out_dev);
+/* Observed scores with the node rows sharded over several GPUs: compute rows [row0, row1) into the plan's own [n x m]
+ * score array (returned), let the host program exchange the row blocks in place (all-gather / broadcasts), then declare
+ * the array complete; sb_enrich_null_finalize and sb_enrich_score then use it instead of recomputing every row. */
+int sb_enrich_observed_rows_dev(sb_enrich* e, int score_type, int64_t row0, int64_t row1, double** scores_dev);
+int sb_enrich_observed_set_ready(sb_enrich* e, int score_type);
 
 /* run_permutations core, safe_extras.py:56-66.
  * perm_rows[p*n + t] = row of B that sits at node t during permutation p (the caller composes the reference's
@@ -187,6 +192,11 @@ int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_
  * place (one NCCL all-reduce over 2 * n * m words), and the number of permutations they hold afterwards.  The caller
  * orders the streams: sb_ctx_synchronize before the collective, its own stream before the next library call. */
 int sb_enrich_null_counts_dev(sb_enrich* e, uint32_t** counts_neg_dev, uint32_t** counts_pos_dev);
+/* The cheaper exchange while the total number of permutations stays below 65536: the open null keeps the permutations
+ * it has counted since its last fold in ONE packed word per cell, (counts_pos << 16) | counts_neg ([n x m] uint32, half
+ * the bytes of the two arrays).  Returns that array and how many permutations it holds; after summing it across the
+ * ranks in place (one all-reduce over n * m words), sb_enrich_null_set_perms(total) declares what it holds now. */
+int sb_enrich_null_packed_dev(sb_enrich* e, uint32_t** counts_packed_dev, int64_t* perms_in_packed);
 int sb_enrich_null_set_perms(sb_enrich* e, int64_t num_perm);
 
 /* run_permutations' index stream (safe_extras.py:46-58) replayed natively on the host: np.random.seed(seed) of

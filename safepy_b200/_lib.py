@@ -70,7 +70,10 @@ SIGNATURES = {
     "sb_enrich_null_add": (C.c_int, [_vp, _vp, _i64]),
     "sb_enrich_null_counts": (C.c_int, [_vp, C.POINTER(_i64), _vp, _vp]),
     "sb_enrich_null_counts_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
+    "sb_enrich_null_packed_dev": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     "sb_enrich_null_set_perms": (C.c_int, [_vp, _i64]),
+    "sb_enrich_observed_rows_dev": (C.c_int, [_vp, C.c_int, _i64, _i64, C.POINTER(_vp)]),
+    "sb_enrich_observed_set_ready": (C.c_int, [_vp, C.c_int]),
     "sb_perm_stream_create": (C.c_int, [_i64, _vp, _i64, C.c_int, C.c_uint32, C.POINTER(_vp)]),
     "sb_perm_stream_destroy": (C.c_int, [_vp]),
     "sb_perm_stream_next": (C.c_int, [_vp, _i64, _vp]),
@@ -421,6 +424,22 @@ class Enrichment:
         neg, pos = _vp(), _vp()
         _check(self.lib, self.lib.sb_enrich_null_counts_dev(self.h, C.byref(neg), C.byref(pos)))
         return int(neg.value), int(pos.value)
+
+    def null_packed_dev(self):
+        """(device address of the packed count words [n, m] (pos << 16 | neg), permutations they hold)."""
+        pk, held = _vp(), _i64()
+        _check(self.lib, self.lib.sb_enrich_null_packed_dev(self.h, C.byref(pk), C.byref(held)))
+        return int(pk.value), held.value
+
+    def observed_rows_dev(self, score_type, row0, row1):
+        """Compute observed-score rows [row0, row1) into the plan's [n, m] fp64 array; returns its device address."""
+        ptr = _vp()
+        _check(self.lib, self.lib.sb_enrich_observed_rows_dev(self.h, SCORE_TYPES[score_type], int(row0), int(row1),
+                                                              C.byref(ptr)))
+        return int(ptr.value)
+
+    def observed_set_ready(self, score_type):
+        _check(self.lib, self.lib.sb_enrich_observed_set_ready(self.h, SCORE_TYPES[score_type]))
 
     def null_set_perms(self, num_perm):
         _check(self.lib, self.lib.sb_enrich_null_set_perms(self.h, int(num_perm)))

@@ -300,7 +300,13 @@ __device__ double hg_sf(const double* __restrict__ lf, double k, double Mt, doub
     return fmin(fmax(result, 0.0), 1.0);
 }
 
-__global__ void __launch_bounds__(256) k_hypergeom(const double* __restrict__ X, const double* __restrict__ colsum,
+// X: the observed counts either as fp64 scores (k_score) or, FIXED, straight from the tensor-core plan's exact
+// fixed-point scores (row order of the plan, per-column binary exponent)
+template <bool FIXED>
+__global__ void __launch_bounds__(256) k_hypergeom(const double* __restrict__ X, const int64_t* __restrict__ xfix,
+                                                   const int32_t* __restrict__ shift,
+                                                   const int32_t* __restrict__ row_of_node, int64_t mpad,
+                                                   const double* __restrict__ colsum,
                                                    const double* __restrict__ nneigh, const double* __restrict__ lf,
                                                    double n_total, int64_t n, int64_t m, double* __restrict__ pv,
                                                    double* __restrict__ nes) {
@@ -309,7 +315,14 @@ __global__ void __launch_bounds__(256) k_hypergeom(const double* __restrict__ X,
     const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (; idx < total; idx += step) {
         const int64_t i = idx / m, j = idx % m;
-        const double p = hg_sf(lf, X[idx] - 1.0, n_total, colsum[j], nneigh[i]);
+        double x;
+        if (FIXED) {
+            const int64_t row = row_of_node ? row_of_node[i] : i;
+            x = ldexp(static_cast<double>(xfix[row * mpad + j]), -shift[j]);
+        } else {
+            x = X[idx];
+        }
+        const double p = hg_sf(lf, x - 1.0, n_total, colsum[j], nneigh[i]);
         if (pv) pv[idx] = p;
         if (nes) nes[idx] = -log10(p);
     }
@@ -515,7 +528,13 @@ void fixup_flag_buckets(sb_enrich* e, cudaStream_t st, const int32_t* perm_dev, 
 static void hypergeom_dev(sb_enrich* e, double* pv_dev, double* nes_dev) {
     sb_ctx* ctx = e->ctx;
     const int64_t n = e->n, m = e->m;
-    const double* X = enrich_observed(e, SB_SCORE_SUM);
+    // X = A @ nan0(B): exact integers.  Annotation matrices are binary, i.e. exactly representable in the tensor-core
+    // plan's fixed point: X then comes from one pass of the digit GEMM (TCK_STORE); anything else takes the fp64 kernel.
+    const int64_t* xfix = nullptr;
+    const int32_t *shift = nullptr, *row_of_node = nullptr;
+    int64_t mpad = 0;
+    const bool fixed = tc_observed_exact(e, &xfix, &shift, &row_of_node, &mpad);
+    const double* X = fixed ? nullptr : enrich_observed(e, SB_SCORE_SUM);
     DevBuf<int32_t> has;
     DevBuf<double> colsum, nneigh, lf;
     DevBuf<unsigned long long> total;
@@ -554,8 +573,12 @@ static void hypergeom_dev(sb_enrich* e, double* pv_dev, double* nes_dev) {
     const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * m, 256), ctx->num_sms * 16));
     {
         KernelTimer kt(ctx, SB_K_HYPERGEOM);
-        k_hypergeom<<<blocks, 256, 0, st>>>(X, colsum.p, nneigh.p, lf.p, static_cast<double>(n_total), n, m, pv_dev,
-                                            nes_dev);
+        if (fixed)
+            k_hypergeom<true><<<blocks, 256, 0, st>>>(nullptr, xfix, shift, row_of_node, mpad, colsum.p, nneigh.p, lf.p,
+                                                      static_cast<double>(n_total), n, m, pv_dev, nes_dev);
+        else
+            k_hypergeom<false><<<blocks, 256, 0, st>>>(X, nullptr, nullptr, nullptr, 0, colsum.p, nneigh.p, lf.p,
+                                                       static_cast<double>(n_total), n, m, pv_dev, nes_dev);
         SB_LAUNCH_CHECK(ctx);
     }
     SB_CUDA(cudaStreamSynchronize(st));

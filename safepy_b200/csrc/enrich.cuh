@@ -75,5 +75,7 @@ void null_count_dev(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm);
 void null_flush(sb_enrich* e);
 void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
                     uint32_t* packed = nullptr);
+bool tc_observed_exact(sb_enrich* e, const int64_t** s0fix, const int32_t** shift, const int32_t** row_of_node,
+                       int64_t* mpad);
 
 }  // namespace sb

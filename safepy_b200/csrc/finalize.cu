@@ -460,6 +460,30 @@ void colcnt_out(sb_ctx* ctx, const int32_t* colcnt, int64_t m, double* num_enric
 }  // namespace
 }  // namespace sb
 
+namespace sb {
+// Permutations of an open streaming null go into ONE packed word per cell (pos << 16 | neg) -- no memset / unpack
+// per piece, and the array that crosses NVLink when the permutations are sharded over several GPUs -- and are folded
+// into the two count arrays before the 16-bit fields could overflow and whenever the counts are read.
+void null_flush(sb_enrich* e) {
+    if (e->null_pk_perms == 0) return;
+    const size_t cells = static_cast<size_t>(e->n) * e->m;
+    unpack_add_counts(e->ctx, e->null_pk.p, static_cast<int64_t>(cells), e->null_cnt.p, e->null_cnt.p + cells);
+    e->null_pk_perms = 0;
+}
+
+void null_count_dev(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm) {
+    for (int64_t p0 = 0; p0 < num_perm;) {
+        if (e->null_pk_perms >= 60000) null_flush(e);
+        const int64_t np = std::min<int64_t>(num_perm - p0, 60000 - e->null_pk_perms);
+        int rc = sb_enrich_perm_counts_packed_dev(e, e->null_score, e->null_engine, perm_dev + p0 * e->n, np,
+                                                  e->null_pk.p);
+        if (rc) fail("%s", sb_last_error());
+        e->null_pk_perms += np;
+        p0 += np;
+    }
+}
+}  // namespace sb
+
 using namespace sb;
 
 extern "C" {
@@ -479,6 +503,9 @@ int sb_enrich_null_begin(sb_enrich* e, int score_type, int engine) {
     const size_t cells = static_cast<size_t>(e->n) * e->m;
     e->null_cnt.reserve(2 * cells);
     SB_CUDA(cudaMemsetAsync(e->null_cnt.p, 0, 2 * cells * sizeof(uint32_t), ctx->stream));
+    e->null_pk.reserve(cells);
+    SB_CUDA(cudaMemsetAsync(e->null_pk.p, 0, cells * sizeof(uint32_t), ctx->stream));
+    e->null_pk_perms = 0;
     e->null_score = score_type;
     e->null_engine = engine;
     e->null_perms = 0;
@@ -493,16 +520,13 @@ int sb_enrich_null_add(sb_enrich* e, const int32_t* perm_rows_host, int64_t num_
     SB_CHECK(num_perm >= 0, "sb_enrich_null_add: num_perm < 0");
     sb_ctx* ctx = e->ctx;
     ctx->bind();
-    const size_t cells = static_cast<size_t>(e->n) * e->m;
     const int64_t piece = std::max<int64_t>(1, (256ll << 20) / e->n);  // <= 1 GiB of indices on the device at a time
     for (int64_t p0 = 0; p0 < num_perm; p0 += piece) {
         const int64_t np = std::min(piece, num_perm - p0);
         e->null_perm.reserve(static_cast<size_t>(np) * e->n);
         SB_CUDA(cudaMemcpyAsync(e->null_perm.p, perm_rows_host + p0 * e->n, static_cast<size_t>(np) * e->n * sizeof(int32_t),
                                 cudaMemcpyHostToDevice, ctx->stream));
-        int rc = sb_enrich_perm_counts_dev(e, e->null_score, e->null_engine, e->null_perm.p, np, e->null_cnt.p,
-                                           e->null_cnt.p + cells);
-        if (rc) fail("%s", sb_last_error());
+        null_count_dev(e, e->null_perm.p, np);
         SB_CUDA(cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next piece
         for (int i = 0; i < 7; ++i) {
             if (i == 2 || i == 3 || i == 4)
@@ -523,6 +547,7 @@ int sb_enrich_null_counts(sb_enrich* e, int64_t* num_perm_out, uint32_t* counts_
     sb_ctx* ctx = e->ctx;
     ctx->bind();
     const size_t cells = static_cast<size_t>(e->n) * e->m;
+    null_flush(e);
     if (num_perm_out) *num_perm_out = e->null_perms;
     if (counts_neg_host) copy_out(ctx, counts_neg_host, e->null_cnt.p, cells * sizeof(uint32_t));
     if (counts_pos_host) copy_out(ctx, counts_pos_host, e->null_cnt.p + cells, cells * sizeof(uint32_t));
@@ -534,8 +559,19 @@ int sb_enrich_null_counts_dev(sb_enrich* e, uint32_t** counts_neg_dev, uint32_t*
     SB_API_BEGIN
     SB_CHECK(e && counts_neg_dev && counts_pos_dev, "sb_enrich_null_counts_dev: NULL argument");
     SB_CHECK(e->null_score >= 0, "sb_enrich_null_counts_dev: no null has been started on this plan");
+    e->ctx->bind();
+    null_flush(e);
     *counts_neg_dev = e->null_cnt.p;
     *counts_pos_dev = e->null_cnt.p + static_cast<size_t>(e->n) * e->m;
+    SB_API_END
+}
+
+int sb_enrich_null_packed_dev(sb_enrich* e, uint32_t** counts_packed_dev, int64_t* perms_in_packed) {
+    SB_API_BEGIN
+    SB_CHECK(e && counts_packed_dev, "sb_enrich_null_packed_dev: NULL argument");
+    SB_CHECK(e->null_score >= 0, "sb_enrich_null_packed_dev: no null has been started on this plan");
+    *counts_packed_dev = e->null_pk.p;
+    if (perms_in_packed) *perms_in_packed = e->null_pk_perms;
     SB_API_END
 }
 
@@ -543,6 +579,10 @@ int sb_enrich_null_set_perms(sb_enrich* e, int64_t num_perm) {
     SB_API_BEGIN
     SB_CHECK(e && num_perm >= 0, "sb_enrich_null_set_perms: bad argument");
     SB_CHECK(e->null_score >= 0, "sb_enrich_null_set_perms: no null has been started on this plan");
+    SB_CHECK(num_perm < 65536 || e->null_pk_perms == 0 || num_perm == e->null_perms,
+             "sb_enrich_null_set_perms: %lld permutations do not fit the packed counters (sum the unpacked arrays)",
+             (long long)num_perm);
+    if (num_perm != e->null_perms) e->null_pk_perms = std::min<int64_t>(num_perm, 65535);  // summed over the ranks
     e->null_perms = num_perm;
     SB_API_END
 }
@@ -564,6 +604,7 @@ int sb_enrich_null_finalize(sb_enrich* e, const double* pvalue_of_count_host, co
     PhaseTrace tr(ctx, "null.finalize");
     const int64_t n = e->n, m = e->m;
     const size_t cells = static_cast<size_t>(n) * m;
+    null_flush(e);
     const double* ns = enrich_observed(e, e->null_score);
     DevBuf<double> ptab, nestab, pn, pp, nes, nb;
     DevBuf<int32_t> colcnt;

@@ -1015,6 +1015,7 @@ struct TcPlan {
     DevBuf<int8_t> digits;
     DevBuf<uint8_t> inexact;
     DevBuf<int64_t> s0fix;
+    DevBuf<int32_t> shift;  // per-column binary exponent of the fixed point: q = rint(v * 2^shift[j])
     DevBuf<unsigned int> flag_count;
     int64_t cpk_perms = 0;  // permutations accumulated in the packed counters since the last unpack (16-bit fields)
     uint32_t* cpk = nullptr;  // packed counters of the call in progress (context scratch or the caller's array)
@@ -1267,7 +1268,8 @@ static TcPlan* build_plan(sb_enrich* e) {
         delete tr;
         tr = new PhaseTrace(ctx, "tc.plan.digits");
         // ---- digit planes
-        DevBuf<int32_t> kmax, lmin, flags, shift;
+        DevBuf<int32_t> kmax, lmin, flags;
+        DevBuf<int32_t>& shift = pl->shift;
         kmax.reserve(m);
         lmin.reserve(m);
         flags.reserve(1);
@@ -1444,6 +1446,21 @@ static void flush_counts(sb_enrich* e, TcPlan* pl, uint32_t* cneg, uint32_t* cpo
 // Counts of `num_perm` permutations.  Either ADDED to the caller's two arrays (cneg / cpos), or, with `packed`
 // (cneg == cpos == nullptr), ADDED to one word per cell, pos << 16 | neg -- the form that crosses NVLink in the
 // multi-GPU all-reduce; the caller keeps the number of permutations summed into a word below 65536.
+// Observed 'sum' scores from the tensor cores when every attribute column is exactly representable in the plan's fixed
+// point (binary / integer / dyadic data -- what the hypergeometric test is given): S[i][j] = s0fix[row_of[i]][j] *
+// 2^-shift[j], exact.  Returns false when the plan cannot serve (inexact columns, +-inf, giant neighborhoods).
+bool tc_observed_exact(sb_enrich* e, const int64_t** s0fix, const int32_t** shift, const int32_t** row_of_node,
+                       int64_t* mpad) {
+    if (!e->tc) e->tc = build_plan(e);
+    TcPlan* pl = e->tc;
+    if (!pl->usable || pl->any_inexact) return false;
+    *s0fix = pl->s0fix.p;
+    *shift = pl->shift.p;
+    *row_of_node = e->have_order ? e->order_inv.p : nullptr;
+    *mpad = pl->mpad;
+    return true;
+}
+
 void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
                     uint32_t* packed) {
     sb_ctx* ctx = e->ctx;

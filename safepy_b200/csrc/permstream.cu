@@ -209,7 +209,6 @@ int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num
     ctx->bind();
     cudaStream_t st = ctx->stream;
     const int64_t n = e->n;
-    const size_t cells = static_cast<size_t>(n) * e->m;
     // Piece schedule.  One rank: pieces double from 16 permutations (the device gets work at once) up to `piece`.
     // Several ranks: equal pieces dealt round-robin, ~4 per rank, so that drawing the other ranks' pieces (the RNG
     // cannot jump) overlaps with counting one's own instead of preceding it.
@@ -270,9 +269,7 @@ int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num
             }
             SB_CUDA(cudaMemcpyAsync(e->null_perm.p, ring + static_cast<size_t>(slot) * piece * n,
                                     static_cast<size_t>(np) * n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-            int rc = sb_enrich_perm_counts_dev(e, e->null_score, e->null_engine, e->null_perm.p, np, e->null_cnt.p,
-                                               e->null_cnt.p + cells);
-            if (rc) fail("%s", sb_last_error());
+            sb::null_count_dev(e, e->null_perm.p, np);
             SB_CUDA(cudaStreamSynchronize(st));  // slot and staging buffer are reused
             {
                 std::lock_guard<std::mutex> lk(mu);

@@ -281,19 +281,33 @@ class SafeB200Mixin:
                 raise ValueError("permutation shards over several GPUs need a random_seed: with None every rank "
                                  "would draw its own stream")
             if dist:
-                # permutations sharded over the ranks; ONE sum all-reduce of the device count arrays (safe.py:518-519
-                # sums its worker results the same way), then every rank runs the tail on the full counts
+                # permutations sharded over the ranks; ONE sum all-reduce of the device counts (safe.py:518-519 sums
+                # its worker results the same way) -- the packed word per cell (pos << 16 | neg) while P < 65536,
+                # half the bytes of the two arrays
                 import torch
+                device = torch.device("cuda", plan.ctx.device)
                 stream = perm_stream(self.node2attribute, self.random_seed)
                 plan.null_add_stream(stream, self.num_permutations, dist.get_world_size(), dist.get_rank())
                 stream.sync_numpy()
                 stream.close()
                 plan.ctx.synchronize()
-                neg, _ = plan.null_counts_dev()
-                counts = torch.as_tensor(DeviceArray(neg, 2 * plan.n * plan.m),
-                                         device=torch.device("cuda", plan.ctx.device))
+                if self.num_permutations < 65536:
+                    pk, _ = plan.null_packed_dev()
+                    counts = torch.as_tensor(DeviceArray(pk, plan.n * plan.m), device=device)
+                else:
+                    neg, _ = plan.null_counts_dev()
+                    plan.ctx.synchronize()
+                    counts = torch.as_tensor(DeviceArray(neg, 2 * plan.n * plan.m), device=device)
                 dist.all_reduce(counts)
+                # the observed scores the tail needs (NaN mask, self.ns): every rank computes its block of node rows,
+                # the blocks are exchanged in place (the exact fp64 kernel is the expensive part of the tail)
+                r0, r1 = row_shard(plan.n, dist.get_world_size(), dist.get_rank())
+                ns_ptr = plan.observed_rows_dev(self.neighborhood_score_type, r0, r1)
+                plan.ctx.synchronize()
+                ns_t = torch.as_tensor(DeviceArray(ns_ptr, plan.n * plan.m, "<f8"), device=device).view(plan.n, plan.m)
+                broadcast_row_shards(dist, ns_t, plan.n)
                 torch.cuda.synchronize(plan.ctx.device)
+                plan.observed_set_ready(self.neighborhood_score_type)
                 plan.null_set_perms(self.num_permutations)
             elif native_seed(self.random_seed):
                 # one C call: a producer thread replays the RNG stream piece by piece into pinned memory while the
@@ -312,9 +326,19 @@ class SafeB200Mixin:
                 logging.info("Running FDR-adjustment of p-values...")
             want = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
             if dist and self.results_rank is not None and dist.get_rank() != self.results_rank:
-                want = ()            # this rank keeps only the per-attribute sums
-            out = plan.null_finalize(self.num_permutations, self.attribute_sign, self.enrichment_threshold,
-                                     self.multiple_testing, want=want)
+                # this rank keeps only the per-attribute sums, which the results rank sends: no tail here at all
+                import torch
+                enriched = torch.empty(plan.m, dtype=torch.float64, device=torch.device("cuda", plan.ctx.device))
+                dist.broadcast(enriched, src=self.results_rank)
+                out = {"num_neighborhoods_enriched": enriched.cpu().numpy()}
+            else:
+                out = plan.null_finalize(self.num_permutations, self.attribute_sign, self.enrichment_threshold,
+                                         self.multiple_testing, want=want)
+                if dist and self.results_rank is not None:
+                    import torch
+                    enriched = torch.from_numpy(out["num_neighborhoods_enriched"]).to(
+                        torch.device("cuda", plan.ctx.device))
+                    dist.broadcast(enriched, src=self.results_rank)
             self.last_enrichment_stats = plan.stats()
         # host wall clock of the three phases (upload + CSR view, streamed null, fused tail + result copies)
         self.last_enrichment_seconds = {"plan": t1 - t0, "null": t2 - t1, "tail": time.perf_counter() - t2}

@@ -1,6 +1,6 @@
 """Device time and roofline bookkeeping of the non-GEMM kernels at the BASELINE.json shapes.
 
-    python tools/kernel_bench.py [--only sssp|euclid|hypergeom|components|tail] [--small]
+    python tools/kernel_bench.py [--only sssp,euclid,hypergeom,components,tail] [--configs C1,C3,C5] [--small]
 
 Algorithmic bytes follow SURVEY.md section 8(d):
   k_sssp      sum over sources s and settled nodes t of (8 + deg(t) * 12) + N*N/8   (computed exactly from the result)
@@ -38,12 +38,13 @@ def timed(ctx, cls, fn, reps=3):
 
 
 def main():
-    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+    only = set(sys.argv[sys.argv.index("--only") + 1].replace("+", ",").split(",")) if "--only" in sys.argv else None
+    sssp_cfgs = tuple(sys.argv[sys.argv.index("--configs") + 1].split(",")) if "--configs" in sys.argv else None
     small = "--small" in sys.argv
     ctx = get_context()
     out = []
-    if only in (None, "sssp"):
-        for name in (("C1",) if small else ("C1", "C3", "C5")):
+    if only is None or "sssp" in only:
+        for name in sssp_cfgs or (("C1",) if small else ("C1", "C3", "C5")):
             cfg = syn.make_config(name, shuffle=True)
             net, n = cfg["net"], cfg["n"]
             nr = cfg["radius"] * (net["x"].max() - net["x"].min())
@@ -58,7 +59,7 @@ def main():
                             settled_pairs=pairs, pairs_per_s=pairs / (ms * 1e-3), algorithmic_bytes=alg,
                             achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=PEAK, frac=alg / (ms * 1e-3) / 1e9 / PEAK))
             nb.close()
-    if only in (None, "euclid"):
+    if only is None or "euclid" in only:
         cfg = syn.make_config("C4", 0.1 if small else 1.0, shuffle=True)
         net, n = cfg["net"], cfg["n"]
         nr = cfg["radius"] * (net["x"].max() - net["x"].min())
@@ -69,7 +70,7 @@ def main():
                         algorithmic_bytes=alg, achieved_gbs=alg / (ms * 1e-3) / 1e9, peak_gbs=PEAK,
                         frac=alg / (ms * 1e-3) / 1e9 / PEAK, fp64_gflops=5.0 * n * n / (ms * 1e-3) / 1e9))
         nb.close()
-    if only in (None, "hypergeom"):
+    if only is None or "hypergeom" in only:
         cfg = syn.make_config("C2", 0.2 if small else 1.0, shuffle=True)
         net, n, m = cfg["net"], cfg["n"], cfg["m"]
         nr = cfg["radius"] * (net["x"].max() - net["x"].min())
@@ -88,7 +89,7 @@ def main():
                         frac=alg / (ms * 1e-3) / 1e9 / PEAK, call_wall_s=wall, first_call_wall_s=wall_first))
         plan.close()
         nb.close()
-    if only in (None, "components"):
+    if only is None or "components" in only:
         # define_top_attributes' connectivity test at C3 size: 2000 attributes, each enriched in 1-3 spatial blobs
         cfg = syn.make_config("C3", 0.1 if small else 1.0, shuffle=True)
         net, n, m = cfg["net"], cfg["n"], cfg["m"]
@@ -116,7 +117,7 @@ def main():
         out.append(dict(kernel="k_components", workload="C3 nodes x %d candidate attributes" % len(cand), n=n,
                         call_wall_s=wall, attributes_per_s=len(cand) / wall,
                         cpu_scipy_s_per_attribute=cpu, mean_components=float(ncc.mean())))
-    if only in (None, "tail"):
+    if only is None or "tail" in only:
         # what follows the counts inside compute_pvalues at C3 size (20k x 2000): fused tail, row-wise FDR, and the
         # Jaccard distances define_domains needs between 1000 top attributes
         from safepy_b200.permutations import make_perm_rows

@@ -799,6 +799,34 @@ def run_ours(args):
                        "perm_index_replay_host_s": t_rng, "node_order_hint_host_s": t_order,
                        "compute_pvalues_null_s": sec_per_step},
         }
+    # ---- neighborhood_score_type='z-score' on the same inputs (three digit contractions + fp64 comparison kernel per
+    # permutation): a short resident pass of this rank's first permutations, reported beside the 'sum' null
+    zscore = None
+    try:
+        zp = int(min(hi - lo, 96))
+        if zp > 0:
+            plan = _lib.Enrichment(nb, b_dev=attrs_dev.data_ptr(), dtype=np.float32, shape=(n, m))
+            plan.set_node_order(node_order)
+            counts.zero_()
+            plan.perm_counts_dev(rows_dev.data_ptr(), zp, counts[0].data_ptr(), counts[1].data_ptr(), "z-score", "auto")
+            torch.cuda.synchronize()
+            counts.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan.perm_counts_dev(rows_dev.data_ptr(), zp, counts[0].data_ptr(), counts[1].data_ptr(), "z-score", "auto")
+            e1.record()
+            torch.cuda.synchronize()
+            zst = plan.stats()
+            plan.close()
+            zms = e0.elapsed_time(e1)
+            zscore = {"permutations": zp, "ms_per_permutation": zms / zp, "scores_per_s": float(n) * m * zp / (zms / 1e3),
+                      "fixup_fraction": zst["fixups"] / max(1, zst["fixups"] + zst["decided"]),
+                      "note": "resident z-score null of this rank's first %d permutations (digit GEMM in its store "
+                              "flavour for value / square / valid sums + k_zcount + exact fix-ups)" % zp}
+    except Exception as exc:  # noqa: BLE001
+        zscore = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    if rank == 0:
+        out["stages"]["zscore_null"] = zscore
     if not args.no_safe_api:
         # BASELINE.json's second metric, through the SAFE class itself (host call to host return: graph -> CSR,
         # layout order, RNG replay, H2D / D2H, NES arithmetic all included).  With several ranks the class shards

@@ -47,7 +47,7 @@ extern "C" {
 /* engine selection for the permutation null */
 #define SB_ENGINE_AUTO 0   /* tcgen05 int8 digit GEMM + exact fix-up for 'sum'; SIMT fp64 for 'z-score' */
 #define SB_ENGINE_SIMT 1   /* fp64 CUDA-core sparse kernel (exact by construction; validation / z-score) */
-#define SB_ENGINE_TC 2     /* force the tensor-core path ('sum' only) */
+#define SB_ENGINE_TC 2     /* force the tensor-core path (z-score: needs 64+ attributes and finite values) */
 
 typedef struct sb_ctx sb_ctx;       /* one device + stream + workspaces */
 typedef struct sb_neigh sb_neigh;   /* bit-packed N x N neighborhood matrix on the device */

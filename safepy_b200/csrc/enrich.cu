@@ -72,51 +72,6 @@ __global__ void k_fill_csr(const uint32_t* __restrict__ words, int64_t n, int64_
 }
 
 // ------------------------------------------------------------------------------------------------ scores
-template <class T>
-__device__ __forceinline__ double sq_like_numpy(T v);
-// np.power(B, 2) keeps B's dtype: float32 squares are rounded to float32 before the fp64 dot (safe_extras.py:24)
-template <>
-__device__ __forceinline__ double sq_like_numpy<float>(float v) {
-    return static_cast<double>(__fmul_rn(v, v));
-}
-template <>
-__device__ __forceinline__ double sq_like_numpy<double>(double v) {
-    return __dmul_rn(v, v);
-}
-
-// One (node i, virtual column c) score; c = p * m + j selects permutation p (perm == nullptr: identity) and
-// attribute j.  Accumulation is fp64 in ascending neighbor order -- the order the oracle uses.
-template <class T, bool ZS>
-__device__ __forceinline__ double score_one(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                                            const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
-                                            int64_t m, int64_t i, int64_t p, int64_t j) {
-    const int64_t e0 = row_ptr[i], e1 = row_ptr[i + 1];
-    const int32_t* pr = perm ? perm + p * n : nullptr;
-    double sum = 0.0, sq = 0.0;
-    int64_t cnt = 0;
-    for (int64_t e = e0; e < e1; ++e) {
-        const int32_t t = col_idx[e];
-        const int64_t r = pr ? pr[t] : t;
-        const T v = b[r * m + j];
-        if (v == v) {
-            sum += static_cast<double>(v);
-            if (ZS) {
-                sq += sq_like_numpy<T>(v);
-                ++cnt;
-            }
-        }
-    }
-    if (!ZS) return sum;
-    // safe_extras.py:19-31
-    const double N = static_cast<double>(cnt);
-    const double M = sum / N;
-    const double EXX = sq / N;
-    const double EEX = __dmul_rn(M, M);
-    const double sd = sqrt(__dsub_rn(EXX, EEX));
-    double z = M / sd;
-    if (sd == 0.0 || cnt < 3) z = __longlong_as_double(0x7FF8000000000000ll);
-    return z;
-}
 
 template <class T, bool ZS>
 __global__ void __launch_bounds__(128) k_score(const int64_t* __restrict__ row_ptr,
@@ -165,21 +120,28 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
                                                int64_t m, const uint64_t* __restrict__ flag_ij,
                                                const uint32_t* __restrict__ flag_p,
                                                unsigned int total, const unsigned int* __restrict__ count_dev,
-                                               unsigned int cap, uint32_t* __restrict__ cneg,
+                                               int n_bucket_lists, unsigned int cap, uint32_t* __restrict__ cneg,
                                                uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
     const int lane = threadIdx.x & 31;
+    // Bucketed list: the whole grid walks the buckets one after the other, so that at any time the scattered reads
+    // fall into one column group's slab of b_t (64 columns x n values, L2-resident) -- with all buckets in flight at
+    // once the kernel was DRAM-bound on 32-byte sectors fetched for 4-byte values (ncu: 11 GB per C3 batch).
+    const int n_buckets = count_dev ? n_bucket_lists : 1;
+    for (int bucket = 0; bucket < n_buckets; ++bucket) {
+    const uint64_t* fij = flag_ij;
+    const uint32_t* fp = flag_p;
     if (count_dev) {
-        total = count_dev[blockIdx.y];
-        if (total > cap) return;  // overflowed bucket: redone by the caller
-        flag_ij += static_cast<size_t>(blockIdx.y) * cap;
-        flag_p += static_cast<size_t>(blockIdx.y) * cap;
+        total = count_dev[bucket];
+        if (total > cap) continue;  // overflowed bucket: redone by the caller
+        fij += static_cast<size_t>(bucket) * cap;
+        fp += static_cast<size_t>(bucket) * cap;
     }
     unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int step = (gridDim.x * blockDim.x) >> 5;
     for (; k < total; k += step) {
-        const uint64_t ij = flag_ij[k];
+        const uint64_t ij = fij[k];
         const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
-        const int32_t* pr = perm + static_cast<int64_t>(flag_p[k]) * n;
+        const int32_t* pr = perm + static_cast<int64_t>(fp[k]) * n;
         const T* col = b_t + j * n;
         double sp = 0.0, so = 0.0;
         for (int64_t e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
@@ -202,6 +164,7 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
                 if (sp >= so) atomicAdd(&cpos[i * m + j], 1u);
             }
         }
+    }
     }
 }
 
@@ -496,11 +459,11 @@ void fixup_flags(sb_enrich* e, const int32_t* perm_dev, const uint64_t* flag_ij,
     KernelTimer kt(ctx, SB_K_FIXUP);
     if (e->dtype == SB_F32)
         k_fixup<float><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt),
-                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0,
+                                                        perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0, 0,
                                                         cneg, cpos, packed);
     else
         k_fixup<double><<<blocks, 256, 0, ctx->stream>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt),
-                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0,
+                                                         perm_dev, e->n, e->m, flag_ij, flag_p, count, nullptr, 0, 0,
                                                          cneg, cpos, packed);
     SB_LAUNCH_CHECK(ctx);
 }
@@ -511,17 +474,15 @@ void fixup_flag_buckets(sb_enrich* e, cudaStream_t st, const int32_t* perm_dev, 
     sb_ctx* ctx = e->ctx;
     const void* bt = e->b_t;
     SB_CHECK(bt, "internal error: transposed attribute matrix not built");
-    // blocks per bucket: the whole device, split over the buckets (a bucket usually holds a few thousand entries)
-    const int bx = std::max(1, std::min(64, (ctx->num_sms * 8) / std::max(1, n_buckets)));
-    dim3 grid(static_cast<unsigned>(bx), static_cast<unsigned>(n_buckets));
-    SB_CHECK(grid.y <= 65535, "too many fix-up buckets");
+    const unsigned grid = static_cast<unsigned>(ctx->num_sms * 8);  // the whole device on one bucket at a time
     KernelTimer kt(ctx, SB_K_FIXUP, st);
     if (e->dtype == SB_F32)
         k_fixup<float><<<grid, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt), perm_dev, e->n,
-                                             e->m, flag_ij, flag_p, 0, count_dev, cap, cneg, cpos, packed);
+                                             e->m, flag_ij, flag_p, 0, count_dev, n_buckets, cap, cneg, cpos, packed);
     else
         k_fixup<double><<<grid, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt), perm_dev,
-                                              e->n, e->m, flag_ij, flag_p, 0, count_dev, cap, cneg, cpos, packed);
+                                              e->n, e->m, flag_ij, flag_p, 0, count_dev, n_buckets, cap, cneg, cpos,
+                                              packed);
     SB_LAUNCH_CHECK(ctx);
 }
 
@@ -603,6 +564,21 @@ static sb_enrich* enrich_new(sb_ctx* ctx, sb_neigh* a, int dtype, int64_t n, int
     e->m = m;
     e->dtype = dtype;
     return e;
+}
+
+// engine selection: 'sum' -> digit GEMM with the fused comparison; 'z-score' -> digit GEMM (three sums per permutation)
+// + fp64 comparison kernel when the plan can serve it (64+ attributes, finite values), else the exact SIMT engine
+static void perm_counts_dispatch(sb_enrich* e, int score_type, int engine, const int32_t* perm_dev, int64_t num_perm,
+                                 uint32_t* cneg, uint32_t* cpos, uint32_t* packed) {
+    if (engine == SB_ENGINE_SIMT) {
+        simt_perm_counts(e, score_type, perm_dev, num_perm, cneg, cpos, packed);
+    } else if (score_type == SB_SCORE_SUM) {
+        tc_perm_counts(e, perm_dev, num_perm, cneg, cpos, packed);
+    } else if (!tc_perm_counts_z(e, perm_dev, num_perm, cneg, cpos, packed)) {
+        SB_CHECK(engine != SB_ENGINE_TC,
+                 "the tensor-core z-score null needs 64+ attributes, finite values and neighborhoods below 65536 nodes");
+        simt_perm_counts(e, score_type, perm_dev, num_perm, cneg, cpos, packed);
+    }
 }
 
 extern "C" {
@@ -712,15 +688,9 @@ int sb_enrich_perm_counts_dev(sb_enrich* e, int score_type, int engine, const in
              score_type);
     SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
              engine);
-    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
-             "the tensor-core engine implements neighborhood_score_type 'sum' only");
     e->ctx->bind();
     if (num_perm == 0) return 0;
-    const bool use_tc = engine == SB_ENGINE_TC || (engine == SB_ENGINE_AUTO && score_type == SB_SCORE_SUM);
-    if (use_tc)
-        tc_perm_counts(e, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
-    else
-        simt_perm_counts(e, score_type, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev);
+    perm_counts_dispatch(e, score_type, engine, perm_rows_dev, num_perm, counts_neg_dev, counts_pos_dev, nullptr);
     SB_API_END
 }
 
@@ -734,15 +704,9 @@ int sb_enrich_perm_counts_packed_dev(sb_enrich* e, int score_type, int engine, c
              score_type);
     SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
              engine);
-    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
-             "the tensor-core engine implements neighborhood_score_type 'sum' only");
     e->ctx->bind();
     if (num_perm == 0) return 0;
-    const bool use_tc = engine == SB_ENGINE_TC || (engine == SB_ENGINE_AUTO && score_type == SB_SCORE_SUM);
-    if (use_tc)
-        tc_perm_counts(e, perm_rows_dev, num_perm, nullptr, nullptr, counts_packed_dev);
-    else
-        simt_perm_counts(e, score_type, perm_rows_dev, num_perm, nullptr, nullptr, counts_packed_dev);
+    perm_counts_dispatch(e, score_type, engine, perm_rows_dev, num_perm, nullptr, nullptr, counts_packed_dev);
     SB_API_END
 }
 

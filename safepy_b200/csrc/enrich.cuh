@@ -46,6 +46,58 @@ struct sb_enrich {
 
 namespace sb {
 
+#ifdef __CUDACC__
+// np.power(B, 2) keeps B's dtype: float32 squares are rounded to float32 before the fp64 dot (safe_extras.py:24)
+template <class T>
+__device__ __forceinline__ double sq_like_numpy(T v);
+template <>
+__device__ __forceinline__ double sq_like_numpy<float>(float v) {
+    return static_cast<double>(__fmul_rn(v, v));
+}
+template <>
+__device__ __forceinline__ double sq_like_numpy<double>(double v) {
+    return __dmul_rn(v, v);
+}
+// z-score of a neighborhood from the sum, the sum of squares and the number of its non-NaN values, safe_extras.py:19-31
+// (one definition: the exact kernels and the tensor-core z-score path must round identically)
+__device__ __forceinline__ double zscore_from_sums(double sum, double sq, int64_t cnt) {
+    const double N = static_cast<double>(cnt);
+    const double M = sum / N;
+    const double EXX = sq / N;
+    const double EEX = __dmul_rn(M, M);
+    const double sd = sqrt(__dsub_rn(EXX, EEX));
+    double z = M / sd;
+    if (sd == 0.0 || cnt < 3) z = __longlong_as_double(0x7FF8000000000000ll);
+    return z;
+}
+// One (node i, virtual column c) score; c = p * m + j selects permutation p (perm == nullptr: identity) and
+// attribute j.  Accumulation is fp64 in ascending neighbor order -- the order the oracle uses.
+template <class T, bool ZS>
+__device__ __forceinline__ double score_one(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                            const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                            int64_t m, int64_t i, int64_t p, int64_t j) {
+    const int64_t e0 = row_ptr[i], e1 = row_ptr[i + 1];
+    const int32_t* pr = perm ? perm + p * n : nullptr;
+    double sum = 0.0, sq = 0.0;
+    int64_t cnt = 0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int32_t t = col_idx[e];
+        const int64_t r = pr ? pr[t] : t;
+        const T v = b[r * m + j];
+        if (v == v) {
+            sum += static_cast<double>(v);
+            if (ZS) {
+                sq += sq_like_numpy<T>(v);
+                ++cnt;
+            }
+        }
+    }
+    if (!ZS) return sum;
+    return zscore_from_sums(sum, sq, cnt);
+}
+
+#endif
+
 // enrich.cu
 void enrich_score_into(sb_enrich* e, int score_type, double* out_dev);
 // rows [row0, row1) only (out_dev is the whole [n x m] array)
@@ -75,6 +127,9 @@ void null_count_dev(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm);
 void null_flush(sb_enrich* e);
 void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
                     uint32_t* packed = nullptr);
+// z-score null on the tensor cores; false: the plan cannot serve (the caller takes the exact SIMT engine)
+bool tc_perm_counts_z(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
+                      uint32_t* packed = nullptr);
 bool tc_observed_exact(sb_enrich* e, const int64_t** s0fix, const int32_t** shift, const int32_t** row_of_node,
                        int64_t* mpad);
 

@@ -496,8 +496,6 @@ int sb_enrich_null_begin(sb_enrich* e, int score_type, int engine) {
              score_type);
     SB_CHECK(engine == SB_ENGINE_AUTO || engine == SB_ENGINE_SIMT || engine == SB_ENGINE_TC, "unknown engine %d",
              engine);
-    SB_CHECK(!(engine == SB_ENGINE_TC && score_type != SB_SCORE_SUM),
-             "the tensor-core engine implements neighborhood_score_type 'sum' only");
     sb_ctx* ctx = e->ctx;
     ctx->bind();
     const size_t cells = static_cast<size_t>(e->n) * e->m;

@@ -65,11 +65,13 @@ struct GemmParams {
     int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;  // n_rb: blocks of TC_PROWS rows
     int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
     int32_t rb0;              // first row block of this launch (units cover row blocks [rb0, rb0 + n_rb))
+    int32_t n_rb_total;       // row blocks of the whole matrix (column stride of a batch STORE)
     unsigned int* unit_counter;  // dynamic scheduler (zeroed before the launch)
     int32_t mode;
     int64_t n, m, mpad;
     int32_t log2_mpad, pps, batch_perms;
-    int64_t* s0fix;           // [n_rb * 256][mpad]
+    int64_t* s0fix;           // [n_rb * 256][mpad]; TCK_STORE: output, slot q at s0fix + q * store_stride
+    int64_t store_stride;     // TCK_STORE over a batch: elements between the outputs of consecutive slots (0: one slot)
     const int64_t* row_ptr;   // band_i = row_ptr[i+1] - row_ptr[i]
     const int32_t* node_of_row;  // internal row -> caller's node id (nullptr: identity)
     const uint8_t* inexact;   // [mpad]
@@ -577,12 +579,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                                     p.raw_out[(rank * TC_ROWS + row_in_tile) * C::NCOLS + d * 64 + c] =
                                         static_cast<int32_t>(acc[d][x]);
                             }
-                        } else if (KIND == TCK_STORE) {
+                        } else if (KIND == TCK_STORE && SMALL_M) {
                             long long S = static_cast<int32_t>(acc[0][x]);
                             if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][x])) << 8;
                             if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][x])) << 16;
-                            const bool col_ok = SMALL_M ? (c < p.mpad) : true;
-                            if (col_ok) p.s0fix[row * p.mpad + jbase + c] = S;
+                            if (c < p.mpad) p.s0fix[row * p.mpad + c] = S;
+                        }
+                    }
+                    if (KIND == TCK_STORE && !SMALL_M) {
+                        // one slot (observed scores): row-major [n_rb * 256][mpad], what the COUNT flavour preloads.
+                        // A batch (store_stride != 0): slot q at q * store_stride, COLUMN-major [mpad][n_rb * 256] -- the
+                        // 32 rows of a warp are 256 contiguous bytes per column (row-major 16-byte stores per thread
+                        // cost the z-score null 7 ms per 48 C3 permutations more).
+                        const int64_t rows_pad = static_cast<int64_t>(p.n_rb_total) * TC_PROWS;
+#pragma unroll
+                        for (int x = 0; x < CW; ++x) {
+                            long long S = static_cast<int32_t>(acc[0][x]);
+                            if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][x])) << 8;
+                            if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][x])) << 16;
+                            const int64_t col = jbase + c0 + ch * CW + x;
+                            if (p.store_stride)
+                                p.s0fix[q * p.store_stride + col * rows_pad + row] = S;
+                            else
+                                p.s0fix[row * p.mpad + col] = S;
                         }
                     }
                     if (KIND == TCK_COUNT) {
@@ -832,9 +851,20 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__
     out[(((g * 2 + rank) * TC_TPS) + t) * TC_ROWS + r] = w;
 }
 
-// per-column exponent range of nan0(B): kmax = exponent of the largest magnitude, lmin = exponent of the lowest
+// The matrices the digit GEMM multiplies the neighborhoods with are functions of the attribute matrix, evaluated on
+// the fly: XF_VALUE nan0(B) (the 'sum' score); and for the z-score (safe_extras.py:19-31) XF_SQUARE nan0(B^2) with
+// the square rounded like np.power(B, 2) rounds it, and XF_VALID the 0/1 matrix of the non-NaN entries.
+enum : int { XF_VALUE = 0, XF_SQUARE = 1, XF_VALID = 2 };
+template <int XF, class T>
+__device__ __forceinline__ double xf_value(T v) {  // NaN = "contributes nothing"
+    if (XF == XF_VALUE) return static_cast<double>(v);
+    if (XF == XF_SQUARE) return v == v ? sq_like_numpy<T>(v) : static_cast<double>(v);
+    return v == v ? 1.0 : 0.0;
+}
+
+// per-column exponent range of the operand: kmax = exponent of the largest magnitude, lmin = exponent of the lowest
 // set mantissa bit over all non-zero values.  flags: bit0 = some value is +-inf
-template <class T>
+template <class T, int XF>
 __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32_t* __restrict__ kmax,
                             int32_t* __restrict__ lmin, int32_t* __restrict__ flags) {
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -843,7 +873,7 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
     int hi = INT_MIN, lo = INT_MAX, bad = 0;
     for (int64_t r = r0; r < r1; ++r) {
-        const double v = static_cast<double>(b[r * m + j]);
+        const double v = xf_value<XF, T>(b[r * m + j]);
         if (v != v || v == 0.0) continue;
         if (isinf(v)) {
             bad = 1;
@@ -868,7 +898,7 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
 // RECORDS = true: one 64*D-byte record per (column group, node), digits[(cg * n + r) * 64 D + d * 64 + (j & 63)] --
 // what k_gather copies (192 contiguous bytes at D = 3), one column group's records being a compact N * 64 D byte
 // slab that stays L2-resident while the permutations of a batch are gathered from it.
-template <class T, int D, bool RECORDS>
+template <class T, int D, bool RECORDS, int XF>
 __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_t mpad,
                            const int32_t* __restrict__ shift, int8_t* __restrict__ digits) {
     const int64_t total = n * mpad;
@@ -878,7 +908,7 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
         const int64_t r = idx / mpad, j = idx % mpad;
         int q = 0;
         if (j < m) {
-            const double v = static_cast<double>(b[r * m + j]);
+            const double v = xf_value<XF, T>(b[r * m + j]);
             if (v == v) q = -static_cast<int>(rint(ldexp(v, shift[j])));
         }
 #pragma unroll
@@ -1001,8 +1031,20 @@ __global__ void k_unpack_counts(uint32_t* __restrict__ cpk, int64_t cells, uint3
 }
 
 // ------------------------------------------------------------------------------------------------ plan
+// One matrix the neighborhoods are multiplied with (see XF_*): fixed-point digits of its columns
+struct TcOperand {
+    int D = 0;                 // digit planes
+    bool built = false;
+    bool usable = true;        // false: +-inf among the values
+    bool any_inexact = false;  // some column is not exactly representable (its comparisons carry an error band)
+    DevBuf<int8_t> digits;
+    DevBuf<int32_t> shift;     // per-column binary exponent of the fixed point: q = rint(v * 2^shift[j])
+    DevBuf<uint8_t> inexact;   // [mpad]
+    DevBuf<int64_t> s0fix;     // observed fixed-point scores [n_rb * 256][mpad], internal row order
+};
+
 struct TcPlan {
-    int D = 0;
+    TcOperand op[3];           // indexed by XF_VALUE / XF_SQUARE / XF_VALID; [0] serves the 'sum' null
     int64_t n = 0, m = 0, mpad = 0;
     int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
     int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
@@ -1012,15 +1054,10 @@ struct TcPlan {
     DevBuf<uint64_t> a_bits;
     const int32_t* order = nullptr;  // e->order.p when the caller supplied a node order (internal row -> node)
     DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
-    DevBuf<int8_t> digits;
-    DevBuf<uint8_t> inexact;
-    DevBuf<int64_t> s0fix;
-    DevBuf<int32_t> shift;  // per-column binary exponent of the fixed point: q = rint(v * 2^shift[j])
     DevBuf<unsigned int> flag_count;
     int64_t cpk_perms = 0;  // permutations accumulated in the packed counters since the last unpack (16-bit fields)
     uint32_t* cpk = nullptr;  // packed counters of the call in progress (context scratch or the caller's array)
     unsigned int flag_cap = 0;
-    bool any_inexact = false;
 };
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
@@ -1095,18 +1132,18 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
 }
 
 // Gathered operand tiles of a batch of permutations -> bcat, on stream st
-static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, int slots, int batch_perms, int8_t* bcat,
-                          cudaStream_t st) {
+static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const TcOperand& op, const int32_t* perm, int slots,
+                          int batch_perms, int8_t* bcat, cudaStream_t st) {
     KernelTimer kt(ctx, SB_K_GATHER, st);
     if (pl->mpad >= 64) {
         const int nq = slots / pl->n_cg;
         dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(nq), static_cast<unsigned>(pl->n_cg));
         SB_CHECK(grid.y <= 65535 && grid.z <= 65535, "too many column groups / permutations in one batch");
 #define SB_G(DD) \
-    k_gather<DD><<<grid, 256, 0, st>>>(pl->digits.p, perm, pl->order, pl->n, pl->n_kt, pl->n_cg, bcat)
-        if (pl->D == 1)
+    k_gather<DD><<<grid, 256, 0, st>>>(op.digits.p, perm, pl->order, pl->n, pl->n_kt, pl->n_cg, bcat)
+        if (op.D == 1)
             SB_G(1);
-        else if (pl->D == 2)
+        else if (op.D == 2)
             SB_G(2);
         else
             SB_G(3);
@@ -1115,11 +1152,11 @@ static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, in
         dim3 grid(static_cast<unsigned>(pl->n_kt), static_cast<unsigned>(slots));
         SB_CHECK(grid.y <= 65535, "too many column slots in one batch (%d)", slots);
 #define SB_G(DD)                                                                                                  \
-    k_gather_small<DD><<<grid, 256, 0, st>>>(pl->digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt, pl->pps,   \
+    k_gather_small<DD><<<grid, 256, 0, st>>>(op.digits.p, perm, pl->order, pl->n, pl->mpad, pl->n_kt, pl->pps,    \
                                              pl->log2_mpad, batch_perms, bcat)
-        if (pl->D == 1)
+        if (op.D == 1)
             SB_G(1);
-        else if (pl->D == 2)
+        else if (op.D == 2)
             SB_G(2);
         else
             SB_G(3);
@@ -1128,7 +1165,7 @@ static void launch_gather(sb_ctx* ctx, const TcPlan* pl, const int32_t* perm, in
     SB_LAUNCH_CHECK(ctx);
 }
 
-static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
+static GemmParams base_params(sb_enrich* e, TcPlan* pl, const TcOperand& op) {
     sb_ctx* ctx = e->ctx;
     GemmParams gp{};
     gp.a_bits = pl->a_bits.p;
@@ -1137,22 +1174,23 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
     gp.bcat = ctx->ws_bcat.p;
     gp.n_kt = pl->n_kt;
     gp.n_rb = pl->n_rb;
+    gp.n_rb_total = pl->n_rb;
     gp.n_cg = pl->n_cg;
     gp.n = pl->n;
     gp.m = pl->m;
     gp.mpad = pl->mpad;
     gp.log2_mpad = pl->log2_mpad;
     gp.pps = pl->pps;
-    gp.s0fix = pl->s0fix.p;
+    gp.s0fix = op.s0fix.p;
     gp.row_ptr = e->row_ptr.p;
     gp.node_of_row = pl->order;
-    gp.inexact = pl->inexact.p;
+    gp.inexact = op.inexact.p;
     gp.flag_ij = ctx->ws_flag_ij.p;
     gp.flag_p = ctx->ws_flag_p.p;
     gp.flag_count = pl->flag_count.p;
     gp.flag_cap = pl->flag_cap / static_cast<unsigned int>(pl->n_cg);
     gp.cpk = pl->cpk;
-    const uint32_t ncols = 64u * pl->D;
+    const uint32_t ncols = 64u * op.D;
     gp.b_lbo = ncols / 2 * 8;  // MN-major B half tile: stride between 8-row K groups
     gp.b_sbo = 128;        //             stride between 16-column chunks
     gp.q_wrap = INT_MAX;
@@ -1162,6 +1200,141 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl) {
 
 static int64_t slots_for(const TcPlan* pl, int64_t perms) {
     return pl->mpad >= 64 ? perms * pl->n_cg : sb_ceil_div(perms, pl->pps);
+}
+
+// Digit planes of one operand (XF_*) and its observed fixed-point scores
+static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    TcOperand& op = pl->op[xf];
+    if (op.built) return;
+    const int64_t n = e->n, m = e->m;
+    PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.digits");
+    DevBuf<int32_t> kmax, lmin, flags;
+    kmax.reserve(m);
+    lmin.reserve(m);
+    flags.reserve(1);
+    std::vector<int32_t> h_kmax(m, INT_MIN), h_lmin(m, INT_MAX);
+    SB_CUDA(cudaMemcpyAsync(kmax.p, h_kmax.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(lmin.p, h_lmin.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t), st));
+    dim3 cgrid(static_cast<unsigned>(sb_ceil_div(m, 128)),
+               static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, n / 256))));
+#define SB_R(T, X) \
+    k_col_range<T, X><<<cgrid, 128, 0, st>>>(static_cast<const T*>(e->b), n, m, kmax.p, lmin.p, flags.p)
+#define SB_RX(T)                 \
+    do {                         \
+        if (xf == XF_VALUE)      \
+            SB_R(T, XF_VALUE);   \
+        else if (xf == XF_SQUARE) \
+            SB_R(T, XF_SQUARE);  \
+        else                     \
+            SB_R(T, XF_VALID);   \
+    } while (0)
+    if (e->dtype == SB_F32)
+        SB_RX(float);
+    else
+        SB_RX(double);
+#undef SB_RX
+#undef SB_R
+    SB_LAUNCH_CHECK(ctx);
+    int32_t h_flags = 0;
+    SB_CUDA(cudaMemcpyAsync(h_kmax.data(), kmax.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(h_lmin.data(), lmin.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    op.built = true;
+    if (h_flags & 1) {
+        op.usable = false;
+        delete tr;
+        return;
+    }
+    // digits needed for exactness: a column needs bits = kmax - lmin + 1 magnitude bits; D balanced digits hold
+    // |q| <= 127 * (256^D - 1) / 255, i.e. bits <= 8 D - 2
+    int D = 1;
+    for (int64_t j = 0; j < m; ++j)
+        if (h_kmax[j] != INT_MIN) {
+            const int bits = h_kmax[j] - h_lmin[j] + 1;
+            D = std::max(D, std::min(3, (bits + 2 + 7) / 8));
+        }
+    op.D = D;
+    std::vector<int32_t> h_shift(m, 0);
+    std::vector<uint8_t> h_inexact(pl->mpad, 0);
+    for (int64_t j = 0; j < m; ++j) {
+        if (h_kmax[j] == INT_MIN) continue;
+        const int bits = h_kmax[j] - h_lmin[j] + 1;
+        if (bits <= 8 * D - 2) {
+            h_shift[j] = -h_lmin[j];  // lowest set bit lands on 2^0: every value is an exact integer
+        } else {
+            h_shift[j] = (8 * D - 3) - h_kmax[j];  // |q| < 2^(8D-2)
+            h_inexact[j] = 1;
+            op.any_inexact = true;
+        }
+    }
+    op.shift.reserve(m);
+    op.inexact.reserve(pl->mpad);
+    SB_CUDA(cudaMemcpyAsync(op.shift.p, h_shift.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(op.inexact.p, h_inexact.data(), pl->mpad, cudaMemcpyHostToDevice, st));
+    op.digits.reserve(static_cast<size_t>(D) * n * pl->mpad);
+    const unsigned qblocks =
+        static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * pl->mpad, 256), ctx->num_sms * 32));
+#define SB_Q(T, DD, X)                                                                                              \
+    do {                                                                                                            \
+        if (pl->mpad >= 64)                                                                                         \
+            k_quantize<T, DD, true, X><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad,        \
+                                                                op.shift.p, op.digits.p);                           \
+        else                                                                                                        \
+            k_quantize<T, DD, false, X><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad,       \
+                                                                 op.shift.p, op.digits.p);                          \
+    } while (0)
+#define SB_QD(T, X)          \
+    do {                     \
+        if (D == 1)          \
+            SB_Q(T, 1, X);   \
+        else if (D == 2)     \
+            SB_Q(T, 2, X);   \
+        else                 \
+            SB_Q(T, 3, X);   \
+    } while (0)
+#define SB_QX(T)                  \
+    do {                          \
+        if (xf == XF_VALUE)       \
+            SB_QD(T, XF_VALUE);   \
+        else if (xf == XF_SQUARE) \
+            SB_QD(T, XF_SQUARE);  \
+        else                      \
+            SB_QD(T, XF_VALID);   \
+    } while (0)
+    if (e->dtype == SB_F32)
+        SB_QX(float);
+    else
+        SB_QX(double);
+#undef SB_QX
+#undef SB_QD
+#undef SB_Q
+    SB_LAUNCH_CHECK(ctx);
+    SB_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
+
+    delete tr;
+    tr = new PhaseTrace(ctx, "tc.plan.s0fix");
+    // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
+    ctx->ws_flag_ij.reserve(pl->flag_cap);
+    ctx->ws_flag_p.reserve(pl->flag_cap);
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
+    const int64_t slots1 = slots_for(pl, 1);
+    ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
+    op.s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_PROWS * pl->mpad);
+    launch_gather(ctx, pl, op, nullptr, static_cast<int>(slots1), 1, ctx->ws_bcat.p, st);
+    GemmParams gp = base_params(e, pl, op);
+    gp.mode = TCM_STORE;
+    gp.q_total = 1;
+    gp.q_chunks = 1;
+    gp.q_per = 1;
+    gp.batch_perms = 1;
+    const int units = pl->n_rb * pl->n_cg;
+    launch_gemm_d(ctx, D, gp, std::min(units, ctx->num_sms / 2));
+    SB_CUDA(cudaStreamSynchronize(st));
+    delete tr;
 }
 
 static TcPlan* build_plan(sb_enrich* e) {
@@ -1266,119 +1439,21 @@ static TcPlan* build_plan(sb_enrich* e) {
         SB_LAUNCH_CHECK(ctx);
 
         delete tr;
-        tr = new PhaseTrace(ctx, "tc.plan.digits");
-        // ---- digit planes
-        DevBuf<int32_t> kmax, lmin, flags;
-        DevBuf<int32_t>& shift = pl->shift;
-        kmax.reserve(m);
-        lmin.reserve(m);
-        flags.reserve(1);
-        std::vector<int32_t> h_kmax(m, INT_MIN), h_lmin(m, INT_MAX);
-        SB_CUDA(cudaMemcpyAsync(kmax.p, h_kmax.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemcpyAsync(lmin.p, h_lmin.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t), st));
-        dim3 cgrid(static_cast<unsigned>(sb_ceil_div(m, 128)),
-                   static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, n / 256))));
-        if (e->dtype == SB_F32)
-            k_col_range<float><<<cgrid, 128, 0, st>>>(static_cast<const float*>(e->b), n, m, kmax.p, lmin.p, flags.p);
-        else
-            k_col_range<double><<<cgrid, 128, 0, st>>>(static_cast<const double*>(e->b), n, m, kmax.p, lmin.p,
-                                                       flags.p);
-        SB_LAUNCH_CHECK(ctx);
-        int32_t h_flags = 0;
-        SB_CUDA(cudaMemcpyAsync(h_kmax.data(), kmax.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpyAsync(h_lmin.data(), lmin.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (h_flags & 1) {
-            pl->usable = false;
-            return pl;
-        }
-        // digits needed for exactness: a column needs bits = kmax - lmin + 1 magnitude bits; D balanced digits hold
-        // |q| <= 127 * (256^D - 1) / 255, i.e. bits <= 8 D - 2
-        int D = 1;
-        for (int64_t j = 0; j < m; ++j)
-            if (h_kmax[j] != INT_MIN) {
-                const int bits = h_kmax[j] - h_lmin[j] + 1;
-                D = std::max(D, std::min(3, (bits + 2 + 7) / 8));
-            }
-        pl->D = D;
-        std::vector<int32_t> h_shift(m, 0);
-        std::vector<uint8_t> h_inexact(pl->mpad, 0);
-        for (int64_t j = 0; j < m; ++j) {
-            if (h_kmax[j] == INT_MIN) continue;
-            const int bits = h_kmax[j] - h_lmin[j] + 1;
-            if (bits <= 8 * D - 2) {
-                h_shift[j] = -h_lmin[j];  // lowest set bit lands on 2^0: every value is an exact integer
-            } else {
-                h_shift[j] = (8 * D - 3) - h_kmax[j];  // |q| < 2^(8D-2)
-                h_inexact[j] = 1;
-            }
-        }
-        shift.reserve(m);
-        pl->inexact.reserve(pl->mpad);
-        SB_CUDA(cudaMemcpyAsync(shift.p, h_shift.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaMemcpyAsync(pl->inexact.p, h_inexact.data(), pl->mpad, cudaMemcpyHostToDevice, st));
-        pl->digits.reserve(static_cast<size_t>(D) * n * pl->mpad);
-        const unsigned qblocks =
-            static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(n * pl->mpad, 256), ctx->num_sms * 32));
-#define SB_Q(T, DD)                                                                                              \
-    do {                                                                                                         \
-        if (pl->mpad >= 64)                                                                                      \
-            k_quantize<T, DD, true><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad, shift.p, \
-                                                             pl->digits.p);                                      \
-        else                                                                                                     \
-            k_quantize<T, DD, false><<<qblocks, 256, 0, st>>>(static_cast<const T*>(e->b), n, m, pl->mpad,       \
-                                                              shift.p, pl->digits.p);                            \
-    } while (0)
-        if (e->dtype == SB_F32) {
-            if (D == 1) SB_Q(float, 1);
-            else if (D == 2) SB_Q(float, 2);
-            else SB_Q(float, 3);
-        } else {
-            if (D == 1) SB_Q(double, 1);
-            else if (D == 2) SB_Q(double, 2);
-            else SB_Q(double, 3);
-        }
-#undef SB_Q
-        SB_LAUNCH_CHECK(ctx);
-        SB_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
-
-        delete tr;
-        tr = new PhaseTrace(ctx, "tc.plan.alloc_flags");
         // ---- flag list.  Only inexact columns can flag (~3e-5 of their comparisons for N(0,1) data); the list is
         // sized for a quarter of the cells per launch (4M .. 128M entries of 12 bytes) instead of the worst case, and
         // an overflowing launch is redone in (slot, row-block range) pieces whose worst case fits (tc_perm_counts).
-        bool any_inexact = false;
-        for (int64_t j = 0; j < m; ++j) any_inexact |= h_inexact[j] != 0;
-        pl->any_inexact = any_inexact;
-        const int64_t padded_cells = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
-        int64_t cap = any_inexact ? std::min<int64_t>(std::max<int64_t>(padded_cells / 4, 4ll << 20), 128ll << 20) : 0;
-        if (getenv("SB_FLAG_CAP")) cap = atoll(getenv("SB_FLAG_CAP"));  // tests: force the overflow recovery
-        cap = std::max<int64_t>(cap, static_cast<int64_t>(TC_PROWS) * 64 * pl->n_cg);  // >= one row block per bucket
-        pl->flag_cap = static_cast<unsigned int>(sb_ceil_div(cap, pl->n_cg) * pl->n_cg);
-        ctx->ws_flag_ij.reserve(pl->flag_cap);
-        ctx->ws_flag_p.reserve(pl->flag_cap);
+        const int64_t min_cap = static_cast<int64_t>(TC_PROWS) * 64 * pl->n_cg;  // >= one row block per bucket
+        pl->flag_cap = static_cast<unsigned int>(min_cap);
         pl->flag_count.reserve(pl->n_cg);
-
-        delete tr;
-        tr = new PhaseTrace(ctx, "tc.plan.s0fix");
-        // ---- observed fixed-point scores: one identity-permutation pass through the same kernel
-        const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * D;
-        const int64_t slots1 = slots_for(pl, 1);
-        ctx->ws_bcat.reserve(static_cast<size_t>(slots1) * pl->n_kt * tile_b);
-        pl->s0fix.reserve(static_cast<size_t>(pl->n_rb) * TC_PROWS * pl->mpad);
-        launch_gather(ctx, pl, nullptr, static_cast<int>(slots1), 1, ctx->ws_bcat.p, st);
-        GemmParams gp = base_params(e, pl);
-        gp.mode = TCM_STORE;
-        gp.q_total = 1;
-        gp.q_chunks = 1;
-        gp.q_per = 1;
-        gp.batch_perms = 1;
-        const int units = pl->n_rb * pl->n_cg;
-        launch_gemm_d(ctx, D, gp, std::min(units, ctx->num_sms / 2));
-        SB_CUDA(cudaStreamSynchronize(st));
-        delete tr;
+        build_operand(e, pl, XF_VALUE);
+        pl->usable = pl->op[XF_VALUE].usable;
+        if (pl->op[XF_VALUE].any_inexact) {  // exactly representable data never flags: nothing to reserve
+            const int64_t padded_cells = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
+            int64_t cap = std::min<int64_t>(std::max<int64_t>(padded_cells / 4, 4ll << 20), 128ll << 20);
+            if (getenv("SB_FLAG_CAP")) cap = atoll(getenv("SB_FLAG_CAP"));  // tests: force the overflow recovery
+            cap = std::max<int64_t>(cap, min_cap);
+            pl->flag_cap = static_cast<unsigned int>(sb_ceil_div(cap, pl->n_cg) * pl->n_cg);
+        }
     } catch (...) {
         delete pl;
         throw;
@@ -1387,16 +1462,20 @@ static TcPlan* build_plan(sb_enrich* e) {
 }
 
 // one GEMM launch over slots [q_first, q_first + q_total) of the prepared batch and row blocks [rb0, rb0 + n_rb)
-static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_first, int q_total, int batch_perms, int rb0,
-                           int n_rb) {
+static void run_batch_gemm(sb_enrich* e, TcPlan* pl, const TcOperand& op, int mode, int q_first, int q_total,
+                           int batch_perms, int rb0, int n_rb, int64_t* store_to = nullptr) {
     sb_ctx* ctx = e->ctx;
-    GemmParams gp = base_params(e, pl);
+    GemmParams gp = base_params(e, pl, op);
     gp.mode = mode;
     gp.q_total = q_total;
     gp.batch_perms = batch_perms;
     gp.rb0 = rb0;
     gp.n_rb = n_rb;
-    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
+    if (store_to) {  // TCM_STORE over a batch: slot q -> store_to + q * (padded rows x mpad)
+        gp.s0fix = store_to;
+        gp.store_stride = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
+    }
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * op.D;
     // slot offset into the gathered operand of the batch
     gp.bcat += static_cast<size_t>(q_first) * pl->n_cg * pl->n_kt * tile_b;
     // L2 blocking (see decode_unit; bands are chosen in build_plan).  The number of slots per unit (q_per) trades
@@ -1428,7 +1507,7 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, int mode, int q_first, int 
     }
     static const int dbg = getenv("SB_DBG") ? atoi(getenv("SB_DBG")) : 0;  // timing experiments only (8, 16)
     gp.dbg = dbg;
-    launch_gemm_d(ctx, pl->D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms / 2)));
+    launch_gemm_d(ctx, op.D, gp, static_cast<int>(std::min<int64_t>(units, ctx->num_sms / 2)));
     if (trace) print_prof(ctx, d_prof.p, "batch gemm");
 }
 
@@ -1453,9 +1532,9 @@ bool tc_observed_exact(sb_enrich* e, const int64_t** s0fix, const int32_t** shif
                        int64_t* mpad) {
     if (!e->tc) e->tc = build_plan(e);
     TcPlan* pl = e->tc;
-    if (!pl->usable || pl->any_inexact) return false;
-    *s0fix = pl->s0fix.p;
-    *shift = pl->shift.p;
+    if (!pl->usable || pl->op[XF_VALUE].any_inexact) return false;
+    *s0fix = pl->op[XF_VALUE].s0fix.p;
+    *shift = pl->op[XF_VALUE].shift.p;
     *row_of_node = e->have_order ? e->order_inv.p : nullptr;
     *mpad = pl->mpad;
     return true;
@@ -1484,7 +1563,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     // k_gemm CTA -- but the step does not get shorter (C3: 290 / 289 / 292 ms for none / fix-ups / both overlapped):
     // the GEMM slows down by what the side work takes, because the chip runs at its 1 kW power cap (SM clock 1.6-1.7
     // of 1.965 GHz, sw_power_cap active) and a step costs the same energy either way.
-    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->D;
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->op[XF_VALUE].D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
     if (ctx->bcat_budget == 0) {
         size_t free_b = 0, total_b = 0;
@@ -1515,7 +1594,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         pl->cpk = ctx->ws_cpk.p;
     }
     pl->cpk_perms = 0;
-    if (pl->any_inexact) enrich_transposed(e);
+    if (pl->op[XF_VALUE].any_inexact) enrich_transposed(e);
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
@@ -1533,7 +1612,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         int64_t np;
         int slots, q_total;
         batch_of(b, perm, np, slots, q_total);
-        launch_gather(ctx, pl, perm, slots, static_cast<int>(np), ctx->ws_bcat.p, on);
+        launch_gather(ctx, pl, pl->op[XF_VALUE], perm, slots, static_cast<int>(np), ctx->ws_bcat.p, on);
     };
     for (int64_t b = 0; b < n_batches; ++b) {
         const int32_t* perm;
@@ -1548,9 +1627,9 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);  // 16-bit fields about to overflow
         pl->cpk_perms += np;
         SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-        run_batch_gemm(e, pl, TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
+        run_batch_gemm(e, pl, pl->op[XF_VALUE], TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
         ktile_iters += tiles_per_pass * q_total;
-        if (pl->any_inexact) {
+        if (pl->op[XF_VALUE].any_inexact) {
             SB_CUDA(cudaMemcpyAsync(count_log.p + b * pl->n_cg, pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
                                     cudaMemcpyDeviceToDevice, st));
             fixup_flag_buckets(e, st, perm, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->n_cg, cap_cg,
@@ -1560,7 +1639,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
 
     // ---- bucket counters of all batches: statistics, and the (rare) overflowed buckets, which the fix-up kernel skipped
     std::vector<unsigned int> h_log(static_cast<size_t>(n_batches) * pl->n_cg, 0u);
-    if (pl->any_inexact) {
+    if (pl->op[XF_VALUE].any_inexact) {
         SB_CUDA(cudaMemcpyAsync(h_log.data(), count_log.p, h_log.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
     }
@@ -1596,7 +1675,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
             for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
                 const int nrb = std::min(rb_step, pl->n_rb - rb0);
                 SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-                run_batch_gemm(e, pl, TCM_FLAG, q, 1, bp, rb0, nrb);
+                run_batch_gemm(e, pl, pl->op[XF_VALUE], TCM_FLAG, q, 1, bp, rb0, nrb);
                 SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
                                         cudaMemcpyDeviceToHost, st));
                 SB_CUDA(cudaStreamSynchronize(st));
@@ -1617,9 +1696,394 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     e->stats[1] = flagged;
     e->stats[2] = pl->n_tiles_real;
     e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
-    e->stats[4] = pl->D;
+    e->stats[4] = pl->op[XF_VALUE].D;
     e->stats[5] = ktile_iters;
     e->stats[6] = overflow_batches;
+}
+
+// ================================================================================================ z-score null
+// neighborhood_score_type = 'z-score' (safe_extras.py:19-31) on the tensor cores.  Per permutation the score needs
+// three contractions with the neighborhood matrix -- sum of the values (XF_VALUE), sum of their squares (XF_SQUARE), number
+// of non-NaN values (XF_VALID) -- and then fp64 arithmetic per cell, which does not belong in the GEMM's epilogue.  So
+// the digit GEMM runs in its STORE flavour for a small batch of permutations and writes the three exact fixed-point
+// sums; k_zcount turns them into the comparison against the observed z-score:
+//   * columns whose values AND squares are exactly representable (binary / integer / dyadic data): the fixed-point
+//     sums are the exact sums, the fp64 z-score is evaluated by the very function the exact engine uses
+//     (zscore_from_sums) and compared directly -- same bits as the SIMT engine, no fix-ups;
+//   * otherwise |fixed-point sum - true sum| <= (non-NaN neighbors) / 2 units, which bounds the z-score from both
+//     sides (it is increasing in the sum, and monotone in the sum of squares with the sign of the mean); a comparison
+//     whose interval does not contain the observed z-score is decided rigorously, the rest go to a list that k_zfix
+//     re-evaluates with the exact engine's own accumulation (score_one order), one thread per entry.
+struct ZParams {
+    const int64_t *s1, *s2, *s3;  // [qb][mpad][rows_pad] fixed-point sums of the batch (value, square, valid)
+    const double* z0t;            // [mpad][rows_pad] observed z-score (exact engine) in the plan's internal layout
+    uint32_t* zc;                 // [mpad][rows_pad] packed counts (pos << 16 | neg) of the decided comparisons
+    const int32_t *shift1, *shift2;
+    const uint8_t *inex1, *inex2;
+    const int32_t* node_of_row;   // internal row -> node (nullptr: identity)
+    int64_t n, m, mpad, rows_pad, stride;  // stride = rows_pad * mpad
+    int32_t q0, q1;               // slots of the batch to evaluate
+    int32_t r0, r1;               // internal rows to evaluate
+    int32_t count;                // 0: emit flags only (overflow recovery)
+    uint64_t* flag_ij;
+    uint32_t* flag_p;
+    unsigned int* flag_count;
+    unsigned int flag_cap;
+};
+
+// a warp = 32 consecutive internal rows of one attribute column: sums, observed z-scores and counters are all in the
+// plan's column-major internal layout, i.e. every access is a contiguous run (the caller's node-major arrays are
+// touched once per null, by k_z_flush)
+__global__ void __launch_bounds__(256) k_zcount(const ZParams p) {
+    const int64_t r = p.r0 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t j = blockIdx.y;
+    if (j >= p.m || r >= p.r1 || r >= p.n) return;
+    const int64_t at = j * p.rows_pad + r;
+    const double z0 = p.z0t[at];
+    if (z0 != z0) return;  // NaN never compares (safe_extras.py:65-66)
+    const bool inex1 = p.inex1[j] != 0, inex2 = p.inex2[j] != 0;
+    const double sc1 = ldexp(1.0, -p.shift1[j]), sc2 = ldexp(1.0, -p.shift2[j]);  // fixed point -> value, exact
+    // error radii of the two sums per non-NaN neighbor: half a unit, widened by 2^-12 for the exact engine's own fp64
+    // accumulation error (< n * 2^-53 * 2^22 units, n < 65536); zero for exactly representable columns
+    const double ra = inex1 ? 0.5 * sc1 * (1.0 + 0x1p-12) : 0.0, rb = inex2 ? 0.5 * sc2 * (1.0 + 0x1p-12) : 0.0;
+    const float sc1f = static_cast<float>(sc1), sc2f = static_cast<float>(sc2);  // (0 / inf out of range: filter off)
+    const float raf = static_cast<float>(ra) * 1.000001f, rbf = static_cast<float>(rb) * 1.000001f;
+    const float z0f = static_cast<float>(z0);
+    uint32_t neg = 0, pos = 0;
+    constexpr int U = 4;  // slots whose three sums are loaded before any is evaluated (memory-level parallelism)
+    for (int qq = p.q0; qq < p.q1; qq += U) {
+      int64_t l3[U], l1[U], l2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+          const bool live = qq + u < p.q1;
+          l3[u] = live ? __ldcs(p.s3 + (qq + u) * p.stride + at) : 0;
+          l1[u] = live ? __ldcs(p.s1 + (qq + u) * p.stride + at) : 0;
+          l2[u] = live ? __ldcs(p.s2 + (qq + u) * p.stride + at) : 0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = qq + u;
+        const int64_t cnt = l3[u];
+        if (cnt < 3) continue;  // z is NaN (also the padding slots of the last group)
+        const int64_t s1 = l1[u], s2 = l2[u];
+        {
+            // fp32 pre-filter: the interval below in single precision, accepted only well away from cancellation
+            // (spread < 64 x variance: every step is then good to ~1e-5 relative) and with a 1e-4 relative margin.
+            // All but ~1e-3 of the comparisons end here, without a single fp64 instruction.
+            const float Nf = static_cast<float>(cnt);
+            const float af = static_cast<float>(s1) * sc1f, bf = static_cast<float>(s2) * sc2f;
+            const float eaf = raf * Nf, ebf = rbf * Nf;
+            const float mh = (af + eaf) / Nf, ml = (af - eaf) / Nf;
+            const float mmax = fmaxf(fabsf(mh), fabsf(ml));
+            const float vmin = (bf - ebf) / Nf - mmax * mmax, spread = (bf + ebf) / Nf + mmax * mmax;
+            if (vmin > 0.f && spread < 64.f * vmin) {
+                const float bh = mh > 0.f ? bf - ebf : bf + ebf, bl = ml > 0.f ? bf + ebf : bf - ebf;
+                const float zhi = mh * rsqrtf(bh / Nf - mh * mh), zlo = ml * rsqrtf(bl / Nf - ml * ml);
+                const float tol = 1e-4f * (fabsf(zhi) + fabsf(zlo) + fabsf(z0f)) + 1e-30f;
+                if (zlo - tol > z0f) {
+                    ++pos;
+                    continue;
+                }
+                if (zhi + tol < z0f) {
+                    ++neg;
+                    continue;
+                }
+            }
+        }
+        const double a = static_cast<double>(s1) * sc1, b = static_cast<double>(s2) * sc2;
+        const double N = static_cast<double>(cnt);
+        bool undecided = false;
+        if (!inex1 && !inex2) {
+            const double z = zscore_from_sums(a, b, cnt);
+            neg += z <= z0;
+            pos += z >= z0;
+        } else {
+            const double ea = ra * N, eb = rb * N;
+            const double alo = a - ea, ahi = a + ea;
+            const double mmax = fmax(fabs(alo), fabs(ahi)) / N;
+            const double var_min = (b - eb) / N - mmax * mmax;
+            // well inside the domain only (no cancellation in EXX - EEX): else the exact engine decides
+            if (!(var_min > 0.0) || !((b + eb) / N + mmax * mmax < 1e6 * var_min)) {
+                undecided = true;
+            } else {
+                const double mh = ahi / N, ml = alo / N;
+                const double bh = ahi > 0.0 ? b - eb : b + eb;  // the z-score falls with the spread when the mean is > 0
+                const double bl = alo > 0.0 ? b + eb : b - eb;
+                double zhi = mh / sqrt(bh / N - mh * mh);
+                double zlo = ml / sqrt(bl / N - ml * ml);
+                zhi += 1e-12 * fabs(zhi) + 1e-300;
+                zlo -= 1e-12 * fabs(zlo) + 1e-300;
+                if (zlo > z0)
+                    ++pos;
+                else if (zhi < z0)
+                    ++neg;
+                else
+                    undecided = true;
+            }
+        }
+        if (undecided) {
+            const unsigned int k = atomicAdd(p.flag_count, 1u);
+            if (k < p.flag_cap) {
+                const int64_t node = p.node_of_row ? p.node_of_row[r] : r;
+                p.flag_ij[k] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(j);
+                p.flag_p[k] = static_cast<uint32_t>(q);
+            }
+        }
+      }
+    }
+    if (p.count && (neg | pos)) p.zc[at] += neg | (pos << 16);  // this thread owns the cell in this launch
+}
+
+// observed z-scores into the plan's layout: z0t[j][r] = z0[node_of_row[r]][j]  (tiled transpose, one pass per null)
+__global__ void __launch_bounds__(256) k_z_layout(const double* __restrict__ z0, const int32_t* __restrict__ node_of_row,
+                                                  int64_t n, int64_t m, int64_t rows_pad, double* __restrict__ z0t) {
+    __shared__ double tile[32][33];
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, j0 = static_cast<int64_t>(blockIdx.y) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k, j = j0 + tx;
+        double v = __longlong_as_double(0x7FF8000000000000ll);
+        if (r < n && j < m) v = z0[static_cast<int64_t>(node_of_row ? node_of_row[r] : r) * m + j];
+        tile[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t j = j0 + k, r = r0 + tx;
+        if (j < m && r < rows_pad) z0t[j * rows_pad + r] = tile[tx][k];
+    }
+}
+
+// packed counters of the plan's layout -> the caller's node-major arrays (added), counters cleared
+__global__ void __launch_bounds__(256) k_z_flush(uint32_t* __restrict__ zc, const int32_t* __restrict__ node_of_row,
+                                                 int64_t n, int64_t m, int64_t rows_pad, uint32_t* __restrict__ cneg,
+                                                 uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
+    __shared__ uint32_t tile[32][33];
+    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, j0 = static_cast<int64_t>(blockIdx.y) * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t j = j0 + k, r = r0 + tx;
+        uint32_t v = 0;
+        if (j < m && r < n) {
+            v = zc[j * rows_pad + r];
+            zc[j * rows_pad + r] = 0;
+        }
+        tile[k][tx] = v;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t r = r0 + k, j = j0 + tx;
+        const uint32_t v = tile[tx][k];
+        if (r < n && j < m && v) {
+            const int64_t at = static_cast<int64_t>(node_of_row ? node_of_row[r] : r) * m + j;
+            if (packed) {
+                atomicAdd(&packed[at], v);  // (the exact fix-ups of this batch add to the same words)
+            } else {
+                atomicAdd(&cneg[at], v & 0xffffu);
+                atomicAdd(&cpos[at], v >> 16);
+            }
+        }
+    }
+}
+
+// Exact re-evaluation of the undecided z-score comparisons.  One warp per entry: the lanes fetch 32 neighbors' values
+// at a time (the dependent index -> permutation -> value loads are what a sequential walk spends its time on), then
+// every lane adds them IN ASCENDING NEIGHBOR ORDER -- the exact engine's accumulation order (score_one), so the
+// result has the exact engine's bits.
+template <class T>
+__global__ void __launch_bounds__(256) k_zfix(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
+                                              const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                              int64_t m, const double* __restrict__ z0,
+                                              const uint64_t* __restrict__ flag_ij, const uint32_t* __restrict__ flag_p,
+                                              unsigned int total, uint32_t* __restrict__ cneg,
+                                              uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
+    const int lane = threadIdx.x & 31;
+    unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned int step = (gridDim.x * blockDim.x) >> 5;
+    for (; k < total; k += step) {
+        const uint64_t ij = flag_ij[k];
+        const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
+        const int32_t* pr = perm + static_cast<int64_t>(flag_p[k]) * n;
+        double sum = 0.0, sq = 0.0;
+        int64_t cnt = 0;
+        const int64_t e1 = row_ptr[i + 1];
+        for (int64_t e0 = row_ptr[i]; e0 < e1; e0 += 32) {
+            T v = static_cast<T>(0);
+            bool have = false;
+            if (e0 + lane < e1) {
+                v = b[static_cast<int64_t>(pr[col_idx[e0 + lane]]) * m + j];
+                have = v == v;
+            }
+            const int chunk = static_cast<int>(min(static_cast<int64_t>(32), e1 - e0));
+            for (int t = 0; t < chunk; ++t) {
+                const T vt = __shfl_sync(0xffffffffu, v, t);
+                if (__shfl_sync(0xffffffffu, have ? 1 : 0, t)) {
+                    sum += static_cast<double>(vt);
+                    sq += sq_like_numpy<T>(vt);
+                    ++cnt;
+                }
+            }
+        }
+        if (lane == 0) {
+            const double z = zscore_from_sums(sum, sq, cnt);
+            const double o = z0[i * m + j];
+            if (packed) {
+                const uint32_t inc = (z <= o ? 1u : 0u) + (z >= o ? 0x10000u : 0u);
+                if (inc) atomicAdd(&packed[i * m + j], inc);
+            } else {
+                if (z <= o) atomicAdd(&cneg[i * m + j], 1u);
+                if (z >= o) atomicAdd(&cpos[i * m + j], 1u);
+            }
+        }
+    }
+}
+
+bool tc_perm_counts_z(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
+                      uint32_t* packed) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    PhaseTrace tr_all(ctx, "tc.perm_counts_z(total)");
+    if (!e->tc) e->tc = build_plan(e);
+    TcPlan* pl = e->tc;
+    // +-inf / giant neighborhoods / fewer than 64 attributes: exact SIMT engine
+    if (!pl->usable || pl->mpad < 64 || e->m > 65535) return false;
+    build_operand(e, pl, XF_SQUARE);
+    build_operand(e, pl, XF_VALID);
+    const TcOperand* ops[3] = {&pl->op[XF_VALUE], &pl->op[XF_SQUARE], &pl->op[XF_VALID]};
+    if (!ops[1]->usable || !ops[2]->usable) return false;
+    SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
+    const double* z0 = enrich_observed(e, SB_SCORE_ZSCORE);
+
+    // batch: the three sum arrays of qb permutations (int64 [qb][rows_pad][mpad] each) take <= 6 GiB
+    const int64_t rows_pad = static_cast<int64_t>(pl->n_rb) * TC_PROWS;
+    const int64_t stride = rows_pad * pl->mpad;
+    int64_t qb = std::max<int64_t>(1, (6ll << 30) / (3 * stride * 8));
+    qb = std::min<int64_t>(std::min<int64_t>(qb, 64), num_perm);
+    DevBuf<int64_t> sums;
+    sums.reserve(static_cast<size_t>(3) * qb * stride);
+    size_t tile_max = 0;
+    for (int o = 0; o < 3; ++o) tile_max = std::max(tile_max, static_cast<size_t>(TC_KT) * 64 * ops[o]->D);
+    ctx->ws_bcat.reserve(static_cast<size_t>(qb) * pl->n_cg * pl->n_kt * tile_max);
+    const bool any_inexact = ops[0]->any_inexact || ops[1]->any_inexact;
+    const unsigned int cap = any_inexact ? std::max<unsigned int>(pl->flag_cap, 4u << 20) : 1u;
+    ctx->ws_flag_ij.reserve(cap);
+    ctx->ws_flag_p.reserve(cap);
+    DevBuf<unsigned int> fcount;
+    fcount.reserve(1);
+
+    // observed z-scores and decided-count accumulators in the plan's internal column-major layout
+    DevBuf<double> z0t;
+    DevBuf<uint32_t> zc;
+    z0t.reserve(static_cast<size_t>(stride));
+    zc.reserve(static_cast<size_t>(stride));
+    SB_CUDA(cudaMemsetAsync(zc.p, 0, static_cast<size_t>(stride) * sizeof(uint32_t), st));
+    {
+        dim3 grid(static_cast<unsigned>(sb_ceil_div(rows_pad, 32)), static_cast<unsigned>(sb_ceil_div(e->m, 32)));
+        SB_CHECK(grid.y <= 65535, "z-score tensor path: too many attributes");
+        k_z_layout<<<grid, 256, 0, st>>>(z0, pl->order, e->n, e->m, rows_pad, z0t.p);
+        SB_LAUNCH_CHECK(ctx);
+    }
+    auto zflush = [&]() {
+        dim3 grid(static_cast<unsigned>(sb_ceil_div(e->n, 32)), static_cast<unsigned>(sb_ceil_div(e->m, 32)));
+        k_z_flush<<<grid, 256, 0, st>>>(zc.p, pl->order, e->n, e->m, rows_pad, cneg, cpos, packed);
+        SB_LAUNCH_CHECK(ctx);
+    };
+    int64_t zc_perms = 0;
+
+    ZParams zp{};
+    zp.z0t = z0t.p;
+    zp.zc = zc.p;
+    zp.shift1 = ops[0]->shift.p;
+    zp.shift2 = ops[1]->shift.p;
+    zp.inex1 = ops[0]->inexact.p;
+    zp.inex2 = ops[1]->inexact.p;
+    zp.node_of_row = pl->order;
+    zp.n = e->n;
+    zp.m = e->m;
+    zp.mpad = pl->mpad;
+    zp.rows_pad = rows_pad;
+    zp.stride = stride;
+    zp.flag_ij = ctx->ws_flag_ij.p;
+    zp.flag_p = ctx->ws_flag_p.p;
+    zp.flag_count = fcount.p;
+    zp.flag_cap = cap;
+    auto zcount = [&](int q0, int q1, int64_t r0, int64_t r1, bool count) {
+        ZParams a = zp;
+        a.q0 = q0;
+        a.q1 = q1;
+        a.r0 = static_cast<int32_t>(r0);
+        a.r1 = static_cast<int32_t>(r1);
+        a.count = count ? 1 : 0;
+        dim3 grid(static_cast<unsigned>(sb_ceil_div(r1 - r0, 256)), static_cast<unsigned>(e->m));
+        KernelTimer kt(ctx, SB_K_FIXUP);
+        k_zcount<<<grid, 256, 0, st>>>(a);
+        SB_LAUNCH_CHECK(ctx);
+    };
+    auto zfix = [&](const int32_t* perm, unsigned int count) {
+        if (!count) return;
+        const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(count, 8), ctx->num_sms * 16));
+        KernelTimer kt(ctx, SB_K_SCORE);
+        if (e->dtype == SB_F32)
+            k_zfix<float><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b), perm, e->n,
+                                                  e->m, z0, zp.flag_ij, zp.flag_p, count, cneg, cpos, packed);
+        else
+            k_zfix<double><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(e->b), perm,
+                                                   e->n, e->m, z0, zp.flag_ij, zp.flag_p, count, cneg, cpos, packed);
+        SB_LAUNCH_CHECK(ctx);
+    };
+
+    int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
+    for (int64_t p0 = 0; p0 < num_perm; p0 += qb) {
+        const int64_t np = std::min(qb, num_perm - p0);
+        const int32_t* perm = perm_dev + p0 * e->n;
+        for (int o = 0; o < 3; ++o) {
+            launch_gather(ctx, pl, *ops[o], perm, static_cast<int>(np * pl->n_cg), static_cast<int>(np), ctx->ws_bcat.p, st);
+            run_batch_gemm(e, pl, *ops[o], TCM_STORE, 0, static_cast<int>(np), static_cast<int>(np), 0, pl->n_rb,
+                           sums.p + static_cast<size_t>(o) * qb * stride);
+            ktile_iters += static_cast<int64_t>(pl->n_tiles) * pl->n_cg * np * ops[o]->D / 3;  // in 3-digit tile units
+        }
+        zp.s1 = sums.p;
+        zp.s2 = sums.p + static_cast<size_t>(qb) * stride;
+        zp.s3 = sums.p + static_cast<size_t>(2) * qb * stride;
+        SB_CUDA(cudaMemsetAsync(fcount.p, 0, sizeof(unsigned int), st));
+        if (zc_perms + np > 60000) {  // 16-bit fields about to overflow
+            zflush();
+            zc_perms = 0;
+        }
+        zc_perms += np;
+        zcount(0, static_cast<int>(np), 0, e->n, true);
+        unsigned int h_count = 0;
+        if (any_inexact) {
+            SB_CUDA(cudaMemcpyAsync(&h_count, fcount.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+        }
+        if (h_count <= cap) {
+            zfix(perm, h_count);
+            flagged += h_count;
+        } else {
+            // list overflow: the decided counts are in; re-emit the flags in (slot, row range) pieces that fit
+            ++overflow_batches;
+            const int64_t rows_step = std::max<int64_t>(1, static_cast<int64_t>(cap) / std::max<int64_t>(1, e->m));
+            for (int q = 0; q < np; ++q)
+                for (int64_t r0 = 0; r0 < e->n; r0 += rows_step) {
+                    SB_CUDA(cudaMemsetAsync(fcount.p, 0, sizeof(unsigned int), st));
+                    zcount(q, q + 1, r0, std::min<int64_t>(e->n, r0 + rows_step), false);
+                    SB_CUDA(cudaMemcpyAsync(&h_count, fcount.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
+                    SB_CUDA(cudaStreamSynchronize(st));
+                    SB_CHECK(h_count <= cap, "internal error: z-score flag list overflow in recovery");
+                    zfix(perm, h_count);  // flag_p holds the batch-local slot q
+                    flagged += h_count;
+                }
+        }
+    }
+    zflush();
+    e->stats[0] = e->n * e->m * num_perm - flagged;
+    e->stats[1] = flagged;
+    e->stats[2] = pl->n_tiles_real;
+    e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
+    e->stats[4] = ops[0]->D;
+    e->stats[5] = ktile_iters;
+    e->stats[6] = overflow_batches;
+    return true;
 }
 
 }  // namespace sb

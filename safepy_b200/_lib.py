@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsafe_b200.so")
+# SAFE_B200_LIB selects another build of the library (A/B kernel experiments on one GPU box); default: the in-tree one
+LIB_PATH = os.environ.get("SAFE_B200_LIB") or os.path.join(HERE, "libsafe_b200.so")
 
 SB_F32, SB_F64 = 0, 1
 SCORE_TYPES = {"sum": 0, "z-score": 1}

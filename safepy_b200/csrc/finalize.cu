@@ -61,7 +61,7 @@ struct HostRing {
             used[i] = false;
         }
         const unsigned hw = std::thread::hardware_concurrency();
-        workers = static_cast<int>(std::max(2u, std::min(8u, hw ? hw : 2u)));
+        workers = static_cast<int>(std::max(2u, std::min(16u, hw ? hw : 2u)));
         for (int w = 0; w < workers; ++w) std::thread([this] { run(); }).detach();
     }
     void run() {

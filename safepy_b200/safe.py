@@ -129,6 +129,11 @@ class SafeB200Mixin:
 
     device = -1
     multi_gpu = True  # follow torch.distributed when the caller has initialised it (one process per GPU)
+    # Opt-in promise by the caller: the graph built by load_network(edges=..., x=..., y=...) has not been edited
+    # since.  define_neighborhoods then builds its CSR on the device from the arrays load_network kept (sb_graph_csr)
+    # instead of re-reading every edge of the graph object (0.4 s for 720k edges).  Off by default: the reference
+    # re-reads the edge data on every call, and in-place edits of 'length' cannot be detected from outside.
+    assume_graph_unchanged = False
     results_rank = None  # with several ranks: None = every rank receives the [N, M] result arrays, r = only rank r
     _plan = None  # enrichment plan of the compute_pvalues call in progress
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
@@ -157,7 +162,11 @@ class SafeB200Mixin:
         else:
             if metric == "shortpath_weighted_layout":
                 nr = self.neighborhood_radius * (np.max(x) - np.min(x))      # safe.py:404-405
-                indptr, indices, cost = graph_csr(self.graph, "length")
+                kept = getattr(self, "_loaded_edge_arrays", None)
+                if self.assume_graph_unchanged and kept is not None and kept[0] is self.graph:
+                    indptr, indices, cost = _lib.build_csr(ctx, n, kept[1][:, 0], kept[1][:, 1], kept[2])
+                else:
+                    indptr, indices, cost = graph_csr(self.graph, "length")
             else:
                 nr = self.neighborhood_radius                                # safe.py:409
                 indptr, indices, cost = graph_csr(self.graph, "weight")
@@ -558,6 +567,7 @@ class SAFE(SafeB200Mixin):
         if "node_key_attribute" in kwargs:
             self.node_key_attribute = kwargs["node_key_attribute"]
         self.validate_config()
+        self._loaded_edge_arrays = None
         if graph is None:
             x = np.asarray(x, dtype=np.float64)
             y = np.asarray(y, dtype=np.float64)
@@ -571,6 +581,11 @@ class SAFE(SafeB200Mixin):
                 length = np.asarray(length, dtype=np.float64)
                 graph.add_edges_from((int(u), int(v), {} if w != w else {"length": float(w)})
                                      for (u, v), w in zip(edges, length))
+                lo, hi = np.minimum(edges[:, 0], edges[:, 1]), np.maximum(edges[:, 0], edges[:, 1])
+                if len(np.unique(lo * x.shape[0] + hi)) == len(edges):
+                    # no repeated edge (nx.Graph would keep only the last).  Used only under assume_graph_unchanged;
+                    # an edge without 'length' costs Dijkstra's default 1 (safe.py:406-407)
+                    self._loaded_edge_arrays = (graph, edges.copy(), np.where(np.isnan(length), 1.0, length))
         self.graph = graph
 
     def load_attributes(self, attribute_file=None, **kwargs):

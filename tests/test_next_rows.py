@@ -172,3 +172,20 @@ def test_gpu_changed_lengths_change_the_neighborhoods(ctx, stage1_small):
     from safepy_b200._lib import unpack_packed
     assert np.array_equal(unpack_packed(after, len(g["x"])), dense)
     assert not np.array_equal(before, after)
+
+
+@pytest.mark.gpu
+def test_gpu_opt_in_device_csr_gives_the_same_neighborhoods(ctx, stage1_small):
+    """sf.assume_graph_unchanged = True: the CSR comes from sb_graph_csr on the arrays load_network kept (no walk over
+    the graph object); same neighborhoods as the reference.  Without the promise (default) in-place edits are honoured,
+    with it they are -- by contract -- not looked at."""
+    from safepy_b200 import SAFE
+    g = stage1_small
+    sf = SAFE(verbose=False)
+    sf.load_network(edges=g["edges"], x=g["x"], y=g["y"])
+    sf.assume_graph_unchanged = True
+    sf.define_neighborhoods(neighborhood_radius=float(g["r_layout"]))
+    assert np.array_equal(sf.neighborhoods.words, g["nb_layout"])
+    sf.load_network(graph=sf.graph)                       # a graph handed in as an object has no kept arrays
+    sf.define_neighborhoods(neighborhood_radius=float(g["r_layout"]))
+    assert np.array_equal(sf.neighborhoods.words, g["nb_layout"])

@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity gate (profiling runs only)")
     ap.add_argument("--no-variant-b", action="store_true", help="reference arm: skip the multiprocessing variant")
+    ap.add_argument("--no-ceiling", action="store_true",
+                    help="skip the same-box tensor-rate probe reported as roofline.tensor_ceiling_same_box")
     return ap.parse_args()
 
 
@@ -750,7 +752,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {
                 "workload": workload_name(cfg, args),
-                "step": "whole permutation null (operand prep + tcgen05 digit GEMM with in-kernel row gather and fused "
+                "step": "whole permutation null (operand prep + slab-ordered row gather + tcgen05 digit GEMM with fused "
                         "compare + fp64 fix-up%s)" % (" + NCCL all-reduce of the packed counts" if world > 1 else ""),
                 "parallelism": "stage 2: permutations sharded %d-way + one all-reduce of the counts; stage 1: source "
                                "rows sharded %d-way + one all-gather of the packed rows" % (world, world),
@@ -799,6 +801,30 @@ def run_ours(args):
                        "perm_index_replay_host_s": t_rng, "node_order_hint_host_s": t_order,
                        "compute_pvalues_null_s": sec_per_step},
         }
+    # ---- what the tensor pipe of THIS chip sustains on operands with this null's statistics (random digits, masks
+    # filled like the non-empty A tiles), L2-hot, through the same k_gemm pipeline with a store-nothing epilogue: the
+    # chip runs at its power cap and the draw depends on the data, so the executed rate is compared with this ceiling
+    # measured in the same process rather than with a nominal peak (speed-only probe, sb_selftest_mma_rate)
+    if rank == 0 and not args.no_ceiling:
+        try:
+            fill = out["config"]["a_tile_fill"]
+            ncols, kt, slots, sms = 64 * stats["digits"], 32, 32768, 148
+            os.environ["SB_RATE_RANDOM"] = str(max(1, min(100, int(round(100 * fill)))))
+            ceil = {}
+            for tag, dbg in (("pipeline_l2_hot", 0), ("no_bulk_copies", 2)):
+                ms = _lib.selftest_mma_rate(ctx, ncols, kt, slots, sms, dbg)
+                ceil[tag + "_int8_tops"] = sms * slots * kt * 2.0 * 128 * ncols * 64 / ms / 1e9
+                ceil[tag + "_ms"] = ms
+            del os.environ["SB_RATE_RANDOM"]
+            ex = out["roofline"]["executed_int8_tops"]
+            ceil["executed_frac_of_pipeline_l2_hot"] = ex / ceil["pipeline_l2_hot_int8_tops"] if ex else None
+            ceil["executed_frac_of_no_bulk_copies"] = ex / ceil["no_bulk_copies_int8_tops"] if ex else None
+            ceil["note"] = ("k_gemm pipeline on %d L2-resident k-tiles, random int8 digits, masks %s %% filled, %d "
+                            "accumulations per CTA pair; second figure without the bulk copies (MMAs + A expansion "
+                            "only)" % (kt, os.environ.get("SB_RATE_RANDOM", str(int(round(100 * fill)))), slots))
+            out["roofline"]["tensor_ceiling_same_box"] = ceil
+        except Exception as exc:  # noqa: BLE001
+            out["roofline"]["tensor_ceiling_same_box"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     # ---- neighborhood_score_type='z-score' on the same inputs (three digit contractions + fp64 comparison kernel per
     # permutation): a short resident pass of this rank's first permutations, reported beside the 'sum' null
     zscore = None

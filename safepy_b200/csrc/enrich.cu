@@ -237,12 +237,16 @@ __device__ double hg_sf(const double* __restrict__ lf, double k, double Mt, doub
         result = hg_pmf(lf, x, r, n, N);
         double diff = result;
         const int64_t lower = max(static_cast<int64_t>(0), n + r - N);
+        // the four factors are carried as doubles (exact below 2^53) and the quotient of a step does not depend on
+        // the running term, so the loop-carried chain is one multiply and one add
+        double fa = static_cast<double>(x), fb = static_cast<double>((N + x) - n - r);
+        double fc = static_cast<double>(1 + n - x), fd = static_cast<double>(1 + r - x);
         while (diff > eps) {
-            diff = static_cast<double>(x) * static_cast<double>((N + x) - n - r) * diff /
-                   (static_cast<double>(1 + n - x) * static_cast<double>(1 + r - x));
+            diff *= (fa * fb) * __drcp_rn(fc * fd);
             result += diff;
             if (x == lower) break;
             --x;
+            fa -= 1.0, fb -= 1.0, fc += 1.0, fd += 1.0;
         }
         result = 1.0 - result;
     } else {
@@ -252,11 +256,13 @@ __device__ double hg_sf(const double* __restrict__ lf, double k, double Mt, doub
             ++x;
             result = hg_pmf(lf, x, r, n, N);
             double diff = result;
+            double fa = static_cast<double>(n - x), fb = static_cast<double>(r - x);
+            double fc = static_cast<double>(x + 1), fd = static_cast<double>((N + x + 1) - n - r);
             while (x <= upper && diff > result * eps) {
-                diff = static_cast<double>(n - x) * static_cast<double>(r - x) * diff /
-                       (static_cast<double>(x + 1) * static_cast<double>((N + x + 1) - n - r));
+                diff *= (fa * fb) * __drcp_rn(fc * fd);
                 result += diff;
                 ++x;
+                fa -= 1.0, fb -= 1.0, fc += 1.0, fd += 1.0;
             }
         }
     }

@@ -2199,6 +2199,23 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     cudaStream_t st = ctx->stream;
     SB_CUDA(cudaMemsetAsync(d_a.p, 0x55, static_cast<size_t>(ktiles) * TC_PROWS * sizeof(uint64_t), st));
     SB_CUDA(cudaMemsetAsync(d_b.p, 1, static_cast<size_t>(ktiles) * tile_b, st));
+    if (const char* fill = getenv("SB_RATE_RANDOM")) {
+        // operands with the statistics of a real null (random digits, masks filled to SB_RATE_RANDOM percent): the
+        // tensor pipe's power draw, and with it the clock the chip holds under its cap, depends on the data
+        const unsigned pct = static_cast<unsigned>(atoi(fill));
+        uint64_t x = 0x9E3779B97F4A7C15ull;
+        auto next = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+        std::vector<uint64_t> ha(static_cast<size_t>(ktiles) * TC_PROWS);
+        for (auto& w : ha) {
+            w = 0;
+            for (int b = 0; b < 64; ++b) w |= static_cast<uint64_t>(next() % 100 < pct) << b;
+        }
+        std::vector<int8_t> hb(static_cast<size_t>(ktiles) * tile_b);
+        for (auto& v : hb) v = static_cast<int8_t>(next() >> 24);
+        SB_CUDA(cudaMemcpyAsync(d_a.p, ha.data(), ha.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpyAsync(d_b.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
     std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
     for (int i = 0; i < ktiles; ++i) kts[i] = i;
     // all units share tiles [0, ktiles): one row block, the CTAs are spread over the q chunks

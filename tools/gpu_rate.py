@@ -19,8 +19,10 @@ def run(tag, ncols, grid, dbg=0, kt=32, slots=64):
 
 
 slots = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-for grid in (1, 148):
-    for n in (64, 128, 192):
+grids = tuple(int(g) for g in sys.argv[2].split(",")) if len(sys.argv) > 2 else (1, 148)
+widths = tuple(int(g) for g in sys.argv[3].split(",")) if len(sys.argv) > 3 else (64, 128, 192)
+for grid in grids:
+    for n in widths:
         for dbg, tag in ((0, "production"), (1, "copies only"), (2, "MMAs only"), (3, "barriers only"),
                          (6, "MMA issue only"), (7, "issue loop only")):
             run(tag, n, grid, dbg, 32, slots)

@@ -53,9 +53,9 @@ static_assert(TC_APS * 16 == 32 && TC_ASLOTS == 4 && TC_TPS == 2 * TC_APS, "A sl
 constexpr int TC_SCHED = 4;              // depth of the work-unit ring (scheduler -> all other roles of the pair)
 constexpr int TC_KT_SMEM = 1024;         // k-tile ids of the current row block cached in smem (tail: global)
 
-enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8 };
+enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8, TCM_Z = 16 };
 // kernel flavours (compile-time, so the hot epilogue carries no mode tests)
-enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2 };
+enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2, TCK_Z = 3 };
 
 struct GemmParams {
     const uint64_t* a_bits;   // [n_tiles / TPS][2 (CTA rank)][TPS][128]: bit k of a word = A[row][64 kt + k]
@@ -86,6 +86,13 @@ struct GemmParams {
     int32_t dbg;              // rate probe only: bit0 = no MMAs, bit1 = no copies, bit2 = MMA warp does not wait for operands
     uint32_t b_kstep;         // descriptor start-address advance per K=32 MMA
     long long* prof;          // per-role cycle counters [16] (see print_prof), or nullptr
+    // TCK_Z (z-score null): a column group is 32 attributes x 6 digit planes (3 of the value, 2 of the square, 1 of
+    // the non-NaN indicator), so one accumulation holds the three sums of a cell (see the epilogue)
+    const double* z0t;        // [32 n_cg][rows_pad] observed z-scores (exact engine), internal row order
+    const float4* zcol;       // per attribute {2^-shift1, 2^-shift2, error radius per neighbor of the sum, of the squares}
+    const int32_t *zshift1, *zshift2;
+    const uint8_t *zinex1, *zinex2;
+    int64_t rows_pad;
 };
 
 // cycle accounting per role, enabled by a non-null GemmParams::prof (SB_TRACE runs and the rate probe)
@@ -152,6 +159,48 @@ __device__ __forceinline__ void expand_bits(uint64_t w, uint32_t (&r)[16]) {
         r[g * 4 + 2] = expand4<0x00000000u, 0xFFFFFFFFu>(x);
         r[g * 4 + 3] = expand4<0xFF00FF00u, 0xFF00FF00u>(word >> (16 * (g & 1) + 3));
     }
+}
+
+// z-score comparison of one (cell, permutation) in fp64 from the exact fixed-point sums -- what the fp32 filter of the
+// TCK_Z epilogue could not settle (~1e-3 of the comparisons).  Columns whose values AND squares are exactly
+// representable: the fixed-point sums are the exact sums and the z-score is evaluated by the very function the exact
+// engine uses (same bits, ties included).  Otherwise |fixed-point sum - true sum| <= (non-NaN neighbors) / 2 units,
+// which bounds the z-score from both sides (it increases with the sum and is monotone in the sum of squares with the
+// sign of the mean); an interval that does not contain the observed z-score decides rigorously, the rest is left to the
+// exact engine (*undecided).  Returns the packed count increment (pos << 16 | neg).
+__device__ __noinline__ uint32_t z_compare_fp64(long long s1, long long s2, int cnt, double z0, int shift1,
+                                                int shift2, bool inex1, bool inex2, bool* undecided) {
+    const double sc1 = ldexp(1.0, -shift1), sc2 = ldexp(1.0, -shift2);  // fixed point -> value, exact
+    const double a = static_cast<double>(s1) * sc1, b = static_cast<double>(s2) * sc2;
+    const double N = static_cast<double>(cnt);
+    *undecided = false;
+    if (!inex1 && !inex2) {
+        const double z = zscore_from_sums(a, b, cnt);
+        return (z <= z0 ? 1u : 0u) | (z >= z0 ? 0x10000u : 0u);
+    }
+    // error radii of the two sums per non-NaN neighbor: half a unit, widened by 2^-12 for the exact engine's own fp64
+    // accumulation error (< n * 2^-53 * 2^22 units, n < 65536); zero for exactly representable columns
+    const double ra = inex1 ? 0.5 * sc1 * (1.0 + 0x1p-12) : 0.0, rb = inex2 ? 0.5 * sc2 * (1.0 + 0x1p-12) : 0.0;
+    const double ea = ra * N, eb = rb * N;
+    const double alo = a - ea, ahi = a + ea;
+    const double mmax = fmax(fabs(alo), fabs(ahi)) / N;
+    const double var_min = (b - eb) / N - mmax * mmax;
+    // well inside the domain only (no cancellation in EXX - EEX): else the exact engine decides
+    if (!(var_min > 0.0) || !((b + eb) / N + mmax * mmax < 1e6 * var_min)) {
+        *undecided = true;
+        return 0u;
+    }
+    const double mh = ahi / N, ml = alo / N;
+    const double bh = ahi > 0.0 ? b - eb : b + eb;  // the z-score falls with the spread when the mean is > 0
+    const double bl = alo > 0.0 ? b + eb : b - eb;
+    double zhi = mh / sqrt(bh / N - mh * mh);
+    double zlo = ml / sqrt(bl / N - ml * ml);
+    zhi += 1e-12 * fabs(zhi) + 1e-300;
+    zlo -= 1e-12 * fabs(zlo) + 1e-300;
+    if (zlo > z0) return 0x10000u;
+    if (zhi < z0) return 1u;
+    *undecided = true;
+    return 0u;
 }
 
 // Work units are numbered so that consecutive units share operands in L2: inside a band of row blocks (whose A
@@ -551,6 +600,28 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 #pragma unroll
                 for (int cc = 0; cc < 32; ++cc) cnt[cc] = 0;
             }
+            // TCK_Z: this thread owns 16 attributes of the group (its 32-column half of the three plane pairs holds
+            // all six planes of them); their observed z-scores and column constants sit in a warp-private smem area
+            float* const zw = reinterpret_cast<float*>(smem + C::OFF_S0HI) + warp * (16 * 32 + 16 * 4);
+            const int64_t jz0 = static_cast<int64_t>(cg) * 32 + half * 16;
+            if (KIND == TCK_Z) {
+                __syncwarp();
+#pragma unroll 4
+                for (int aa = 0; aa < 16; ++aa) {
+                    const int64_t j = jz0 + aa;
+                    float z = __int_as_float(0x7fc00000);
+                    if (row_ok && j < p.m) z = static_cast<float>(p.z0t[j * p.rows_pad + row]);
+                    zw[aa * 32 + lane] = z;
+                }
+                if (lane < 16) {
+                    float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (jz0 + lane < p.m) c = p.zcol[jz0 + lane];
+                    reinterpret_cast<float4*>(zw + 16 * 32)[lane] = c;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) cnt[cc] = 0;
+            }
             // one band per warp-uniform test: columns of a group are normally all exact or all inexact
             const bool all_exact = __all_sync(0xffffffffu, inexact_mask == 0);
             const bool all_inexact = __all_sync(0xffffffffu, inexact_mask == 0xffffffffu);
@@ -562,8 +633,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 const uint32_t t_addr = tbase + (static_cast<uint32_t>(quarter * 32) << 16) + buf * 256 + c0;
                 uint32_t flagmask = 0;
                 constexpr int CW = 8;  // columns per TMEM load: keeps the live accumulator set at 8 D registers
+                if (KIND == TCK_Z) {
+                    // TMEM column d * 64 + half * 32 + s * 16 + a = plane 2 d + s of attribute half * 16 + a;
+                    // planes 0-2: digits of the sum of the values, 3-4: of the sum of the squares, 5: non-NaN neighbors
+                    const float4* const zc4 = reinterpret_cast<const float4*>(zw + 16 * 32);
 #pragma unroll
-                for (int ch = 0; ch < ((p.dbg & 16) ? 0 : 32 / CW); ++ch) {  // dbg 16: timing experiment, no epilogue work
+                    for (int it = 0; it < 2; ++it) {
+                        uint32_t acc[6][8];
+#pragma unroll
+                        for (int pl = 0; pl < 6; ++pl) tmem_ld8(t_addr + (pl >> 1) * 64 + (pl & 1) * 16 + it * 8, acc[pl]);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int x = 0; x < 8; ++x) {
+                            const int aa = it * 8 + x;
+                            const float z0f = zw[aa * 32 + lane];
+                            const int cntv = static_cast<int32_t>(acc[5][x]);
+                            if (!(z0f == z0f) || cntv < 3) continue;  // NaN never compares (safe_extras.py:65-66)
+                            const int v0 = static_cast<int32_t>(acc[0][x]);
+                            const int hi1 = (v0 >> 8) + static_cast<int32_t>(acc[1][x]) +
+                                            (static_cast<int32_t>(acc[2][x]) << 8);  // sum = hi1 * 256 + lo1
+                            const int lo1 = v0 & 255;
+                            const int s2 = static_cast<int32_t>(acc[3][x]) + (static_cast<int32_t>(acc[4][x]) << 8);
+                            const float4 zc = zc4[aa];
+                            {
+                                // fp32 filter: the interval of z_compare_fp64 in single precision, accepted only well
+                                // away from cancellation (spread < 64 x variance: every step is then good to ~1e-5
+                                // relative) and with a 1e-4 relative margin.  All but ~1e-3 of the comparisons end here.
+                                const float Nf = static_cast<float>(cntv), rN = 1.f / Nf;
+                                const float af = fmaf(static_cast<float>(hi1), 256.f, static_cast<float>(lo1)) * zc.x;
+                                const float bf = static_cast<float>(s2) * zc.y;
+                                const float eaf = zc.z * Nf, ebf = zc.w * Nf;
+                                const float mh = (af + eaf) * rN, ml = (af - eaf) * rN;
+                                const float mmax = fmaxf(fabsf(mh), fabsf(ml));
+                                const float vmin = (bf - ebf) * rN - mmax * mmax, spread = (bf + ebf) * rN + mmax * mmax;
+                                if (vmin > 0.f && spread < 64.f * vmin) {
+                                    const float bh = mh > 0.f ? bf - ebf : bf + ebf, bl = ml > 0.f ? bf + ebf : bf - ebf;
+                                    const float zhi = mh * rsqrtf(bh * rN - mh * mh), zlo = ml * rsqrtf(bl * rN - ml * ml);
+                                    const float tol = 1e-4f * (fabsf(zhi) + fabsf(zlo) + fabsf(z0f)) + 1e-30f;
+                                    if (zlo - tol > z0f) {
+                                        cnt[aa] += 0x10000u;
+                                        continue;
+                                    }
+                                    if (zhi + tol < z0f) {
+                                        cnt[aa] += 1u;
+                                        continue;
+                                    }
+                                }
+                            }
+                            const int64_t j = jz0 + aa;
+                            bool und;
+                            cnt[aa] += z_compare_fp64(static_cast<long long>(hi1) * 256 + lo1, s2, cntv,
+                                                      p.z0t[j * p.rows_pad + row], p.zshift1[j], p.zshift2[j],
+                                                      p.zinex1[j] != 0, p.zinex2[j] != 0, &und);
+                            if (und) flagmask |= 1u << aa;
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ch = 0; ch < ((KIND == TCK_Z || (p.dbg & 16)) ? 0 : 32 / CW); ++ch) {  // dbg 16: timing experiment, no epilogue work
                     uint32_t acc[D][CW];
 #pragma unroll
                     for (int d = 0; d < D; ++d) tmem_ld8(t_addr + d * 64 + ch * CW, acc[d]);
@@ -664,6 +791,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                         mbar_arrive_cluster_relaxed(ld_tempty + buf * 8);
                 }
                 ++acc_it;
+                if (KIND == TCK_Z) {
+                    if (!(p.mode & TCM_COUNT)) {
+#pragma unroll
+                        for (int cc = 0; cc < 16; ++cc) cnt[cc] = 0;
+                    }
+                    // rare (~1e-4): comparisons the fixed-point sums cannot decide go to the exact engine (k_zfix)
+                    if (flagmask && (p.mode & TCM_FLAG)) {
+                        while (flagmask) {
+                            const int aa = __ffs(flagmask) - 1;
+                            flagmask &= flagmask - 1;
+                            const unsigned int k = atomicAdd(p.flag_count, 1u);
+                            if (k < p.flag_cap) {
+                                p.flag_ij[k] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(jz0 + aa);
+                                p.flag_p[k] = static_cast<uint32_t>(q);
+                            }
+                        }
+                    }
+                }
                 if (KIND == TCK_COUNT) {
                     if (!(p.mode & TCM_COUNT)) {
 #pragma unroll
@@ -688,6 +833,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                         }
                     }
                 }
+            }
+            if (KIND == TCK_Z && (p.mode & TCM_COUNT) && row_ok) {
+#pragma unroll
+                for (int aa = 0; aa < 16; ++aa)
+                    if (jz0 + aa < p.m && cnt[aa]) atomicAdd(&p.cpk[node * p.m + jz0 + aa], cnt[aa]);
             }
             if (KIND == TCK_COUNT && (p.mode & TCM_COUNT) && row_ok) {
                 if (SMALL_M) {
@@ -873,10 +1023,12 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
     int hi = INT_MIN, lo = INT_MAX, bad = 0;
     for (int64_t r = r0; r < r1; ++r) {
-        const double v = xf_value<XF, T>(b[r * m + j]);
+        const T raw = b[r * m + j];
+        if (raw != raw) bad |= 2;  // a NaN entry: the number of valid neighbors then depends on the permutation
+        const double v = xf_value<XF, T>(raw);
         if (v != v || v == 0.0) continue;
         if (isinf(v)) {
-            bad = 1;
+            bad |= 1;
             continue;
         }
         int e;
@@ -889,7 +1041,7 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
         atomicMax(&kmax[j], hi);
         atomicMin(&lmin[j], lo);
     }
-    if (bad) atomicOr(flags, 1);
+    if (bad) atomicOr(flags, bad);
 }
 
 // fixed-point digits: q = rint(v * 2^shift[j]); stored are the D balanced base-256 int8 digits of -q (the expanded
@@ -1037,6 +1189,7 @@ struct TcOperand {
     bool built = false;
     bool usable = true;        // false: +-inf among the values
     bool any_inexact = false;  // some column is not exactly representable (its comparisons carry an error band)
+    bool has_nan = false;      // some entry of the attribute matrix is NaN
     DevBuf<int8_t> digits;
     DevBuf<int32_t> shift;     // per-column binary exponent of the fixed point: q = rint(v * 2^shift[j])
     DevBuf<uint8_t> inexact;   // [mpad]
@@ -1058,6 +1211,16 @@ struct TcPlan {
     int64_t cpk_perms = 0;  // permutations accumulated in the packed counters since the last unpack (16-bit fields)
     uint32_t* cpk = nullptr;  // packed counters of the call in progress (context scratch or the caller's array)
     unsigned int flag_cap = 0;
+    // z-score null: the 'sum' plan owns a second plan whose column groups are 32 attributes x 6 planes (build_plan_z);
+    // the fields below belong to that second plan
+    TcPlan* z = nullptr;
+    DevBuf<int32_t> z_shift2;          // fixed point of the squares
+    DevBuf<uint8_t> z_inex2;
+    DevBuf<float4> z_col;              // filter constants per attribute (k_zcol)
+    const int32_t* z_shift1 = nullptr;  // fixed point of the values: the owning plan's
+    const uint8_t* z_inex1 = nullptr;
+    const double* z_z0t = nullptr;     // observed z-scores of the null in progress, plan layout
+    ~TcPlan() { delete z; }
 };
 
 void tc_plan_destroy(TcPlan* p) { delete p; }
@@ -1093,7 +1256,10 @@ static void launch_gemm(sb_ctx* ctx, const GemmParams& gp, int grid) {
 
 template <int D, bool PROF>
 static void launch_gemm_k(sb_ctx* ctx, int kind, bool small_m, const GemmParams& gp, int grid) {
-    if (kind == TCK_RAW)
+    if (kind == TCK_Z) {
+        if constexpr (D == 3)  // six planes of 32 attributes: always the 192-column configuration
+            launch_gemm<3, TCK_Z, false, PROF>(ctx, gp, grid);
+    } else if (kind == TCK_RAW)
         launch_gemm<D, TCK_RAW, false, PROF>(ctx, gp, grid);
     else if (kind == TCK_STORE)
         small_m ? launch_gemm<D, TCK_STORE, true, false>(ctx, gp, grid)
@@ -1112,7 +1278,7 @@ static void launch_gemm_d(sb_ctx* ctx, int D, const GemmParams& gp_in, int grid)
     ctx->ws_counter.reserve(1);
     gp.unit_counter = ctx->ws_counter.p;
     SB_CUDA(cudaMemsetAsync(gp.unit_counter, 0, sizeof(unsigned int), ctx->stream));
-    const int kind = (gp.mode & TCM_RAW) ? TCK_RAW : (gp.mode & TCM_STORE) ? TCK_STORE : TCK_COUNT;
+    const int kind = (gp.mode & TCM_Z) ? TCK_Z : (gp.mode & TCM_RAW) ? TCK_RAW : (gp.mode & TCM_STORE) ? TCK_STORE : TCK_COUNT;
     const bool small_m = gp.mpad < 64;
     if (gp.prof) {  // cycle accounting compiled in (SB_TRACE / rate probe)
         if (D == 1)
@@ -1195,6 +1361,16 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl, const TcOperand& op) {
     gp.b_sbo = 128;        //             stride between 16-column chunks
     gp.q_wrap = INT_MAX;
     gp.b_kstep = 4 * (ncols / 2) * 8;
+    if (pl->z_col.p) {  // z-score plan
+        gp.z0t = pl->z_z0t;
+        gp.zcol = pl->z_col.p;
+        gp.zshift1 = pl->z_shift1;
+        gp.zshift2 = pl->z_shift2.p;
+        gp.zinex1 = pl->z_inex1;
+        gp.zinex2 = pl->z_inex2.p;
+        gp.rows_pad = static_cast<int64_t>(pl->n_rb) * TC_PROWS;
+        gp.flag_cap = pl->flag_cap;  // one list, no buckets
+    }
     return gp;
 }
 
@@ -1202,19 +1378,17 @@ static int64_t slots_for(const TcPlan* pl, int64_t perms) {
     return pl->mpad >= 64 ? perms * pl->n_cg : sb_ceil_div(perms, pl->pps);
 }
 
-// Digit planes of one operand (XF_*) and its observed fixed-point scores
-static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
+// Per-column exponent ranges of one operand (XF_*) on the host; returns k_col_range's flags (1: +-inf, 2: NaN seen)
+static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax, std::vector<int32_t>& h_lmin) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
-    TcOperand& op = pl->op[xf];
-    if (op.built) return;
     const int64_t n = e->n, m = e->m;
-    PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.digits");
     DevBuf<int32_t> kmax, lmin, flags;
     kmax.reserve(m);
     lmin.reserve(m);
     flags.reserve(1);
-    std::vector<int32_t> h_kmax(m, INT_MIN), h_lmin(m, INT_MAX);
+    h_kmax.assign(m, INT_MIN);
+    h_lmin.assign(m, INT_MAX);
     SB_CUDA(cudaMemcpyAsync(kmax.p, h_kmax.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(lmin.p, h_lmin.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t), st));
@@ -1243,7 +1417,21 @@ static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
     SB_CUDA(cudaMemcpyAsync(h_lmin.data(), lmin.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
+    return h_flags;
+}
+
+// Digit planes of one operand (XF_*) and its observed fixed-point scores
+static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    TcOperand& op = pl->op[xf];
+    if (op.built) return;
+    const int64_t n = e->n, m = e->m;
+    PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.digits");
+    std::vector<int32_t> h_kmax, h_lmin;
+    const int32_t h_flags = column_ranges(e, xf, h_kmax, h_lmin);
     op.built = true;
+    op.has_nan = (h_flags & 2) != 0;
     if (h_flags & 1) {
         op.usable = false;
         delete tr;
@@ -1337,7 +1525,7 @@ static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
     delete tr;
 }
 
-static TcPlan* build_plan(sb_enrich* e) {
+static TcPlan* build_plan(sb_enrich* e, bool zgroups = false) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
     TcPlan* pl = new TcPlan;
@@ -1347,7 +1535,12 @@ static TcPlan* build_plan(sb_enrich* e) {
         const int64_t n = e->n, m = e->m;
         pl->n = n;
         pl->m = m;
-        if (m >= 64) {
+        if (zgroups) {  // z-score plan: a group is 32 attributes (x 6 planes = the 192 columns of an accumulation)
+            pl->n_cg = static_cast<int32_t>(sb_ceil_div(m, 32));
+            pl->mpad = static_cast<int64_t>(pl->n_cg) * 64;
+            pl->pps = 1;
+            pl->log2_mpad = 0;
+        } else if (m >= 64) {
             pl->mpad = sb_ceil_div(m, 64) * 64;
             pl->n_cg = static_cast<int32_t>(pl->mpad / 64);
             pl->pps = 1;
@@ -1445,6 +1638,7 @@ static TcPlan* build_plan(sb_enrich* e) {
         const int64_t min_cap = static_cast<int64_t>(TC_PROWS) * 64 * pl->n_cg;  // >= one row block per bucket
         pl->flag_cap = static_cast<unsigned int>(min_cap);
         pl->flag_count.reserve(pl->n_cg);
+        if (zgroups) return pl;  // build_plan_z fills in the records
         build_operand(e, pl, XF_VALUE);
         pl->usable = pl->op[XF_VALUE].usable;
         if (pl->op[XF_VALUE].any_inexact) {  // exactly representable data never flags: nothing to reserve
@@ -1703,136 +1897,74 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
 
 // ================================================================================================ z-score null
 // neighborhood_score_type = 'z-score' (safe_extras.py:19-31) on the tensor cores.  Per permutation the score needs
-// three contractions with the neighborhood matrix -- sum of the values (XF_VALUE), sum of their squares (XF_SQUARE), number
-// of non-NaN values (XF_VALID) -- and then fp64 arithmetic per cell, which does not belong in the GEMM's epilogue.  So
-// the digit GEMM runs in its STORE flavour for a small batch of permutations and writes the three exact fixed-point
-// sums; k_zcount turns them into the comparison against the observed z-score:
-//   * columns whose values AND squares are exactly representable (binary / integer / dyadic data): the fixed-point
-//     sums are the exact sums, the fp64 z-score is evaluated by the very function the exact engine uses
-//     (zscore_from_sums) and compared directly -- same bits as the SIMT engine, no fix-ups;
-//   * otherwise |fixed-point sum - true sum| <= (non-NaN neighbors) / 2 units, which bounds the z-score from both
-//     sides (it is increasing in the sum, and monotone in the sum of squares with the sign of the mean); a comparison
-//     whose interval does not contain the observed z-score is decided rigorously, the rest go to a list that k_zfix
-//     re-evaluates with the exact engine's own accumulation (score_one order), one thread per entry.
-struct ZParams {
-    const int64_t *s1, *s2, *s3;  // [qb][mpad][rows_pad] fixed-point sums of the batch (value, square, valid)
-    const double* z0t;            // [mpad][rows_pad] observed z-score (exact engine) in the plan's internal layout
-    uint32_t* zc;                 // [mpad][rows_pad] packed counts (pos << 16 | neg) of the decided comparisons
-    const int32_t *shift1, *shift2;
-    const uint8_t *inex1, *inex2;
-    const int32_t* node_of_row;   // internal row -> node (nullptr: identity)
-    int64_t n, m, mpad, rows_pad, stride;  // stride = rows_pad * mpad
-    int32_t q0, q1;               // slots of the batch to evaluate
-    int32_t r0, r1;               // internal rows to evaluate
-    int32_t count;                // 0: emit flags only (overflow recovery)
-    uint64_t* flag_ij;
-    uint32_t* flag_p;
-    unsigned int* flag_count;
-    unsigned int flag_cap;
-};
+// three contractions with the neighborhood matrix -- the sum of the neighbors' values, the sum of their squares (rounded
+// like np.power(B, 2) rounds them) and the number of non-NaN neighbors -- and then M / std in fp64.  All three come out
+// of ONE accumulation: a column group of the z plan is 32 attributes x 6 int8 digit planes (3 of the value, 2 of the
+// square, 1 of the non-NaN indicator) = the same 192-byte records and 192-column MMAs as the 'sum' null, and the
+// epilogue (k_gemm<3, TCK_Z>) holds the three exact fixed-point sums of a cell in registers:
+//   * an fp32 filter with a 1e-4 margin settles all but ~1e-3 of the comparisons against the observed z-score;
+//   * the rest is evaluated in fp64 (z_compare_fp64): by the exact engine's own formula where values and squares are
+//     exactly representable (binary / integer / dyadic data: same bits, no fix-ups), else through a rigorous interval;
+//   * comparisons whose interval contains the observed z-score (~1e-4) go to a list that k_zfix re-evaluates with the
+//     exact engine's own accumulation (score_one order), one warp per entry.
+// No sum ever reaches HBM (round-2 first version: three STORE GEMMs + a comparison kernel, 24 bytes of sums per
+// comparison written and read back, 1.16 ms per C3 permutation).
 
-// a warp = 32 consecutive internal rows of one attribute column: sums, observed z-scores and counters are all in the
-// plan's column-major internal layout, i.e. every access is a contiguous run (the caller's node-major arrays are
-// touched once per null, by k_z_flush)
-__global__ void __launch_bounds__(256) k_zcount(const ZParams p) {
-    const int64_t r = p.r0 + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-    const int64_t j = blockIdx.y;
-    if (j >= p.m || r >= p.r1 || r >= p.n) return;
-    const int64_t at = j * p.rows_pad + r;
-    const double z0 = p.z0t[at];
-    if (z0 != z0) return;  // NaN never compares (safe_extras.py:65-66)
-    const bool inex1 = p.inex1[j] != 0, inex2 = p.inex2[j] != 0;
-    const double sc1 = ldexp(1.0, -p.shift1[j]), sc2 = ldexp(1.0, -p.shift2[j]);  // fixed point -> value, exact
-    // error radii of the two sums per non-NaN neighbor: half a unit, widened by 2^-12 for the exact engine's own fp64
-    // accumulation error (< n * 2^-53 * 2^22 units, n < 65536); zero for exactly representable columns
-    const double ra = inex1 ? 0.5 * sc1 * (1.0 + 0x1p-12) : 0.0, rb = inex2 ? 0.5 * sc2 * (1.0 + 0x1p-12) : 0.0;
-    const float sc1f = static_cast<float>(sc1), sc2f = static_cast<float>(sc2);  // (0 / inf out of range: filter off)
-    const float raf = static_cast<float>(ra) * 1.000001f, rbf = static_cast<float>(rb) * 1.000001f;
-    const float z0f = static_cast<float>(z0);
-    uint32_t neg = 0, pos = 0;
-    constexpr int U = 4;  // slots whose three sums are loaded before any is evaluated (memory-level parallelism)
-    for (int qq = p.q0; qq < p.q1; qq += U) {
-      int64_t l3[U], l1[U], l2[U];
+// z records: digits[(cg * n + r) * 192 + d * 64 + h * 32 + s * 16 + a] = plane 2 d + s of attribute cg * 32 + h * 16 + a,
+// i.e. the 32-column half h of every plane pair d -- what one epilogue warp reads -- carries all six planes of 16
+// attributes.  Planes 0-2: balanced base-256 digits of -rint(v 2^shift1), 3-4: of -rint(v^2 2^shift2), 5: -1 where v
+// is not NaN (the expanded neighborhood operand is 0 / -1).
+template <class T>
+__global__ void k_quantize_z(const T* __restrict__ b, int64_t n, int64_t m, int32_t n_cg,
+                             const int32_t* __restrict__ shift1, const int32_t* __restrict__ shift2,
+                             int8_t* __restrict__ digits) {
+    const int64_t total = static_cast<int64_t>(n_cg) * n * 32;
+    int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; idx < total; idx += step) {
+        const int a32 = static_cast<int>(idx & 31);
+        const int64_t r = (idx >> 5) % n, cg = (idx >> 5) / n;
+        const int64_t j = cg * 32 + a32;
+        int q1 = 0, q2 = 0, valid = 0;
+        if (j < m) {
+            const T v = b[r * m + j];
+            if (v == v) {
+                valid = -1;
+                q1 = -static_cast<int>(rint(ldexp(static_cast<double>(v), shift1[j])));
+                q2 = -static_cast<int>(rint(ldexp(xf_value<XF_SQUARE, T>(v), shift2[j])));
+            }
+        }
+        int8_t pl[6];
+        int dig = static_cast<int>(static_cast<int8_t>(q1 & 0xff));
+        pl[0] = static_cast<int8_t>(dig);
+        q1 = (q1 - dig) >> 8;
+        dig = static_cast<int>(static_cast<int8_t>(q1 & 0xff));
+        pl[1] = static_cast<int8_t>(dig);
+        pl[2] = static_cast<int8_t>((q1 - dig) >> 8);
+        dig = static_cast<int>(static_cast<int8_t>(q2 & 0xff));
+        pl[3] = static_cast<int8_t>(dig);
+        pl[4] = static_cast<int8_t>((q2 - dig) >> 8);
+        pl[5] = static_cast<int8_t>(valid);
+        int8_t* const rec = digits + ((cg * n + r) * 192) + (a32 >> 4) * 32 + (a32 & 15);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-          const bool live = qq + u < p.q1;
-          l3[u] = live ? __ldcs(p.s3 + (qq + u) * p.stride + at) : 0;
-          l1[u] = live ? __ldcs(p.s1 + (qq + u) * p.stride + at) : 0;
-          l2[u] = live ? __ldcs(p.s2 + (qq + u) * p.stride + at) : 0;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int q = qq + u;
-        const int64_t cnt = l3[u];
-        if (cnt < 3) continue;  // z is NaN (also the padding slots of the last group)
-        const int64_t s1 = l1[u], s2 = l2[u];
-        {
-            // fp32 pre-filter: the interval below in single precision, accepted only well away from cancellation
-            // (spread < 64 x variance: every step is then good to ~1e-5 relative) and with a 1e-4 relative margin.
-            // All but ~1e-3 of the comparisons end here, without a single fp64 instruction.
-            const float Nf = static_cast<float>(cnt);
-            const float af = static_cast<float>(s1) * sc1f, bf = static_cast<float>(s2) * sc2f;
-            const float eaf = raf * Nf, ebf = rbf * Nf;
-            const float mh = (af + eaf) / Nf, ml = (af - eaf) / Nf;
-            const float mmax = fmaxf(fabsf(mh), fabsf(ml));
-            const float vmin = (bf - ebf) / Nf - mmax * mmax, spread = (bf + ebf) / Nf + mmax * mmax;
-            if (vmin > 0.f && spread < 64.f * vmin) {
-                const float bh = mh > 0.f ? bf - ebf : bf + ebf, bl = ml > 0.f ? bf + ebf : bf - ebf;
-                const float zhi = mh * rsqrtf(bh / Nf - mh * mh), zlo = ml * rsqrtf(bl / Nf - ml * ml);
-                const float tol = 1e-4f * (fabsf(zhi) + fabsf(zlo) + fabsf(z0f)) + 1e-30f;
-                if (zlo - tol > z0f) {
-                    ++pos;
-                    continue;
-                }
-                if (zhi + tol < z0f) {
-                    ++neg;
-                    continue;
-                }
-            }
-        }
-        const double a = static_cast<double>(s1) * sc1, b = static_cast<double>(s2) * sc2;
-        const double N = static_cast<double>(cnt);
-        bool undecided = false;
-        if (!inex1 && !inex2) {
-            const double z = zscore_from_sums(a, b, cnt);
-            neg += z <= z0;
-            pos += z >= z0;
-        } else {
-            const double ea = ra * N, eb = rb * N;
-            const double alo = a - ea, ahi = a + ea;
-            const double mmax = fmax(fabs(alo), fabs(ahi)) / N;
-            const double var_min = (b - eb) / N - mmax * mmax;
-            // well inside the domain only (no cancellation in EXX - EEX): else the exact engine decides
-            if (!(var_min > 0.0) || !((b + eb) / N + mmax * mmax < 1e6 * var_min)) {
-                undecided = true;
-            } else {
-                const double mh = ahi / N, ml = alo / N;
-                const double bh = ahi > 0.0 ? b - eb : b + eb;  // the z-score falls with the spread when the mean is > 0
-                const double bl = alo > 0.0 ? b + eb : b - eb;
-                double zhi = mh / sqrt(bh / N - mh * mh);
-                double zlo = ml / sqrt(bl / N - ml * ml);
-                zhi += 1e-12 * fabs(zhi) + 1e-300;
-                zlo -= 1e-12 * fabs(zlo) + 1e-300;
-                if (zlo > z0)
-                    ++pos;
-                else if (zhi < z0)
-                    ++neg;
-                else
-                    undecided = true;
-            }
-        }
-        if (undecided) {
-            const unsigned int k = atomicAdd(p.flag_count, 1u);
-            if (k < p.flag_cap) {
-                const int64_t node = p.node_of_row ? p.node_of_row[r] : r;
-                p.flag_ij[k] = (static_cast<uint64_t>(node) << 32) | static_cast<uint64_t>(j);
-                p.flag_p[k] = static_cast<uint32_t>(q);
-            }
-        }
-      }
+        for (int k = 0; k < 6; ++k) rec[(k >> 1) * 64 + (k & 1) * 16] = pl[k];
     }
-    if (p.count && (neg | pos)) p.zc[at] += neg | (pos << 16);  // this thread owns the cell in this launch
 }
+
+// per-attribute constants of the epilogue's fp32 filter: scales of the two fixed points and the error radii per
+// non-NaN neighbor (half a unit, rounded up; zero for exactly representable columns)
+__global__ void k_zcol(const int32_t* __restrict__ shift1, const int32_t* __restrict__ shift2,
+                       const uint8_t* __restrict__ inex1, const uint8_t* __restrict__ inex2, int64_t m,
+                       float4* __restrict__ zcol) {
+    const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    if (j >= m) return;
+    const double sc1 = ldexp(1.0, -shift1[j]), sc2 = ldexp(1.0, -shift2[j]);
+    const double ra = inex1[j] ? 0.5 * sc1 * (1.0 + 0x1p-12) : 0.0, rb = inex2[j] ? 0.5 * sc2 * (1.0 + 0x1p-12) : 0.0;
+    // (scales outside the fp32 range give 0 / inf: the filter then never accepts and fp64 decides)
+    zcol[j] = make_float4(static_cast<float>(sc1), static_cast<float>(sc2), static_cast<float>(ra) * 1.000001f,
+                          static_cast<float>(rb) * 1.000001f);
+}
+
 
 // observed z-scores into the plan's layout: z0t[j][r] = z0[node_of_row[r]][j]  (tiled transpose, one pass per null)
 __global__ void __launch_bounds__(256) k_z_layout(const double* __restrict__ z0, const int32_t* __restrict__ node_of_row,
@@ -1853,73 +1985,59 @@ __global__ void __launch_bounds__(256) k_z_layout(const double* __restrict__ z0,
     }
 }
 
-// packed counters of the plan's layout -> the caller's node-major arrays (added), counters cleared
-__global__ void __launch_bounds__(256) k_z_flush(uint32_t* __restrict__ zc, const int32_t* __restrict__ node_of_row,
-                                                 int64_t n, int64_t m, int64_t rows_pad, uint32_t* __restrict__ cneg,
-                                                 uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
-    __shared__ uint32_t tile[32][33];
-    const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 32, j0 = static_cast<int64_t>(blockIdx.y) * 32;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    for (int k = ty; k < 32; k += 8) {
-        const int64_t j = j0 + k, r = r0 + tx;
-        uint32_t v = 0;
-        if (j < m && r < n) {
-            v = zc[j * rows_pad + r];
-            zc[j * rows_pad + r] = 0;
-        }
-        tile[k][tx] = v;
-    }
-    __syncthreads();
-    for (int k = ty; k < 32; k += 8) {
-        const int64_t r = r0 + k, j = j0 + tx;
-        const uint32_t v = tile[tx][k];
-        if (r < n && j < m && v) {
-            const int64_t at = static_cast<int64_t>(node_of_row ? node_of_row[r] : r) * m + j;
-            if (packed) {
-                atomicAdd(&packed[at], v);  // (the exact fix-ups of this batch add to the same words)
-            } else {
-                atomicAdd(&cneg[at], v & 0xffffu);
-                atomicAdd(&cpos[at], v >> 16);
-            }
-        }
-    }
-}
-
 // Exact re-evaluation of the undecided z-score comparisons.  One warp per entry: the lanes fetch 32 neighbors' values
-// at a time (the dependent index -> permutation -> value loads are what a sequential walk spends its time on), then
-// every lane adds them IN ASCENDING NEIGHBOR ORDER -- the exact engine's accumulation order (score_one), so the
-// result has the exact engine's bits.
+// at a time (the dependent index -> permutation -> value loads are what a sequential walk spends its time on) and
+// convert them, value and square, into a warp-private shared-memory line; then they are added IN ASCENDING NEIGHBOR
+// ORDER -- the exact engine's accumulation order (score_one), so the result has the exact engine's bits -- at one
+// broadcast load and two additions per neighbor.  A NaN neighbor contributes +0.0 to both sums (x + 0.0 == x except
+// for the sign of a zero sum, which no comparison sees) and is left out of the count.
 template <class T>
 __global__ void __launch_bounds__(256) k_zfix(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col_idx,
-                                              const T* __restrict__ b, const int32_t* __restrict__ perm, int64_t n,
+                                              const T* __restrict__ bt, const int32_t* __restrict__ perm, int64_t n,
                                               int64_t m, const double* __restrict__ z0,
                                               const uint64_t* __restrict__ flag_ij, const uint32_t* __restrict__ flag_p,
                                               unsigned int total, uint32_t* __restrict__ cneg,
                                               uint32_t* __restrict__ cpos, uint32_t* __restrict__ packed) {
+    __shared__ double2 s_line[8][32];
     const int lane = threadIdx.x & 31;
+    double2* const line = s_line[threadIdx.x >> 5];
     unsigned int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned int step = (gridDim.x * blockDim.x) >> 5;
     for (; k < total; k += step) {
         const uint64_t ij = flag_ij[k];
         const int64_t i = static_cast<int64_t>(ij >> 32), j = static_cast<int64_t>(ij & 0xffffffffu);
         const int32_t* pr = perm + static_cast<int64_t>(flag_p[k]) * n;
+        const T* const col = bt + j * n;  // transposed copy: a flag's reads stay inside one column
         double sum = 0.0, sq = 0.0;
         int64_t cnt = 0;
         const int64_t e1 = row_ptr[i + 1];
         for (int64_t e0 = row_ptr[i]; e0 < e1; e0 += 32) {
-            T v = static_cast<T>(0);
+            double2 mine = make_double2(0.0, 0.0);
             bool have = false;
             if (e0 + lane < e1) {
-                v = b[static_cast<int64_t>(pr[col_idx[e0 + lane]]) * m + j];
-                have = v == v;
+                const T v = col[pr[col_idx[e0 + lane]]];
+                if (v == v) {
+                    have = true;
+                    mine = make_double2(static_cast<double>(v), sq_like_numpy<T>(v));
+                }
             }
-            const int chunk = static_cast<int>(min(static_cast<int64_t>(32), e1 - e0));
-            for (int t = 0; t < chunk; ++t) {
-                const T vt = __shfl_sync(0xffffffffu, v, t);
-                if (__shfl_sync(0xffffffffu, have ? 1 : 0, t)) {
-                    sum += static_cast<double>(vt);
-                    sq += sq_like_numpy<T>(vt);
-                    ++cnt;
+            cnt += __popc(__ballot_sync(0xffffffffu, have));
+            __syncwarp();
+            line[lane] = mine;
+            __syncwarp();
+            if (e1 - e0 >= 32) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                    const double2 x = line[t];
+                    sum += x.x;
+                    sq += x.y;
+                }
+            } else {
+                const int chunk = static_cast<int>(e1 - e0);
+                for (int t = 0; t < chunk; ++t) {
+                    const double2 x = line[t];
+                    sum += x.x;
+                    sq += x.y;
                 }
             }
         }
@@ -1937,154 +2055,202 @@ __global__ void __launch_bounds__(256) k_zfix(const int64_t* __restrict__ row_pt
     }
 }
 
+// the z plan: tiles of A as in the 'sum' plan, column groups of 32 attributes, z records, filter constants
+static TcPlan* build_plan_z(sb_enrich* e, const TcPlan* main) {
+    sb_ctx* ctx = e->ctx;
+    cudaStream_t st = ctx->stream;
+    TcPlan* pl = build_plan(e, /*zgroups=*/true);
+    try {
+        KernelTimer kt_prep(ctx, SB_K_PREP);
+        PhaseTrace tr(ctx, "tc.plan.z_records");
+        const int64_t n = e->n, m = e->m;
+        TcOperand& op = pl->op[XF_VALUE];  // the z records stand in for the operand of the generic batch code
+        op.built = true;
+        op.D = 3;
+        // squares: two digit planes; exactly representable columns (<= 14 magnitude bits) keep every bit
+        std::vector<int32_t> h_kmax, h_lmin;
+        const int32_t flags = column_ranges(e, XF_SQUARE, h_kmax, h_lmin);
+        if (flags & 1) {  // a square overflows to inf: exact SIMT engine
+            pl->usable = false;
+            return pl;
+        }
+        std::vector<int32_t> h_shift(m, 0);
+        std::vector<uint8_t> h_inexact(m, 0);
+        bool any2 = false;
+        for (int64_t j = 0; j < m; ++j) {
+            if (h_kmax[j] == INT_MIN) continue;
+            const int bits = h_kmax[j] - h_lmin[j] + 1;
+            if (bits <= 14) {
+                h_shift[j] = -h_lmin[j];
+            } else {
+                h_shift[j] = 13 - h_kmax[j];  // |q| < 2^14
+                h_inexact[j] = 1;
+                any2 = true;
+            }
+        }
+        pl->z_shift2.reserve(m);
+        pl->z_inex2.reserve(m);
+        SB_CUDA(cudaMemcpyAsync(pl->z_shift2.p, h_shift.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        SB_CUDA(cudaMemcpyAsync(pl->z_inex2.p, h_inexact.data(), m, cudaMemcpyHostToDevice, st));
+        // values: the 'sum' plan's fixed point (its shifts hold for three planes whatever D it chose: a column is
+        // inexact only when three planes are not enough)
+        pl->z_shift1 = main->op[XF_VALUE].shift.p;
+        pl->z_inex1 = main->op[XF_VALUE].inexact.p;
+        op.any_inexact = main->op[XF_VALUE].any_inexact || any2;
+        pl->z_col.reserve(m);
+        k_zcol<<<static_cast<unsigned>(sb_ceil_div(m, 256)), 256, 0, st>>>(pl->z_shift1, pl->z_shift2.p, pl->z_inex1,
+                                                                          pl->z_inex2.p, m, pl->z_col.p);
+        SB_LAUNCH_CHECK(ctx);
+        op.digits.reserve(static_cast<size_t>(pl->n_cg) * n * 192);
+        const unsigned qblocks = static_cast<unsigned>(
+            std::min<int64_t>(sb_ceil_div(static_cast<int64_t>(pl->n_cg) * n * 32, 256), ctx->num_sms * 32));
+        if (e->dtype == SB_F32)
+            k_quantize_z<float><<<qblocks, 256, 0, st>>>(static_cast<const float*>(e->b), n, m, pl->n_cg, pl->z_shift1,
+                                                         pl->z_shift2.p, op.digits.p);
+        else
+            k_quantize_z<double><<<qblocks, 256, 0, st>>>(static_cast<const double*>(e->b), n, m, pl->n_cg,
+                                                          pl->z_shift1, pl->z_shift2.p, op.digits.p);
+        SB_LAUNCH_CHECK(ctx);
+        // undecided comparisons: one list (no buckets), a quarter of a batch's worst case at most
+        if (op.any_inexact) {
+            const int64_t padded_cells = static_cast<int64_t>(pl->n_rb) * TC_PROWS * 32 * pl->n_cg;
+            int64_t cap = std::min<int64_t>(std::max<int64_t>(padded_cells / 4, 4ll << 20), 128ll << 20);
+            if (getenv("SB_FLAG_CAP")) cap = atoll(getenv("SB_FLAG_CAP"));  // tests: force the overflow recovery
+            pl->flag_cap = static_cast<unsigned int>(std::max<int64_t>(cap, static_cast<int64_t>(TC_PROWS) * 32 * pl->n_cg));
+        } else {
+            pl->flag_cap = 1;
+        }
+        SB_CUDA(cudaStreamSynchronize(st));  // host vectors above go out of scope
+    } catch (...) {
+        delete pl;
+        throw;
+    }
+    return pl;
+}
+
 bool tc_perm_counts_z(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uint32_t* cneg, uint32_t* cpos,
                       uint32_t* packed) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
     PhaseTrace tr_all(ctx, "tc.perm_counts_z(total)");
     if (!e->tc) e->tc = build_plan(e);
-    TcPlan* pl = e->tc;
     // +-inf / giant neighborhoods / fewer than 64 attributes: exact SIMT engine
-    if (!pl->usable || pl->mpad < 64 || e->m > 65535) return false;
-    build_operand(e, pl, XF_SQUARE);
-    build_operand(e, pl, XF_VALID);
-    const TcOperand* ops[3] = {&pl->op[XF_VALUE], &pl->op[XF_SQUARE], &pl->op[XF_VALID]};
-    if (!ops[1]->usable || !ops[2]->usable) return false;
+    if (!e->tc->usable || e->m < 64 || e->m > 65535) return false;
+    if (!e->tc->z) e->tc->z = build_plan_z(e, e->tc);
+    TcPlan* pl = e->tc->z;
+    if (!pl->usable) return false;
+    const TcOperand& op = pl->op[XF_VALUE];
     SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
     const double* z0 = enrich_observed(e, SB_SCORE_ZSCORE);
 
-    // batch: the three sum arrays of qb permutations (int64 [qb][rows_pad][mpad] each) take <= 6 GiB
+    // observed z-scores in the plan's layout: [32 n_cg][rows_pad], internal row order (one pass per null)
     const int64_t rows_pad = static_cast<int64_t>(pl->n_rb) * TC_PROWS;
-    const int64_t stride = rows_pad * pl->mpad;
-    int64_t qb = std::max<int64_t>(1, (6ll << 30) / (3 * stride * 8));
-    qb = std::min<int64_t>(std::min<int64_t>(qb, 64), num_perm);
-    DevBuf<int64_t> sums;
-    sums.reserve(static_cast<size_t>(3) * qb * stride);
-    size_t tile_max = 0;
-    for (int o = 0; o < 3; ++o) tile_max = std::max(tile_max, static_cast<size_t>(TC_KT) * 64 * ops[o]->D);
-    ctx->ws_bcat.reserve(static_cast<size_t>(qb) * pl->n_cg * pl->n_kt * tile_max);
-    const bool any_inexact = ops[0]->any_inexact || ops[1]->any_inexact;
-    const unsigned int cap = any_inexact ? std::max<unsigned int>(pl->flag_cap, 4u << 20) : 1u;
-    ctx->ws_flag_ij.reserve(cap);
-    ctx->ws_flag_p.reserve(cap);
-    DevBuf<unsigned int> fcount;
-    fcount.reserve(1);
-
-    // observed z-scores and decided-count accumulators in the plan's internal column-major layout
     DevBuf<double> z0t;
-    DevBuf<uint32_t> zc;
-    z0t.reserve(static_cast<size_t>(stride));
-    zc.reserve(static_cast<size_t>(stride));
-    SB_CUDA(cudaMemsetAsync(zc.p, 0, static_cast<size_t>(stride) * sizeof(uint32_t), st));
+    z0t.reserve(static_cast<size_t>(rows_pad) * e->m);
     {
         dim3 grid(static_cast<unsigned>(sb_ceil_div(rows_pad, 32)), static_cast<unsigned>(sb_ceil_div(e->m, 32)));
         SB_CHECK(grid.y <= 65535, "z-score tensor path: too many attributes");
         k_z_layout<<<grid, 256, 0, st>>>(z0, pl->order, e->n, e->m, rows_pad, z0t.p);
         SB_LAUNCH_CHECK(ctx);
     }
-    auto zflush = [&]() {
-        dim3 grid(static_cast<unsigned>(sb_ceil_div(e->n, 32)), static_cast<unsigned>(sb_ceil_div(e->m, 32)));
-        k_z_flush<<<grid, 256, 0, st>>>(zc.p, pl->order, e->n, e->m, rows_pad, cneg, cpos, packed);
-        SB_LAUNCH_CHECK(ctx);
-    };
-    int64_t zc_perms = 0;
 
-    ZParams zp{};
-    zp.z0t = z0t.p;
-    zp.zc = zc.p;
-    zp.shift1 = ops[0]->shift.p;
-    zp.shift2 = ops[1]->shift.p;
-    zp.inex1 = ops[0]->inexact.p;
-    zp.inex2 = ops[1]->inexact.p;
-    zp.node_of_row = pl->order;
-    zp.n = e->n;
-    zp.m = e->m;
-    zp.mpad = pl->mpad;
-    zp.rows_pad = rows_pad;
-    zp.stride = stride;
-    zp.flag_ij = ctx->ws_flag_ij.p;
-    zp.flag_p = ctx->ws_flag_p.p;
-    zp.flag_count = fcount.p;
-    zp.flag_cap = cap;
-    auto zcount = [&](int q0, int q1, int64_t r0, int64_t r1, bool count) {
-        ZParams a = zp;
-        a.q0 = q0;
-        a.q1 = q1;
-        a.r0 = static_cast<int32_t>(r0);
-        a.r1 = static_cast<int32_t>(r1);
-        a.count = count ? 1 : 0;
-        dim3 grid(static_cast<unsigned>(sb_ceil_div(r1 - r0, 256)), static_cast<unsigned>(e->m));
-        KernelTimer kt(ctx, SB_K_FIXUP);
-        k_zcount<<<grid, 256, 0, st>>>(a);
-        SB_LAUNCH_CHECK(ctx);
+    // batches as in tc_perm_counts: gathered tiles <= ~1/8 of the free memory seen at the first null (<= 16 GiB)
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 192;
+    const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
+    if (ctx->bcat_budget == 0) {
+        size_t free_b = 0, total_b = 0;
+        SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
+    }
+    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes * pl->n_cg), 16ull << 30),
+                                   ctx->ws_bcat.n);
+    int64_t pb = std::max<int64_t>(1, static_cast<int64_t>(budget / slot_bytes) / pl->n_cg);
+    pb = std::min<int64_t>(std::min<int64_t>(pb, 65535), std::min<int64_t>(16384, num_perm));
+    const int64_t n_batches = sb_ceil_div(num_perm, pb);
+    pb = sb_ceil_div(num_perm, n_batches);  // equal batches
+    ctx->ws_bcat.reserve(static_cast<size_t>(pb) * pl->n_cg * slot_bytes);
+    ctx->ws_flag_ij.reserve(pl->flag_cap);
+    ctx->ws_flag_p.reserve(pl->flag_cap);
+    pl->flag_count.reserve(1);
+    if (packed) {
+        pl->cpk = packed;
+    } else {
+        ctx->ws_cpk.reserve(static_cast<size_t>(e->n) * e->m);
+        SB_CUDA(cudaMemsetAsync(ctx->ws_cpk.p, 0, static_cast<size_t>(e->n) * e->m * sizeof(uint32_t), st));
+        pl->cpk = ctx->ws_cpk.p;
+    }
+    pl->cpk_perms = 0;
+
+    auto zgemm = [&](int mode, int q_first, int q_total, int rb0, int n_rb) {
+        pl->z_z0t = z0t.p;
+        run_batch_gemm(e, pl, op, mode | TCM_Z, q_first, q_total, q_total, rb0, n_rb);
     };
+    const void* bt = op.any_inexact ? enrich_transposed(e) : nullptr;  // [m][n]
     auto zfix = [&](const int32_t* perm, unsigned int count) {
         if (!count) return;
         const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(sb_ceil_div(count, 8), ctx->num_sms * 16));
-        KernelTimer kt(ctx, SB_K_SCORE);
+        KernelTimer kt(ctx, SB_K_FIXUP);
         if (e->dtype == SB_F32)
-            k_zfix<float><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(e->b), perm, e->n,
-                                                  e->m, z0, zp.flag_ij, zp.flag_p, count, cneg, cpos, packed);
+            k_zfix<float><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const float*>(bt), perm, e->n,
+                                                  e->m, z0, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, count, cneg, cpos,
+                                                  packed ? packed : pl->cpk);
         else
-            k_zfix<double><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(e->b), perm,
-                                                   e->n, e->m, z0, zp.flag_ij, zp.flag_p, count, cneg, cpos, packed);
+            k_zfix<double><<<blocks, 256, 0, st>>>(e->row_ptr.p, e->col_idx.p, static_cast<const double*>(bt), perm,
+                                                   e->n, e->m, z0, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, count, cneg,
+                                                   cpos, packed ? packed : pl->cpk);
         SB_LAUNCH_CHECK(ctx);
     };
 
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
-    for (int64_t p0 = 0; p0 < num_perm; p0 += qb) {
-        const int64_t np = std::min(qb, num_perm - p0);
+    const int64_t tiles_per_pass = static_cast<int64_t>(pl->n_tiles) * pl->n_cg;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        const int64_t p0 = b * pb, np = std::min(pb, num_perm - p0);
         const int32_t* perm = perm_dev + p0 * e->n;
-        for (int o = 0; o < 3; ++o) {
-            launch_gather(ctx, pl, *ops[o], perm, static_cast<int>(np * pl->n_cg), static_cast<int>(np), ctx->ws_bcat.p, st);
-            run_batch_gemm(e, pl, *ops[o], TCM_STORE, 0, static_cast<int>(np), static_cast<int>(np), 0, pl->n_rb,
-                           sums.p + static_cast<size_t>(o) * qb * stride);
-            ktile_iters += static_cast<int64_t>(pl->n_tiles) * pl->n_cg * np * ops[o]->D / 3;  // in 3-digit tile units
-        }
-        zp.s1 = sums.p;
-        zp.s2 = sums.p + static_cast<size_t>(qb) * stride;
-        zp.s3 = sums.p + static_cast<size_t>(2) * qb * stride;
-        SB_CUDA(cudaMemsetAsync(fcount.p, 0, sizeof(unsigned int), st));
-        if (zc_perms + np > 60000) {  // 16-bit fields about to overflow
-            zflush();
-            zc_perms = 0;
-        }
-        zc_perms += np;
-        zcount(0, static_cast<int>(np), 0, e->n, true);
+        launch_gather(ctx, pl, op, perm, static_cast<int>(np * pl->n_cg), static_cast<int>(np), ctx->ws_bcat.p, st);
+        if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);  // 16-bit fields about to overflow
+        pl->cpk_perms += np;
+        SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+        zgemm(TCM_COUNT | TCM_FLAG, 0, static_cast<int>(np), 0, pl->n_rb);
+        ktile_iters += tiles_per_pass * np;
         unsigned int h_count = 0;
-        if (any_inexact) {
-            SB_CUDA(cudaMemcpyAsync(&h_count, fcount.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
+        if (op.any_inexact) {
+            SB_CUDA(cudaMemcpyAsync(&h_count, pl->flag_count.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
             SB_CUDA(cudaStreamSynchronize(st));
         }
-        if (h_count <= cap) {
+        if (h_count <= pl->flag_cap) {
             zfix(perm, h_count);
             flagged += h_count;
-        } else {
-            // list overflow: the decided counts are in; re-emit the flags in (slot, row range) pieces that fit
-            ++overflow_batches;
-            const int64_t rows_step = std::max<int64_t>(1, static_cast<int64_t>(cap) / std::max<int64_t>(1, e->m));
-            for (int q = 0; q < np; ++q)
-                for (int64_t r0 = 0; r0 < e->n; r0 += rows_step) {
-                    SB_CUDA(cudaMemsetAsync(fcount.p, 0, sizeof(unsigned int), st));
-                    zcount(q, q + 1, r0, std::min<int64_t>(e->n, r0 + rows_step), false);
-                    SB_CUDA(cudaMemcpyAsync(&h_count, fcount.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
-                    SB_CUDA(cudaStreamSynchronize(st));
-                    SB_CHECK(h_count <= cap, "internal error: z-score flag list overflow in recovery");
-                    zfix(perm, h_count);  // flag_p holds the batch-local slot q
-                    flagged += h_count;
-                }
+            continue;
+        }
+        // list overflow: the decided counts are in; re-emit the flags slot by slot in row-block ranges whose worst
+        // case fits the list
+        ++overflow_batches;
+        const int rb_step = std::max<int>(1, static_cast<int>(pl->flag_cap / (static_cast<unsigned int>(TC_PROWS) * 32u * pl->n_cg)));
+        for (int q = 0; q < np; ++q) {
+            for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
+                SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, sizeof(unsigned int), st));
+                zgemm(TCM_FLAG, q, 1, rb0, std::min(rb_step, pl->n_rb - rb0));
+                SB_CUDA(cudaMemcpyAsync(&h_count, pl->flag_count.p, sizeof h_count, cudaMemcpyDeviceToHost, st));
+                SB_CUDA(cudaStreamSynchronize(st));
+                SB_CHECK(h_count <= pl->flag_cap, "internal error: z-score flag list overflow in recovery");
+                zfix(perm + static_cast<int64_t>(q) * e->n, h_count);  // flag_p holds slot 0 of this launch
+                flagged += h_count;
+            }
+            ktile_iters += tiles_per_pass;
         }
     }
-    zflush();
+    if (!packed) flush_counts(e, pl, cneg, cpos);
+    pl->cpk = nullptr;
     e->stats[0] = e->n * e->m * num_perm - flagged;
     e->stats[1] = flagged;
     e->stats[2] = pl->n_tiles_real;
     e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
-    e->stats[4] = ops[0]->D;
+    e->stats[4] = 3;
     e->stats[5] = ktile_iters;
     e->stats[6] = overflow_batches;
     return true;
 }
+
 
 }  // namespace sb
 

@@ -24,6 +24,8 @@ def _attrs(n, m, kind, seed):
         b = rng.integers(-5, 6, size=(n, m)).astype(np.float32)
         b[rng.uniform(size=n) < 0.05] = np.nan
         return b
+    if kind.endswith("_full"):  # no NaN anywhere
+        return np.nan_to_num(_attrs(n, m, kind[:-5], seed), nan=0.25)
     if kind == "mixed":       # exact and inexact columns side by side in one column group
         b = syn.make_attributes(n, m, seed, "normal32")
         b[:, ::3] = syn.make_attributes(n, m, seed + 1, "binary")[:, ::3]
@@ -32,8 +34,9 @@ def _attrs(n, m, kind, seed):
     return syn.make_attributes(n, m, seed, kind)
 
 
-@pytest.mark.parametrize("kind", ["normal32", "binary", "dyadic", "integer", "normal64", "mixed"])
-@pytest.mark.parametrize("m", [64, 70])
+@pytest.mark.parametrize("kind", ["normal32", "binary", "dyadic", "integer", "normal64", "mixed", "normal32_full",
+                                  "integer_full"])
+@pytest.mark.parametrize("m", [64, 70, 130])
 def test_zscore_tensor_core_equals_exact_engine(ctx, stage1_mid, kind, m):
     g = stage1_mid
     n = g["x"].shape[0]
@@ -46,7 +49,7 @@ def test_zscore_tensor_core_equals_exact_engine(ctx, stage1_mid, kind, m):
     sneg, spos = plan.perm_counts(rows, "z-score", "simt")
     assert np.array_equal(tneg, sneg) and np.array_equal(tpos, spos), (kind, m)
     assert st["decided"] + st["fixups"] == n * m * rows.shape[0]
-    if kind in ("binary", "integer"):
+    if kind in ("binary", "integer", "integer_full"):
         assert st["fixups"] == 0            # exactly representable values and squares: no error band, no fix-ups
     else:
         assert st["fixups"] < 0.01 * n * m * rows.shape[0]

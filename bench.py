@@ -825,7 +825,7 @@ def run_ours(args):
             out["roofline"]["tensor_ceiling_same_box"] = ceil
         except Exception as exc:  # noqa: BLE001
             out["roofline"]["tensor_ceiling_same_box"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
-    # ---- neighborhood_score_type='z-score' on the same inputs (three digit contractions + fp64 comparison kernel per
+    # ---- neighborhood_score_type='z-score' on the same inputs (value / square / non-NaN planes in one accumulation per
     # permutation): a short resident pass of this rank's first permutations, reported beside the 'sum' null
     zscore = None
     try:
@@ -847,8 +847,8 @@ def run_ours(args):
             zms = e0.elapsed_time(e1)
             zscore = {"permutations": zp, "ms_per_permutation": zms / zp, "scores_per_s": float(n) * m * zp / (zms / 1e3),
                       "fixup_fraction": zst["fixups"] / max(1, zst["fixups"] + zst["decided"]),
-                      "note": "resident z-score null of this rank's first %d permutations (digit GEMM in its store "
-                              "flavour for value / square / valid sums + k_zcount + exact fix-ups)" % zp}
+                      "note": "resident z-score null of this rank's first %d permutations (digit GEMM on value / "
+                              "square / non-NaN planes, comparison in the epilogue + exact fix-ups)" % zp}
     except Exception as exc:  # noqa: BLE001
         zscore = {"error": "%s: %s" % (type(exc).__name__, exc)}
     if rank == 0:

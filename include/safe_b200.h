@@ -45,7 +45,7 @@ extern "C" {
 #define SB_SCORE_ZSCORE 1
 
 /* engine selection for the permutation null */
-#define SB_ENGINE_AUTO 0   /* tcgen05 int8 digit GEMM + exact fix-up for 'sum'; SIMT fp64 for 'z-score' */
+#define SB_ENGINE_AUTO 0   /* tcgen05 int8 digit GEMM + exact fix-up ('z-score' with fewer than 64 attributes: SIMT fp64) */
 #define SB_ENGINE_SIMT 1   /* fp64 CUDA-core sparse kernel (exact by construction; validation / z-score) */
 #define SB_ENGINE_TC 2     /* force the tensor-core path (z-score: needs 64+ attributes and finite values) */
 

@@ -65,13 +65,11 @@ struct GemmParams {
     int32_t n_kt, n_rb, n_cg, q_total, q_chunks, q_per;  // n_rb: blocks of TC_PROWS rows
     int32_t band_rb, n_bands; // unit order: band of row blocks, then q chunk, then column group, then row block
     int32_t rb0;              // first row block of this launch (units cover row blocks [rb0, rb0 + n_rb))
-    int32_t n_rb_total;       // row blocks of the whole matrix (column stride of a batch STORE)
     unsigned int* unit_counter;  // dynamic scheduler (zeroed before the launch)
     int32_t mode;
     int64_t n, m, mpad;
     int32_t log2_mpad, pps, batch_perms;
-    int64_t* s0fix;           // [n_rb * 256][mpad]; TCK_STORE: output, slot q at s0fix + q * store_stride
-    int64_t store_stride;     // TCK_STORE over a batch: elements between the outputs of consecutive slots (0: one slot)
+    int64_t* s0fix;           // [n_rb * 256][mpad] observed fixed-point scores (TCK_STORE: output)
     const int64_t* row_ptr;   // band_i = row_ptr[i+1] - row_ptr[i]
     const int32_t* node_of_row;  // internal row -> caller's node id (nullptr: identity)
     const uint8_t* inexact;   // [mpad]
@@ -714,21 +712,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                         }
                     }
                     if (KIND == TCK_STORE && !SMALL_M) {
-                        // one slot (observed scores): row-major [n_rb * 256][mpad], what the COUNT flavour preloads.
-                        // A batch (store_stride != 0): slot q at q * store_stride, COLUMN-major [mpad][n_rb * 256] -- the
-                        // 32 rows of a warp are 256 contiguous bytes per column (row-major 16-byte stores per thread
-                        // cost the z-score null 7 ms per 48 C3 permutations more).
-                        const int64_t rows_pad = static_cast<int64_t>(p.n_rb_total) * TC_PROWS;
+                        // observed scores: row-major [n_rb * 256][mpad], what the COUNT flavour preloads
 #pragma unroll
                         for (int x = 0; x < CW; ++x) {
                             long long S = static_cast<int32_t>(acc[0][x]);
                             if (D > 1) S += static_cast<long long>(static_cast<int32_t>(acc[1][x])) << 8;
                             if (D > 2) S += static_cast<long long>(static_cast<int32_t>(acc[D - 1][x])) << 16;
                             const int64_t col = jbase + c0 + ch * CW + x;
-                            if (p.store_stride)
-                                p.s0fix[q * p.store_stride + col * rows_pad + row] = S;
-                            else
-                                p.s0fix[row * p.mpad + col] = S;
+                            p.s0fix[row * p.mpad + col] = S;
                         }
                     }
                     if (KIND == TCK_COUNT) {
@@ -1003,13 +994,12 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__
 
 // The matrices the digit GEMM multiplies the neighborhoods with are functions of the attribute matrix, evaluated on
 // the fly: XF_VALUE nan0(B) (the 'sum' score); and for the z-score (safe_extras.py:19-31) XF_SQUARE nan0(B^2) with
-// the square rounded like np.power(B, 2) rounds it, and XF_VALID the 0/1 matrix of the non-NaN entries.
-enum : int { XF_VALUE = 0, XF_SQUARE = 1, XF_VALID = 2 };
+// the square rounded like np.power(B, 2) rounds it (plus the 0/1 matrix of the non-NaN entries, see k_quantize_z).
+enum : int { XF_VALUE = 0, XF_SQUARE = 1 };
 template <int XF, class T>
 __device__ __forceinline__ double xf_value(T v) {  // NaN = "contributes nothing"
     if (XF == XF_VALUE) return static_cast<double>(v);
-    if (XF == XF_SQUARE) return v == v ? sq_like_numpy<T>(v) : static_cast<double>(v);
-    return v == v ? 1.0 : 0.0;
+    return v == v ? sq_like_numpy<T>(v) : static_cast<double>(v);
 }
 
 // per-column exponent range of the operand: kmax = exponent of the largest magnitude, lmin = exponent of the lowest
@@ -1023,12 +1013,10 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
     int hi = INT_MIN, lo = INT_MAX, bad = 0;
     for (int64_t r = r0; r < r1; ++r) {
-        const T raw = b[r * m + j];
-        if (raw != raw) bad |= 2;  // a NaN entry: the number of valid neighbors then depends on the permutation
-        const double v = xf_value<XF, T>(raw);
+        const double v = xf_value<XF, T>(b[r * m + j]);
         if (v != v || v == 0.0) continue;
         if (isinf(v)) {
-            bad |= 1;
+            bad = 1;
             continue;
         }
         int e;
@@ -1041,7 +1029,7 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
         atomicMax(&kmax[j], hi);
         atomicMin(&lmin[j], lo);
     }
-    if (bad) atomicOr(flags, bad);
+    if (bad) atomicOr(flags, 1);
 }
 
 // fixed-point digits: q = rint(v * 2^shift[j]); stored are the D balanced base-256 int8 digits of -q (the expanded
@@ -1189,7 +1177,6 @@ struct TcOperand {
     bool built = false;
     bool usable = true;        // false: +-inf among the values
     bool any_inexact = false;  // some column is not exactly representable (its comparisons carry an error band)
-    bool has_nan = false;      // some entry of the attribute matrix is NaN
     DevBuf<int8_t> digits;
     DevBuf<int32_t> shift;     // per-column binary exponent of the fixed point: q = rint(v * 2^shift[j])
     DevBuf<uint8_t> inexact;   // [mpad]
@@ -1197,7 +1184,7 @@ struct TcOperand {
 };
 
 struct TcPlan {
-    TcOperand op[3];           // indexed by XF_VALUE / XF_SQUARE / XF_VALID; [0] serves the 'sum' null
+    TcOperand op;              // the 'sum' operand; in the z plan: the z records
     int64_t n = 0, m = 0, mpad = 0;
     int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
     int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
@@ -1340,7 +1327,6 @@ static GemmParams base_params(sb_enrich* e, TcPlan* pl, const TcOperand& op) {
     gp.bcat = ctx->ws_bcat.p;
     gp.n_kt = pl->n_kt;
     gp.n_rb = pl->n_rb;
-    gp.n_rb_total = pl->n_rb;
     gp.n_cg = pl->n_cg;
     gp.n = pl->n;
     gp.m = pl->m;
@@ -1378,7 +1364,7 @@ static int64_t slots_for(const TcPlan* pl, int64_t perms) {
     return pl->mpad >= 64 ? perms * pl->n_cg : sb_ceil_div(perms, pl->pps);
 }
 
-// Per-column exponent ranges of one operand (XF_*) on the host; returns k_col_range's flags (1: +-inf, 2: NaN seen)
+// Per-column exponent ranges of one operand (XF_*) on the host; returns k_col_range's flags (1: some value is +-inf)
 static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax, std::vector<int32_t>& h_lmin) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
@@ -1400,10 +1386,8 @@ static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax,
     do {                         \
         if (xf == XF_VALUE)      \
             SB_R(T, XF_VALUE);   \
-        else if (xf == XF_SQUARE) \
-            SB_R(T, XF_SQUARE);  \
         else                     \
-            SB_R(T, XF_VALID);   \
+            SB_R(T, XF_SQUARE);  \
     } while (0)
     if (e->dtype == SB_F32)
         SB_RX(float);
@@ -1420,18 +1404,18 @@ static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax,
     return h_flags;
 }
 
-// Digit planes of one operand (XF_*) and its observed fixed-point scores
-static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
+// Digit planes of the 'sum' operand and its observed fixed-point scores
+static void build_operand(sb_enrich* e, TcPlan* pl) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
-    TcOperand& op = pl->op[xf];
+    const int xf = XF_VALUE;
+    TcOperand& op = pl->op;
     if (op.built) return;
     const int64_t n = e->n, m = e->m;
     PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.digits");
     std::vector<int32_t> h_kmax, h_lmin;
     const int32_t h_flags = column_ranges(e, xf, h_kmax, h_lmin);
     op.built = true;
-    op.has_nan = (h_flags & 2) != 0;
     if (h_flags & 1) {
         op.usable = false;
         delete tr;
@@ -1484,20 +1468,10 @@ static void build_operand(sb_enrich* e, TcPlan* pl, int xf) {
         else                 \
             SB_Q(T, 3, X);   \
     } while (0)
-#define SB_QX(T)                  \
-    do {                          \
-        if (xf == XF_VALUE)       \
-            SB_QD(T, XF_VALUE);   \
-        else if (xf == XF_SQUARE) \
-            SB_QD(T, XF_SQUARE);  \
-        else                      \
-            SB_QD(T, XF_VALID);   \
-    } while (0)
     if (e->dtype == SB_F32)
-        SB_QX(float);
+        SB_QD(float, XF_VALUE);
     else
-        SB_QX(double);
-#undef SB_QX
+        SB_QD(double, XF_VALUE);
 #undef SB_QD
 #undef SB_Q
     SB_LAUNCH_CHECK(ctx);
@@ -1639,9 +1613,9 @@ static TcPlan* build_plan(sb_enrich* e, bool zgroups = false) {
         pl->flag_cap = static_cast<unsigned int>(min_cap);
         pl->flag_count.reserve(pl->n_cg);
         if (zgroups) return pl;  // build_plan_z fills in the records
-        build_operand(e, pl, XF_VALUE);
-        pl->usable = pl->op[XF_VALUE].usable;
-        if (pl->op[XF_VALUE].any_inexact) {  // exactly representable data never flags: nothing to reserve
+        build_operand(e, pl);
+        pl->usable = pl->op.usable;
+        if (pl->op.any_inexact) {  // exactly representable data never flags: nothing to reserve
             const int64_t padded_cells = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
             int64_t cap = std::min<int64_t>(std::max<int64_t>(padded_cells / 4, 4ll << 20), 128ll << 20);
             if (getenv("SB_FLAG_CAP")) cap = atoll(getenv("SB_FLAG_CAP"));  // tests: force the overflow recovery
@@ -1657,7 +1631,7 @@ static TcPlan* build_plan(sb_enrich* e, bool zgroups = false) {
 
 // one GEMM launch over slots [q_first, q_first + q_total) of the prepared batch and row blocks [rb0, rb0 + n_rb)
 static void run_batch_gemm(sb_enrich* e, TcPlan* pl, const TcOperand& op, int mode, int q_first, int q_total,
-                           int batch_perms, int rb0, int n_rb, int64_t* store_to = nullptr) {
+                           int batch_perms, int rb0, int n_rb) {
     sb_ctx* ctx = e->ctx;
     GemmParams gp = base_params(e, pl, op);
     gp.mode = mode;
@@ -1665,10 +1639,6 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, const TcOperand& op, int mo
     gp.batch_perms = batch_perms;
     gp.rb0 = rb0;
     gp.n_rb = n_rb;
-    if (store_to) {  // TCM_STORE over a batch: slot q -> store_to + q * (padded rows x mpad)
-        gp.s0fix = store_to;
-        gp.store_stride = static_cast<int64_t>(pl->n_rb) * TC_PROWS * pl->mpad;
-    }
     const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * op.D;
     // slot offset into the gathered operand of the batch
     gp.bcat += static_cast<size_t>(q_first) * pl->n_cg * pl->n_kt * tile_b;
@@ -1726,9 +1696,9 @@ bool tc_observed_exact(sb_enrich* e, const int64_t** s0fix, const int32_t** shif
                        int64_t* mpad) {
     if (!e->tc) e->tc = build_plan(e);
     TcPlan* pl = e->tc;
-    if (!pl->usable || pl->op[XF_VALUE].any_inexact) return false;
-    *s0fix = pl->op[XF_VALUE].s0fix.p;
-    *shift = pl->op[XF_VALUE].shift.p;
+    if (!pl->usable || pl->op.any_inexact) return false;
+    *s0fix = pl->op.s0fix.p;
+    *shift = pl->op.shift.p;
     *row_of_node = e->have_order ? e->order_inv.p : nullptr;
     *mpad = pl->mpad;
     return true;
@@ -1757,7 +1727,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     // k_gemm CTA -- but the step does not get shorter (C3: 290 / 289 / 292 ms for none / fix-ups / both overlapped):
     // the GEMM slows down by what the side work takes, because the chip runs at its 1 kW power cap (SM clock 1.6-1.7
     // of 1.965 GHz, sw_power_cap active) and a step costs the same energy either way.
-    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->op[XF_VALUE].D;
+    const size_t tile_b = static_cast<size_t>(TC_KT) * 64 * pl->op.D;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
     if (ctx->bcat_budget == 0) {
         size_t free_b = 0, total_b = 0;
@@ -1788,7 +1758,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         pl->cpk = ctx->ws_cpk.p;
     }
     pl->cpk_perms = 0;
-    if (pl->op[XF_VALUE].any_inexact) enrich_transposed(e);
+    if (pl->op.any_inexact) enrich_transposed(e);
 
     delete tr_ws;
     int64_t flagged = 0, overflow_batches = 0, ktile_iters = 0;
@@ -1806,7 +1776,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         int64_t np;
         int slots, q_total;
         batch_of(b, perm, np, slots, q_total);
-        launch_gather(ctx, pl, pl->op[XF_VALUE], perm, slots, static_cast<int>(np), ctx->ws_bcat.p, on);
+        launch_gather(ctx, pl, pl->op, perm, slots, static_cast<int>(np), ctx->ws_bcat.p, on);
     };
     for (int64_t b = 0; b < n_batches; ++b) {
         const int32_t* perm;
@@ -1821,9 +1791,9 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
         if (!packed && pl->cpk_perms + np > 60000) flush_counts(e, pl, cneg, cpos);  // 16-bit fields about to overflow
         pl->cpk_perms += np;
         SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-        run_batch_gemm(e, pl, pl->op[XF_VALUE], TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
+        run_batch_gemm(e, pl, pl->op, TCM_COUNT | TCM_FLAG, 0, q_total, static_cast<int>(np), 0, pl->n_rb);
         ktile_iters += tiles_per_pass * q_total;
-        if (pl->op[XF_VALUE].any_inexact) {
+        if (pl->op.any_inexact) {
             SB_CUDA(cudaMemcpyAsync(count_log.p + b * pl->n_cg, pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
                                     cudaMemcpyDeviceToDevice, st));
             fixup_flag_buckets(e, st, perm, ctx->ws_flag_ij.p, ctx->ws_flag_p.p, pl->flag_count.p, pl->n_cg, cap_cg,
@@ -1833,7 +1803,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
 
     // ---- bucket counters of all batches: statistics, and the (rare) overflowed buckets, which the fix-up kernel skipped
     std::vector<unsigned int> h_log(static_cast<size_t>(n_batches) * pl->n_cg, 0u);
-    if (pl->op[XF_VALUE].any_inexact) {
+    if (pl->op.any_inexact) {
         SB_CUDA(cudaMemcpyAsync(h_log.data(), count_log.p, h_log.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         SB_CUDA(cudaStreamSynchronize(st));
     }
@@ -1869,7 +1839,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
             for (int rb0 = 0; rb0 < pl->n_rb; rb0 += rb_step) {
                 const int nrb = std::min(rb_step, pl->n_rb - rb0);
                 SB_CUDA(cudaMemsetAsync(pl->flag_count.p, 0, pl->n_cg * sizeof(unsigned int), st));
-                run_batch_gemm(e, pl, pl->op[XF_VALUE], TCM_FLAG, q, 1, bp, rb0, nrb);
+                run_batch_gemm(e, pl, pl->op, TCM_FLAG, q, 1, bp, rb0, nrb);
                 SB_CUDA(cudaMemcpyAsync(h_flags.data(), pl->flag_count.p, pl->n_cg * sizeof(unsigned int),
                                         cudaMemcpyDeviceToHost, st));
                 SB_CUDA(cudaStreamSynchronize(st));
@@ -1890,7 +1860,7 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     e->stats[1] = flagged;
     e->stats[2] = pl->n_tiles_real;
     e->stats[3] = static_cast<int64_t>(pl->n_rb) * pl->n_kt;
-    e->stats[4] = pl->op[XF_VALUE].D;
+    e->stats[4] = pl->op.D;
     e->stats[5] = ktile_iters;
     e->stats[6] = overflow_batches;
 }
@@ -2064,7 +2034,7 @@ static TcPlan* build_plan_z(sb_enrich* e, const TcPlan* main) {
         KernelTimer kt_prep(ctx, SB_K_PREP);
         PhaseTrace tr(ctx, "tc.plan.z_records");
         const int64_t n = e->n, m = e->m;
-        TcOperand& op = pl->op[XF_VALUE];  // the z records stand in for the operand of the generic batch code
+        TcOperand& op = pl->op;  // the z records stand in for the operand of the generic batch code
         op.built = true;
         op.D = 3;
         // squares: two digit planes; exactly representable columns (<= 14 magnitude bits) keep every bit
@@ -2094,9 +2064,9 @@ static TcPlan* build_plan_z(sb_enrich* e, const TcPlan* main) {
         SB_CUDA(cudaMemcpyAsync(pl->z_inex2.p, h_inexact.data(), m, cudaMemcpyHostToDevice, st));
         // values: the 'sum' plan's fixed point (its shifts hold for three planes whatever D it chose: a column is
         // inexact only when three planes are not enough)
-        pl->z_shift1 = main->op[XF_VALUE].shift.p;
-        pl->z_inex1 = main->op[XF_VALUE].inexact.p;
-        op.any_inexact = main->op[XF_VALUE].any_inexact || any2;
+        pl->z_shift1 = main->op.shift.p;
+        pl->z_inex1 = main->op.inexact.p;
+        op.any_inexact = main->op.any_inexact || any2;
         pl->z_col.reserve(m);
         k_zcol<<<static_cast<unsigned>(sb_ceil_div(m, 256)), 256, 0, st>>>(pl->z_shift1, pl->z_shift2.p, pl->z_inex1,
                                                                           pl->z_inex2.p, m, pl->z_col.p);
@@ -2139,7 +2109,7 @@ bool tc_perm_counts_z(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, u
     if (!e->tc->z) e->tc->z = build_plan_z(e, e->tc);
     TcPlan* pl = e->tc->z;
     if (!pl->usable) return false;
-    const TcOperand& op = pl->op[XF_VALUE];
+    const TcOperand& op = pl->op;
     SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
     const double* z0 = enrich_observed(e, SB_SCORE_ZSCORE);
 

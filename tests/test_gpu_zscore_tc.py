@@ -1,5 +1,5 @@
-"""GPU: the z-score permutation null on the tensor cores (three digit contractions per permutation + fp64 comparison
-kernel + exact fix-ups) against the exact SIMT engine, which is pinned against the reference's recorded z-score counts
+"""GPU: the z-score permutation null on the tensor cores (value / square / non-NaN digit planes in one accumulation,
+comparison in the epilogue + exact fix-ups) against the exact SIMT engine, which is pinned against the reference's recorded z-score counts
 in tests/test_gpu_stage2.py::test_zscore_counts.  The two engines must agree cell for cell: decided comparisons are
 rigorous with respect to the exact engine's value, undecided ones are re-evaluated by the exact engine's own code."""
 import numpy as np

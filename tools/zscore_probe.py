@@ -1,5 +1,5 @@
 """Device time of the z-score permutation null (neighborhood_score_type='z-score') on a named configuration:
-tensor-core path (three digit contractions + fp64 comparison kernel) vs the 'sum' null on the same inputs.
+tensor-core path (six digit planes per accumulation, comparison in the epilogue) vs the 'sum' null on the same inputs.
     python tools/zscore_probe.py [--config C3] [--perms 48]"""
 import json
 import os

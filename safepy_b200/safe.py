@@ -135,6 +135,10 @@ class SafeB200Mixin:
     # re-reads the edge data on every call, and in-place edits of 'length' cannot be detected from outside.
     assume_graph_unchanged = False
     results_rank = None  # with several ranks: None = every rank receives the [N, M] result arrays, r = only rank r
+    # Which [N, M] fp64 results of the randomization test come back to the host (the others are set to None).  All
+    # five by default, as upstream; at N = 100 000 x M = 5000 they are 4 GB each and their way into pageable memory
+    # is the largest part of the call, so a caller who needs, say, only the NES can ask for ("nes", "nes_binary").
+    host_outputs = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
     _plan = None  # enrichment plan of the compute_pvalues call in progress
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
@@ -333,7 +337,11 @@ class SafeB200Mixin:
             t2 = time.perf_counter()
             if self.multiple_testing:
                 logging.info("Running FDR-adjustment of p-values...")
-            want = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
+            known = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
+            unknown = [k for k in self.host_outputs if k not in known]
+            if unknown:
+                raise ValueError("host_outputs: unknown result %r (choose from %s)" % (unknown[0], ", ".join(known)))
+            want = tuple(k for k in known if k in self.host_outputs)
             if dist and self.results_rank is not None and dist.get_rank() != self.results_rank:
                 # this rank keeps only the per-attribute sums, which the results rank sends: no tail here at all
                 import torch

@@ -92,6 +92,23 @@ def test_attribute_sign_and_processes_rounding(stage2_small):
     assert np.array_equal(sf.nes, -np.log10(np.where(sf.pvalues_pos == 0, 1 / 28, sf.pvalues_pos)), equal_nan=True)
 
 
+def test_host_outputs_limits_what_comes_back(stage2_small):
+    """sf.host_outputs: only the named [N, M] results are copied to the host, the others are None; the per-attribute
+    sums (computed on the device in the same pass) are unaffected."""
+    g = stage2_small
+    sf, net = make_sf(g, random_seed=int(g["seed"]))
+    sf.define_neighborhoods(neighborhood_radius=float(g["radius"]))
+    sf.load_attributes(attribute_file=g["attr_normal32"].copy())
+    sf.host_outputs = ("nes",)
+    sf.compute_pvalues(how="randomization", num_permutations=int(g["num_permutations"]), verbose=False)
+    assert np.array_equal(sf.nes, g["rand_nes_normal32"], equal_nan=True)
+    assert sf.ns is None and sf.pvalues_neg is None and sf.pvalues_pos is None and sf.nes_binary is None
+    assert np.array_equal(sf.attributes["num_neighborhoods_enriched"].values, g["rand_enriched_normal32"])
+    sf.host_outputs = ("nes", "bogus")
+    with pytest.raises(ValueError):
+        sf.compute_pvalues(how="randomization", num_permutations=5, verbose=False)
+
+
 def test_free_function_drop_ins(stage2_small):
     g = stage2_small
     n = g["x"].shape[0]

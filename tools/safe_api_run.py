@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--perms", type=int, default=1000)
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--repeats", type=int, default=2)
+    ap.add_argument("--outputs", default=None,
+                    help="comma-separated sf.host_outputs (default: all five result arrays, as upstream); several sets "
+                         "separated by ';' are timed one after the other")
     ap.add_argument("--how", default="randomization", help="compute_pvalues(how=...): randomization | auto | hypergeometric")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -49,35 +52,39 @@ def main():
     sf.results_rank = 0
     sf.assume_graph_unchanged = True     # the graph object is not touched between load_network and the timed calls
     sf.load_attributes(attribute_file=attrs)
-    runs = []
-    for _ in range(args.repeats):
+    # one JSON line per set of host outputs (sets separated by ';'), all in this process
+    for outputs in (args.outputs.split(";") if args.outputs else [None]):
+        if outputs:
+            sf.host_outputs = tuple(outputs.split(","))
+        runs = []
+        for _ in range(args.repeats):
+            if dist:
+                dist.barrier()
+            t0 = time.perf_counter()
+            sf.define_neighborhoods()
+            t1 = time.perf_counter()
+            sf.compute_pvalues(how=args.how, num_permutations=args.perms)
+            t2 = time.perf_counter()
+            runs.append(dict(define_neighborhoods_s=t1 - t0, compute_pvalues_s=t2 - t1,
+                             phases=getattr(sf, "last_enrichment_seconds", None)))
         if dist:
-            dist.barrier()
-        t0 = time.perf_counter()
-        sf.define_neighborhoods()
-        t1 = time.perf_counter()
-        sf.compute_pvalues(how=args.how, num_permutations=args.perms)
-        t2 = time.perf_counter()
-        runs.append(dict(define_neighborhoods_s=t1 - t0, compute_pvalues_s=t2 - t1,
-                         phases=getattr(sf, "last_enrichment_seconds", None)))
-    if dist:
-        import torch
-        worst = torch.tensor([runs[-1]["define_neighborhoods_s"], runs[-1]["compute_pvalues_s"]], device="cuda")
-        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
-        worst = [float(v) for v in worst.cpu()]
-    else:
-        worst = [runs[-1]["define_neighborhoods_s"], runs[-1]["compute_pvalues_s"]]
-    if rank == 0:
-        n, m = attrs.shape
-        print(json.dumps({
-            "metric": "define_neighborhoods+compute_pvalues sec", "config": args.config, "n": n, "m": m,
-            "perms": args.perms, "how": args.how, "n_gpus": world, "node_distance_metric": cfg["metric"],
-            "define_neighborhoods_s": worst[0], "compute_pvalues_s": worst[1], "total_s": worst[0] + worst[1],
-            "timing": "host wall clock of the last of %d calls, max over ranks" % args.repeats,
-            "rank0_runs": runs, "load_network_s": t_load,
-            "mean_neighborhood": float(np.mean(np.sum(sf.neighborhoods, axis=1))),
-            "enriched_cells": float(np.nansum(sf.nes_binary)) if sf.nes_binary is not None else None,
-            "gemm_stats_rank0": getattr(sf, "last_enrichment_stats", None)}))
+            import torch
+            worst = torch.tensor([runs[-1]["define_neighborhoods_s"], runs[-1]["compute_pvalues_s"]], device="cuda")
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+            worst = [float(v) for v in worst.cpu()]
+        else:
+            worst = [runs[-1]["define_neighborhoods_s"], runs[-1]["compute_pvalues_s"]]
+        if rank == 0:
+            n, m = attrs.shape
+            print(json.dumps({
+                "metric": "define_neighborhoods+compute_pvalues sec", "config": args.config, "n": n, "m": m,
+                "perms": args.perms, "how": args.how, "n_gpus": world, "host_outputs": list(sf.host_outputs), "node_distance_metric": cfg["metric"],
+                "define_neighborhoods_s": worst[0], "compute_pvalues_s": worst[1], "total_s": worst[0] + worst[1],
+                "timing": "host wall clock of the last of %d calls, max over ranks" % args.repeats,
+                "rank0_runs": runs, "load_network_s": t_load,
+                "mean_neighborhood": float(np.mean(np.sum(sf.neighborhoods, axis=1))),
+                "enriched_cells": float(np.nansum(sf.nes_binary)) if sf.nes_binary is not None else None,
+                "gemm_stats_rank0": getattr(sf, "last_enrichment_stats", None)}))
     if dist:
         dist.barrier()
         dist.destroy_process_group()

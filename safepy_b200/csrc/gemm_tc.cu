@@ -12,10 +12,9 @@
 // Data movement.  The kernel runs on CTA PAIRS (cluster of two SMs, tcgen05 cta_group::2, M = 256): a pair owns a
 // block of 256 rows of A (128 per CTA) and multiplies it with a gathered-operand tile whose 64*D columns are split
 // between the two CTAs' shared memories, so every byte of the gathered operand that leaves L2 feeds 256 rows.
-// A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row.  The masks ride along with the
-// gathered tiles through the smem ring, expander warps turn them into int8 0 / -1 in TMEM with byte permutes
-// (no table, no shared-memory traffic), and the MMA takes its A operand from TMEM; the digits are stored negated,
-// so the products come out with the right sign.  Gathered tiles are stored in HBM in the tensor core's canonical
+// A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row (stored as two words, split_mask).
+// The masks ride along with the gathered tiles through the smem ring, expander warps turn them into int8 0 / 1 in
+// TMEM with byte permutes (no table), and the MMA takes its A operand from TMEM.  Gathered tiles are stored in HBM in the tensor core's canonical
 // no-swizzle MN-major core-matrix order, one half per CTA, so one 1-D bulk async copy (TMA engine, UBLKCP) lands a
 // half tile MMA-ready.  (A variant in which the kernel gathered the rows itself with 16-byte LDGSTS was measured at
 // 387 ms vs 226 ms for the C3 null -- 16 cache lines per instruction at ~2 cycles per L1TEX wavefront, on a shared
@@ -58,7 +57,8 @@ enum : int { TCM_COUNT = 1, TCM_FLAG = 2, TCM_STORE = 4, TCM_RAW = 8, TCM_Z = 16
 enum : int { TCK_COUNT = 0, TCK_STORE = 1, TCK_RAW = 2, TCK_Z = 3 };
 
 struct GemmParams {
-    const uint64_t* a_bits;   // [n_tiles / TPS][2 (CTA rank)][TPS][128]: bit k of a word = A[row][64 kt + k]
+    const ulonglong2* a_bits; // [n_tiles / TPS][2 (CTA rank)][TPS][128]: the 64 membership bits A[row][64 kt + k] of
+                              // a row as two words, see split_mask
     const int32_t* tile_ptr;  // [n_rb + 1], every row block holds a multiple of TC_TPS tiles
     const int32_t* tile_kt;   // [n_tiles]
     const int8_t* bcat;       // [slot][kt][2 (CTA rank)][64 x 32*D], K rows in the expanders' order (tc_kpos)
@@ -115,7 +115,7 @@ struct TcCfg {
     static constexpr int HALF_B = TC_KT * NCOLS / 2;                // this CTA's half of a gathered tile
     static constexpr int TPS = TC_TPS;
     static constexpr int STAGE_B = TPS * HALF_B;                    // gathered-operand half tiles of one fill
-    static constexpr int STAGE_A = TPS * TC_ROWS * 8;               // this CTA's A bit tiles (one 64-bit mask per row)
+    static constexpr int STAGE_A = TPS * TC_ROWS * 16;              // this CTA's A bit tiles (one split mask per row)
     static constexpr int STAGE = STAGE_B + STAGE_A;
     static constexpr int STAGES = TC_STAGES;
     static constexpr int OFF_S0HI = STAGES * STAGE;                 // int32 [64][128]
@@ -126,18 +126,21 @@ struct TcCfg {
     static constexpr int SMEM = OFF_BAR + 512;  // 34 mbarriers + the TMEM base address
 };
 
-// 64 membership bits -> 16 TMEM words of four int8 values 0 / -1, without a table and without shared memory.
-// One byte permute (PRMT) expands four bits.  Its four selector nibbles are four CONSECUTIVE nibbles of the mask, and
-// the 8-byte source it selects from is constant: {00,FF,00,FF,00,FF,00,FF} returns 0x00 / 0xFF by bit 0 of a
-// nibble, {00,00,FF,FF,00,00,FF,FF} by bit 1, {00,00,00,00,FF,FF,FF,FF} by bit 2, whatever the other bits are (bit 3
-// of a selector asks for the replicated sign of the selected byte -- 0x00 / 0xFF again).  Bit 3 itself takes one shift.
-// So word 4 g + j of a row comes from 16-bit group g of the mask with source j: 6 shifts + 16 permutes per 64 bits
-// (the lookup-table version cost 24 instructions, 8 of them shared-memory loads with bank conflicts: ~400 of the
-// shared-memory pipe's 768 cycles per fill, next to the tensor core's own operand reads).
+// 64 membership bits -> 16 TMEM words of four int8 values 0 / 1, without a table.
+// One byte permute (PRMT) expands four bits.  Its four selector nibbles are four CONSECUTIVE nibbles of a mask word,
+// and the 8-byte source it selects from is constant: {00,01,00,01,00,01,00,01} returns 0 / 1 by bit 0 of a nibble,
+// {00,00,01,01,00,00,01,01} by bit 1, {00,00,00,00,01,01,01,01} by bit 2.  Bit 3 of a selector nibble would ask for
+// the replicated SIGN of the selected byte instead, so the plan stores a row's mask w as two words (split_mask): w with
+// bit 3 of every nibble cleared, and those bits moved down to bit 0 of their nibble (read with the first source).
+// Word 4 g + j of a row comes from 16-bit group g with source j: 16 permutes + 4 shifts per 64 bits (the lookup-table
+// version of round 1 cost 24 instructions, 8 of them shared-memory loads with bank conflicts).
 // Byte i of that word is mask bit 16 g + 4 i + j, i.e. the MMA sees the 64 entries of a tile in the order
 //   K position 16 g + 4 j + i  <->  tile entry 16 g + 4 i + j        (tc_kpos, an involution),
-// and the gathered operand tiles are written with their rows in the same order.  A = -1 where the reference has 1:
-// the digit planes hold the digits of -q (k_quantize), so A @ B is the reference's product.
+// and the gathered operand tiles are written with their rows in the same order.
+// Why 0 / 1 and not 0 / -1 (which a single mask word gives, the sign replication returning 0x00 / 0xFF for bit 3 as
+// well): the chip runs at its power cap and the tensor pipe draws measurably less on 0x01 than on 0xFF -- the same
+// pipeline, masks and instruction stream sustain 3050 int8 TOPS against 2770-2890 in the L2-hot rate probe; the C3 null
+// itself gains ~1 % (profiles/r2h_gemm_ab_experiments.txt, 10).
 __host__ __device__ constexpr int tc_kpos(int p) { return (p & ~15) | ((p & 3) << 2) | ((p >> 2) & 3); }
 
 template <uint32_t LO, uint32_t HI>
@@ -146,16 +149,23 @@ __device__ __forceinline__ uint32_t expand4(uint32_t ctl) {
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(LO), "r"(HI), "r"(ctl));
     return d;
 }
-__device__ __forceinline__ void expand_bits(uint64_t w, uint32_t (&r)[16]) {
-    const uint32_t lo = static_cast<uint32_t>(w), hi = static_cast<uint32_t>(w >> 32);
+// The mask w of a row is stored as two words (split_mask): x = w with bit 3 of every nibble cleared, y = those bits
+// moved to bit 0 of their nibble.
+__host__ __device__ __forceinline__ ulonglong2 split_mask(uint64_t w) {
+    return make_ulonglong2(w & 0x7777777777777777ull, (w >> 3) & 0x1111111111111111ull);
+}
+__device__ __forceinline__ void expand_bits(ulonglong2 m, uint32_t (&r)[16]) {
+    const uint32_t xlo = static_cast<uint32_t>(m.x), xhi = static_cast<uint32_t>(m.x >> 32);
+    const uint32_t ylo = static_cast<uint32_t>(m.y), yhi = static_cast<uint32_t>(m.y >> 32);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const uint32_t word = g < 2 ? lo : hi;
-        const uint32_t x = (g & 1) ? word >> 16 : word;  // PRMT reads the low 16 bits of its selector only
-        r[g * 4 + 0] = expand4<0xFF00FF00u, 0xFF00FF00u>(x);
-        r[g * 4 + 1] = expand4<0xFFFF0000u, 0xFFFF0000u>(x);
-        r[g * 4 + 2] = expand4<0x00000000u, 0xFFFFFFFFu>(x);
-        r[g * 4 + 3] = expand4<0xFF00FF00u, 0xFF00FF00u>(word >> (16 * (g & 1) + 3));
+        const uint32_t xw = g < 2 ? xlo : xhi, yw = g < 2 ? ylo : yhi;
+        const uint32_t x = (g & 1) ? xw >> 16 : xw;  // PRMT reads the low 16 bits of its selector only
+        const uint32_t y = (g & 1) ? yw >> 16 : yw;
+        r[g * 4 + 0] = expand4<0x01000100u, 0x01000100u>(x);
+        r[g * 4 + 1] = expand4<0x01010000u, 0x01010000u>(x);
+        r[g * 4 + 2] = expand4<0x00000000u, 0x01010101u>(x);
+        r[g * 4 + 3] = expand4<0x01000100u, 0x01000100u>(y);
     }
 }
 
@@ -342,7 +352,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
             __syncwarp();
             // this CTA's half of every gathered tile and its own rows of the A bit tiles
             const int8_t* const b_cg = p.bcat + static_cast<size_t>(cg) * p.n_kt * (2 * C::HALF_B) + rank * C::HALF_B;
-            const uint64_t* const a_unit =
+            const ulonglong2* const a_unit =
                 p.a_bits + (static_cast<size_t>(t0 / C::TPS) * 2 + rank) * (C::TPS * TC_ROWS);
             for (int q = q0; q < q1 && !(p.dbg & 4); ++q) {
                 const int8_t* const b_q = b_cg + (p.q_wrap == 1 ? 0 : static_cast<size_t>(q) * q_stride);
@@ -425,9 +435,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
                 for (int f = 0; f < nfills; ++f) {
                     // the bit tiles of this fill arrive in the smem stage together with the gathered operand
                     TC_TIMED(KIND, xt_full, mbar_wait(&full[stage], phase));
-                    const uint64_t* const sbits =
-                        reinterpret_cast<const uint64_t*>(sB + stage * C::STAGE + C::STAGE_B) + r;
-                    uint64_t w[C::TPS];
+                    const ulonglong2* const sbits =
+                        reinterpret_cast<const ulonglong2*>(sB + stage * C::STAGE + C::STAGE_B) + r;
+                    ulonglong2 w[C::TPS];
 #pragma unroll
                     for (int t = 0; t < C::TPS; ++t) w[t] = sbits[t * TC_ROWS];
                     __syncwarp();
@@ -444,7 +454,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
 #pragma unroll
                             for (int t = 0; t < TC_APS; ++t)
 #pragma unroll
-                                for (int c = 0; c < 16; ++c) e[t][c] = static_cast<uint32_t>(w[h * TC_APS + t]);
+                                for (int c = 0; c < 16; ++c) e[t][c] = static_cast<uint32_t>(w[h * TC_APS + t].x);
                         } else {
 #pragma unroll
                             for (int t = 0; t < TC_APS; ++t) expand_bits(w[h * TC_APS + t], e[t]);
@@ -967,13 +977,13 @@ __global__ void __launch_bounds__(256) k_tile_list(const uint8_t* __restrict__ o
     }
 }
 
-// the 256 x 64 bit block of every stored tile as one 64-bit word per row (padding tiles and rows are zero), laid
+// the 256 x 64 bit block of every stored tile as one split mask per row (padding tiles and rows are zero), laid
 // out so that the 128 rows one CTA needs for one fill (TC_TPS consecutive tiles) are contiguous:
 //   out[((tile / TPS) * 2 + rank) * TPS + tile % TPS][r],  rank = row / 128, r = row % 128
 __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__ words, int64_t n, int64_t ld,
                                                     const int32_t* __restrict__ tile_kt,
                                                     const int32_t* __restrict__ tile_rb, int64_t n_tiles,
-                                                    uint64_t* __restrict__ out) {
+                                                    ulonglong2* __restrict__ out) {
     const int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (idx >= n_tiles * TC_PROWS) return;
     const int64_t tile = idx / TC_PROWS;
@@ -989,7 +999,7 @@ __global__ void __launch_bounds__(256) k_pack_tiles(const uint32_t* __restrict__
     }
     const int64_t g = tile / TC_TPS, t = tile % TC_TPS;
     const int rank = r256 / TC_ROWS, r = r256 % TC_ROWS;
-    out[(((g * 2 + rank) * TC_TPS) + t) * TC_ROWS + r] = w;
+    out[(((g * 2 + rank) * TC_TPS) + t) * TC_ROWS + r] = split_mask(w);
 }
 
 // The matrices the digit GEMM multiplies the neighborhoods with are functions of the attribute matrix, evaluated on
@@ -1032,8 +1042,7 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
     if (bad) atomicOr(flags, 1);
 }
 
-// fixed-point digits: q = rint(v * 2^shift[j]); stored are the D balanced base-256 int8 digits of -q (the expanded
-// neighborhood operand is 0 / -1, see expand_bits).
+// fixed-point digits: q = rint(v * 2^shift[j]); stored are the D balanced base-256 int8 digits of q.
 // RECORDS = false (M < 64): plane d at digits + d*n*mpad.
 // RECORDS = true: one 64*D-byte record per (column group, node), digits[(cg * n + r) * 64 D + d * 64 + (j & 63)] --
 // what k_gather copies (192 contiguous bytes at D = 3), one column group's records being a compact N * 64 D byte
@@ -1049,7 +1058,7 @@ __global__ void k_quantize(const T* __restrict__ b, int64_t n, int64_t m, int64_
         int q = 0;
         if (j < m) {
             const double v = xf_value<XF, T>(b[r * m + j]);
-            if (v == v) q = -static_cast<int>(rint(ldexp(v, shift[j])));
+            if (v == v) q = static_cast<int>(rint(ldexp(v, shift[j])));
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
@@ -1191,7 +1200,7 @@ struct TcPlan {
     int64_t n_tiles_real = 0;  // non-empty tiles
     int32_t band_rb = 0, n_bands = 1, band_kt = 0;  // L2 blocking: row blocks per band, max distinct k-tiles of a band
     bool usable = true;  // false: data contains +-inf -> SIMT engine
-    DevBuf<uint64_t> a_bits;
+    DevBuf<ulonglong2> a_bits;
     const int32_t* order = nullptr;  // e->order.p when the caller supplied a node order (internal row -> node)
     DevBuf<int32_t> tile_ptr, tile_kt, tile_rb;
     DevBuf<unsigned int> flag_count;
@@ -1882,8 +1891,8 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
 
 // z records: digits[(cg * n + r) * 192 + d * 64 + h * 32 + s * 16 + a] = plane 2 d + s of attribute cg * 32 + h * 16 + a,
 // i.e. the 32-column half h of every plane pair d -- what one epilogue warp reads -- carries all six planes of 16
-// attributes.  Planes 0-2: balanced base-256 digits of -rint(v 2^shift1), 3-4: of -rint(v^2 2^shift2), 5: -1 where v
-// is not NaN (the expanded neighborhood operand is 0 / -1).
+// attributes.  Planes 0-2: balanced base-256 digits of rint(v 2^shift1), 3-4: of rint(v^2 2^shift2), 5: 1 where v is
+// not NaN.
 template <class T>
 __global__ void k_quantize_z(const T* __restrict__ b, int64_t n, int64_t m, int32_t n_cg,
                              const int32_t* __restrict__ shift1, const int32_t* __restrict__ shift2,
@@ -1899,9 +1908,9 @@ __global__ void k_quantize_z(const T* __restrict__ b, int64_t n, int64_t m, int3
         if (j < m) {
             const T v = b[r * m + j];
             if (v == v) {
-                valid = -1;
-                q1 = -static_cast<int>(rint(ldexp(static_cast<double>(v), shift1[j])));
-                q2 = -static_cast<int>(rint(ldexp(xf_value<XF_SQUARE, T>(v), shift2[j])));
+                valid = 1;
+                q1 = static_cast<int>(rint(ldexp(static_cast<double>(v), shift1[j])));
+                q2 = static_cast<int>(rint(ldexp(xf_value<XF_SQUARE, T>(v), shift2[j])));
             }
         }
         int8_t pl[6];
@@ -2240,7 +2249,7 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     // host-side tiling into the production layouts; A is a 0/1 matrix (any non-zero entry counts as 1) and is given
     // to BOTH CTAs of the pair (rows 0..127 and 128..255 of the unit), which must produce the same product
     const int kt_pad = static_cast<int>(sb_ceil_div(ktiles, TC_TPS) * TC_TPS);  // padding tiles of A are all zero
-    std::vector<uint64_t> at(static_cast<size_t>(kt_pad) * TC_PROWS, 0);
+    std::vector<ulonglong2> at(static_cast<size_t>(kt_pad) * TC_PROWS, make_ulonglong2(0, 0));
     std::vector<int8_t> bt(static_cast<size_t>(ktiles) * tile_b);
     for (int kt = 0; kt < ktiles; ++kt)
         for (int r = 0; r < TC_ROWS; ++r) {
@@ -2248,10 +2257,9 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
             for (int k = 0; k < TC_KT; ++k)
                 if (a_host[static_cast<size_t>(r) * K + kt * TC_KT + k]) w |= 1ull << k;
             for (int rank = 0; rank < 2; ++rank)
-                at[((static_cast<size_t>(kt / TC_TPS) * 2 + rank) * TC_TPS + kt % TC_TPS) * TC_ROWS + r] = w;
+                at[((static_cast<size_t>(kt / TC_TPS) * 2 + rank) * TC_TPS + kt % TC_TPS) * TC_ROWS + r] = split_mask(w);
         }
-    // tile row k (the MMA's K position) holds operand row tc_kpos(k); the expanded A is 0 / -1, so the raw
-    // accumulators are the NEGATED product (production stores the digits of -q instead) and are negated below
+    // tile row k (the MMA's K position) holds operand row tc_kpos(k)
     const int hc = ncols / 32;  // 16-column chunks per half tile
     for (int kt = 0; kt < ktiles; ++kt)
         for (int k = 0; k < TC_KT; ++k)
@@ -2262,7 +2270,7 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
             }
     std::vector<int32_t> ptr = {0, kt_pad}, kts(kt_pad);
     for (int i = 0; i < kt_pad; ++i) kts[i] = std::min(i, ktiles - 1);
-    DevBuf<uint64_t> d_a;
+    DevBuf<ulonglong2> d_a;
     DevBuf<int8_t> d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
     d_a.reserve(at.size());
@@ -2271,7 +2279,7 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     d_kt.reserve(kt_pad);
     d_out.reserve(static_cast<size_t>(TC_PROWS) * ncols);
     cudaStream_t st = ctx->stream;
-    SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(d_a.p, at.data(), at.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_b.p, bt.data(), bt.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_ptr.p, ptr.data(), 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(d_kt.p, kts.data(), kt_pad * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -2304,7 +2312,7 @@ extern "C" int sb_selftest_mma_i8(sb_ctx* ctx, int ncols, int ktiles, int varian
     SB_CUDA(cudaMemcpyAsync(both.data(), d_out.p, both.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     const size_t half_elems = static_cast<size_t>(TC_ROWS) * ncols;
-    for (size_t i = 0; i < half_elems; ++i) d_host[i] = -both[i];
+    for (size_t i = 0; i < half_elems; ++i) d_host[i] = both[i];
     if (!(variant & 2))
         SB_CHECK(memcmp(both.data(), both.data() + half_elems, half_elems * sizeof(int32_t)) == 0,
                  "sb_selftest_mma_i8: the two CTAs of the pair disagree");
@@ -2324,7 +2332,7 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     ctx->bind();
     const int D = ncols / 64;
     const size_t tile_b = static_cast<size_t>(TC_KT) * ncols;
-    DevBuf<uint64_t> d_a;
+    DevBuf<ulonglong2> d_a;
     DevBuf<int8_t> d_b;
     DevBuf<int32_t> d_ptr, d_kt, d_out;
     d_a.reserve(static_cast<size_t>(ktiles) * TC_PROWS);
@@ -2333,7 +2341,7 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
     d_kt.reserve(ktiles);
     d_out.reserve(static_cast<size_t>(TC_PROWS) * ncols);
     cudaStream_t st = ctx->stream;
-    SB_CUDA(cudaMemsetAsync(d_a.p, 0x55, static_cast<size_t>(ktiles) * TC_PROWS * sizeof(uint64_t), st));
+    std::vector<ulonglong2> ha(static_cast<size_t>(ktiles) * TC_PROWS, split_mask(0x5555555555555555ull));
     SB_CUDA(cudaMemsetAsync(d_b.p, 1, static_cast<size_t>(ktiles) * tile_b, st));
     if (const char* fill = getenv("SB_RATE_RANDOM")) {
         // operands with the statistics of a real null (random digits, masks filled to SB_RATE_RANDOM percent): the
@@ -2341,17 +2349,17 @@ extern "C" int sb_selftest_mma_rate(sb_ctx* ctx, int ncols, int ktiles, int slot
         const unsigned pct = static_cast<unsigned>(atoi(fill));
         uint64_t x = 0x9E3779B97F4A7C15ull;
         auto next = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
-        std::vector<uint64_t> ha(static_cast<size_t>(ktiles) * TC_PROWS);
-        for (auto& w : ha) {
-            w = 0;
+        for (auto& m : ha) {
+            uint64_t w = 0;
             for (int b = 0; b < 64; ++b) w |= static_cast<uint64_t>(next() % 100 < pct) << b;
+            m = split_mask(w);
         }
         std::vector<int8_t> hb(static_cast<size_t>(ktiles) * tile_b);
         for (auto& v : hb) v = static_cast<int8_t>(next() >> 24);
-        SB_CUDA(cudaMemcpyAsync(d_a.p, ha.data(), ha.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         SB_CUDA(cudaMemcpyAsync(d_b.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, st));
-        SB_CUDA(cudaStreamSynchronize(st));
     }
+    SB_CUDA(cudaMemcpyAsync(d_a.p, ha.data(), ha.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaStreamSynchronize(st));  // (host vectors)
     std::vector<int32_t> ptr = {0, ktiles}, kts(ktiles);
     for (int i = 0; i < ktiles; ++i) kts[i] = i;
     // all units share tiles [0, ktiles): one row block, the CTAs are spread over the q chunks

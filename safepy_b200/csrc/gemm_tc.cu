@@ -21,6 +21,7 @@
 // memory pipe the expanders already kept half busy; see profiles/r2a_bench_c3_fused_ldgsts_gather.json.)
 #include <algorithm>
 #include <climits>
+#include <cmath>
 #include <vector>
 
 #include "enrich.cuh"
@@ -1013,15 +1014,18 @@ __device__ __forceinline__ double xf_value(T v) {  // NaN = "contributes nothing
 }
 
 // per-column exponent range of the operand: kmax = exponent of the largest magnitude, lmin = exponent of the lowest
-// set mantissa bit over all non-zero values.  flags: bit0 = some value is +-inf
+// set mantissa bit over all non-zero values, vmax = the largest magnitude itself (bit pattern of the double; these
+// order like the values).  flags: bit0 = some value is +-inf
 template <class T, int XF>
 __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32_t* __restrict__ kmax,
-                            int32_t* __restrict__ lmin, int32_t* __restrict__ flags) {
+                            int32_t* __restrict__ lmin, unsigned long long* __restrict__ vmax,
+                            int32_t* __restrict__ flags) {
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= m) return;
     const int64_t rows_per = (n + gridDim.y - 1) / gridDim.y;
     const int64_t r0 = blockIdx.y * rows_per, r1 = min(n, r0 + rows_per);
     int hi = INT_MIN, lo = INT_MAX, bad = 0;
+    double big = 0.0;
     for (int64_t r = r0; r < r1; ++r) {
         const double v = xf_value<XF, T>(b[r * m + j]);
         if (v != v || v == 0.0) continue;
@@ -1034,10 +1038,12 @@ __global__ void k_col_range(const T* __restrict__ b, int64_t n, int64_t m, int32
         const long long mant = static_cast<long long>(ldexp(f, 53));
         hi = max(hi, e - 1);
         lo = min(lo, e - 53 + (__ffsll(mant) - 1));
+        big = fmax(big, fabs(v));
     }
     if (hi != INT_MIN) {
         atomicMax(&kmax[j], hi);
         atomicMin(&lmin[j], lo);
+        atomicMax(&vmax[j], static_cast<unsigned long long>(__double_as_longlong(big)));
     }
     if (bad) atomicOr(flags, 1);
 }
@@ -1196,6 +1202,7 @@ struct TcPlan {
     TcOperand op;              // the 'sum' operand; in the z plan: the z records
     int64_t n = 0, m = 0, mpad = 0;
     int32_t n_rb = 0, n_kt = 0, n_cg = 0, pps = 1, log2_mpad = 0;
+    int64_t max_nb = 0;        // largest neighborhood
     int64_t n_tiles = 0;       // stored tiles (row blocks padded to a multiple of TC_TPS)
     int64_t n_tiles_real = 0;  // non-empty tiles
     int32_t band_rb = 0, n_bands = 1, band_kt = 0;  // L2 blocking: row blocks per band, max distinct k-tiles of a band
@@ -1374,23 +1381,28 @@ static int64_t slots_for(const TcPlan* pl, int64_t perms) {
 }
 
 // Per-column exponent ranges of one operand (XF_*) on the host; returns k_col_range's flags (1: some value is +-inf)
-static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax, std::vector<int32_t>& h_lmin) {
+static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax, std::vector<int32_t>& h_lmin,
+                             std::vector<double>& h_vmax) {
     sb_ctx* ctx = e->ctx;
     cudaStream_t st = ctx->stream;
     const int64_t n = e->n, m = e->m;
     DevBuf<int32_t> kmax, lmin, flags;
+    DevBuf<unsigned long long> vmax;
     kmax.reserve(m);
     lmin.reserve(m);
+    vmax.reserve(m);
     flags.reserve(1);
     h_kmax.assign(m, INT_MIN);
     h_lmin.assign(m, INT_MAX);
+    h_vmax.assign(m, 0.0);
+    SB_CUDA(cudaMemsetAsync(vmax.p, 0, m * sizeof(unsigned long long), st));
     SB_CUDA(cudaMemcpyAsync(kmax.p, h_kmax.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(lmin.p, h_lmin.data(), m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int32_t), st));
     dim3 cgrid(static_cast<unsigned>(sb_ceil_div(m, 128)),
                static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(64, n / 256))));
 #define SB_R(T, X) \
-    k_col_range<T, X><<<cgrid, 128, 0, st>>>(static_cast<const T*>(e->b), n, m, kmax.p, lmin.p, flags.p)
+    k_col_range<T, X><<<cgrid, 128, 0, st>>>(static_cast<const T*>(e->b), n, m, kmax.p, lmin.p, vmax.p, flags.p)
 #define SB_RX(T)                 \
     do {                         \
         if (xf == XF_VALUE)      \
@@ -1409,8 +1421,22 @@ static int32_t column_ranges(sb_enrich* e, int xf, std::vector<int32_t>& h_kmax,
     SB_CUDA(cudaMemcpyAsync(h_kmax.data(), kmax.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaMemcpyAsync(h_lmin.data(), lmin.p, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaMemcpyAsync(&h_flags, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    static_assert(sizeof(double) == sizeof(unsigned long long), "bit patterns");
+    SB_CUDA(cudaMemcpyAsync(h_vmax.data(), vmax.p, m * sizeof(double), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     return h_flags;
+}
+
+// Fixed point of a column that D balanced digits cannot hold exactly: the largest power-of-two scale whose largest
+// value still fits.  D digits hold |q| <= qmax = 127 (256^D - 1) / 255 -- almost 2^(8D-1) -- so the column's exact
+// maximum buys one bit over the exponent-based choice |q| < 2^(8D-2) unless its mantissa sits in the top 0.4 %, and
+// every bit halves the error band, i.e. the number of comparisons that go to the exact fix-up.  `extra_bit` is off
+// where the wider sums could overflow the epilogue's int32 differences (neighborhoods of 32768+ nodes).
+static int inexact_shift(int D, int kmax, double vmax, bool extra_bit) {
+    const int shift = (8 * D - 3) - kmax;  // |q| < 2^(8D-2)
+    const double qmax = 127.0 * (std::pow(256.0, D) - 1.0) / 255.0;
+    if (extra_bit && std::rint(std::ldexp(vmax, shift + 1)) <= qmax) return shift + 1;
+    return shift;
 }
 
 // Digit planes of the 'sum' operand and its observed fixed-point scores
@@ -1423,7 +1449,8 @@ static void build_operand(sb_enrich* e, TcPlan* pl) {
     const int64_t n = e->n, m = e->m;
     PhaseTrace* tr = new PhaseTrace(ctx, "tc.plan.digits");
     std::vector<int32_t> h_kmax, h_lmin;
-    const int32_t h_flags = column_ranges(e, xf, h_kmax, h_lmin);
+    std::vector<double> h_vmax;
+    const int32_t h_flags = column_ranges(e, xf, h_kmax, h_lmin, h_vmax);
     op.built = true;
     if (h_flags & 1) {
         op.usable = false;
@@ -1447,7 +1474,7 @@ static void build_operand(sb_enrich* e, TcPlan* pl) {
         if (bits <= 8 * D - 2) {
             h_shift[j] = -h_lmin[j];  // lowest set bit lands on 2^0: every value is an exact integer
         } else {
-            h_shift[j] = (8 * D - 3) - h_kmax[j];  // |q| < 2^(8D-2)
+            h_shift[j] = inexact_shift(D, h_kmax[j], h_vmax[j], pl->max_nb < 32768);
             h_inexact[j] = 1;
             op.any_inexact = true;
         }
@@ -1539,13 +1566,14 @@ static TcPlan* build_plan(sb_enrich* e, bool zgroups = false) {
         pl->n_rb = static_cast<int32_t>(sb_ceil_div(n, TC_PROWS));
         pl->n_kt = static_cast<int32_t>(sb_ceil_div(n, TC_KT));
 
-        // the epilogue compares in int32 (score = hi * 256 + lo): needs n_i * 2^(8D-2) < 2^38
+        // the epilogue compares in int32 (score = hi * 256 + lo): needs n_i * max|q| < 2^38 (see inexact_shift)
         {
             std::vector<int64_t> h_rp(n + 1);
             SB_CUDA(cudaMemcpyAsync(h_rp.data(), e->row_ptr.p, (n + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
             SB_CUDA(cudaStreamSynchronize(st));
             int64_t max_nb = 0;
             for (int64_t i = 0; i < n; ++i) max_nb = std::max(max_nb, h_rp[i + 1] - h_rp[i]);
+            pl->max_nb = max_nb;
             if (max_nb >= 65536) {
                 pl->usable = false;  // neighborhoods of 65536+ nodes: exact SIMT engine
                 return pl;
@@ -2048,7 +2076,8 @@ static TcPlan* build_plan_z(sb_enrich* e, const TcPlan* main) {
         op.D = 3;
         // squares: two digit planes; exactly representable columns (<= 14 magnitude bits) keep every bit
         std::vector<int32_t> h_kmax, h_lmin;
-        const int32_t flags = column_ranges(e, XF_SQUARE, h_kmax, h_lmin);
+        std::vector<double> h_vmax;
+        const int32_t flags = column_ranges(e, XF_SQUARE, h_kmax, h_lmin, h_vmax);
         if (flags & 1) {  // a square overflows to inf: exact SIMT engine
             pl->usable = false;
             return pl;
@@ -2062,7 +2091,7 @@ static TcPlan* build_plan_z(sb_enrich* e, const TcPlan* main) {
             if (bits <= 14) {
                 h_shift[j] = -h_lmin[j];
             } else {
-                h_shift[j] = 13 - h_kmax[j];  // |q| < 2^14
+                h_shift[j] = inexact_shift(2, h_kmax[j], h_vmax[j], true);  // |q| <= 32639 (no differences in TCK_Z)
                 h_inexact[j] = 1;
                 any2 = true;
             }

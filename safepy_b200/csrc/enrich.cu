@@ -144,12 +144,25 @@ __global__ void __launch_bounds__(256) k_fixup(const int64_t* __restrict__ row_p
         const int32_t* pr = perm + static_cast<int64_t>(fp[k]) * n;
         const T* col = b_t + j * n;
         double sp = 0.0, so = 0.0;
-        for (int64_t e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
-            const int32_t t = col_idx[e];
-            const T vo = col[t];
-            const T vp = col[pr[t]];
-            if (vo == vo) so += static_cast<double>(vo);
-            if (vp == vp) sp += static_cast<double>(vp);
+        // four neighbors per lane and step: the index -> permutation -> value loads of a neighbor depend on each
+        // other, so the independent chains in flight are what hides the latency (a bucket of a batch holds only a
+        // few hundred flags: the walk is latency-bound, not throughput-bound)
+        const int64_t e1 = row_ptr[i + 1];
+        for (int64_t e = row_ptr[i] + lane; e < e1; e += 128) {
+            int32_t t[4];
+            T vo[4], vp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = e + 32 * u < e1 ? col_idx[e + 32 * u] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                vo[u] = t[u] >= 0 ? col[t[u]] : static_cast<T>(0);
+                vp[u] = t[u] >= 0 ? col[pr[t[u]]] : static_cast<T>(0);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (vo[u] == vo[u]) so += static_cast<double>(vo[u]);
+                if (vp[u] == vp[u]) sp += static_cast<double>(vp[u]);
+            }
         }
         for (int o = 16; o; o >>= 1) {
             sp += __shfl_xor_sync(0xffffffffu, sp, o);

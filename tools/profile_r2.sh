@@ -7,6 +7,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpuru
 P="python bench.py --steps 1 --warmup 0 --perms 139 --no-cpu-baseline --no-safe-api --no-parity"
 ncu --set full --clock-control none --import-source on -k regex:k_gemm -s 1 -c 1 -f -o gpurun_out/prof_gemm_r2 $P > /dev/null 2> gpurun_out/prof_gemm_r2.err
 ncu --set full --clock-control none --import-source on -k regex:"k_gather|k_fixup" -s 1 -c 2 -f -o gpurun_out/prof_gather_fixup_r2 $P > /dev/null 2> gpurun_out/prof_gather_r2.err
-ncu --set full --clock-control none --import-source on -k regex:"k_hypergeom|k_euclid" -c 4 -f -o gpurun_out/prof_stage1_hyper_r2 python tools/kernel_bench.py --only euclid,hypergeom > gpurun_out/prof_stage1_hyper_r2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_euclid -c 1 -f -o gpurun_out/prof_stage1_hyper_r2 python tools/kernel_bench.py --only euclid > gpurun_out/prof_stage1_hyper_r2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_hypergeom -c 1 -f -o gpurun_out/prof_hypergeom_r2b python tools/kernel_bench.py --only hypergeom > gpurun_out/prof_hypergeom_r2b.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_sssp" -s 2 -c 1 -f -o gpurun_out/prof_sssp_r2 python tools/kernel_bench.py --only sssp --configs C3 > gpurun_out/prof_sssp_r2.log 2>&1
 ls -la gpurun_out/*.ncu-rep

@@ -119,6 +119,30 @@ def test_mid_size_counts_against_oracle(ctx, stage1_mid):
     assert st["digits"] == 3 and st["a_tiles"] <= st["a_tiles_dense"]
 
 
+def test_fixed_point_scale_at_the_edges_of_the_digit_range(ctx, stage1_mid):
+    """The scale of an inexact column comes from its exact maximum (one bit more than the exponent alone would give)
+    unless that maximum would leave the three balanced digits (|q| <= 8355711): columns whose largest magnitude sits
+    just below / above that limit, at a power of two, and negative, for the 'sum' and the z-score null (whose squares
+    have their own two-digit scale)."""
+    g = stage1_mid
+    n = g["x"].shape[0]
+    nb = _lib.Neighborhoods(ctx, n).upload_packed(g["nb_layout"])
+    rng = np.random.default_rng(11)
+    attrs = rng.uniform(-0.45, 0.45, size=(n, 64)).astype(np.float32)
+    tops = [8355711 / 2 ** 23, 8355712 / 2 ** 23, 0.998, 0.9999999, 1.0, 0.5, 0.50000006, 1.9921, 3.0, 1e-3, 7.96875]
+    for j, top in enumerate(tops):
+        attrs[rng.integers(n), j] = np.float32(top) * (-1 if j % 2 else 1)
+        attrs[rng.integers(n), j + 16] = np.float32(np.sqrt(top))     # the same edges for the squares
+    attrs[rng.uniform(size=attrs.shape) < 0.01] = np.nan
+    rows = make_perm_rows(attrs, 30, 5)
+    plan = _lib.Enrichment(nb, attrs)
+    for score in ("sum", "z-score"):
+        tneg, tpos = plan.perm_counts(rows, score, "tc")
+        sneg, spos = plan.perm_counts(rows, score, "simt")
+        assert np.array_equal(tneg, sneg) and np.array_equal(tpos, spos), score
+    plan.close()
+
+
 @pytest.mark.parametrize("m", [1, 2, 3, 16, 33, 64, 65, 128])
 def test_column_group_shapes(ctx, stage1_small, m):
     """Every column-packing regime of the GEMM (several permutations per 64-column slot for m < 64, ragged last

@@ -104,7 +104,7 @@ struct sb_ctx {
     sb::DevBuf<uint32_t> ws_flag_p;
     sb::DevBuf<uint32_t> ws_cpk;
     sb::DevBuf<unsigned int> ws_counter;
-    size_t bcat_budget = 0;  // 1/8 of the free device memory seen at the first null of this context
+    size_t bcat_budget = 0;  // 1/4 of the free device memory seen at the first null of this context
     void bind() const {
         SB_CUDA(cudaSetDevice(device));
         sb::alloc_stream() = stream;

@@ -1755,8 +1755,8 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     SB_CHECK(!packed || num_perm < 65536, "packed counts hold fewer than 65536 permutations per call");
     PhaseTrace* tr_ws = new PhaseTrace(ctx, "tc.workspace");
 
-    // Batches: the gathered tiles of a batch take <= ~1/8 of the free memory seen at the first null of this context (at
-    // most 16 GiB; cudaMemGetInfo was seen to take hundreds of ms on a busy device: ask once per context).  Per batch:
+    // Batches: the gathered tiles of a batch take <= ~1/4 of the free memory seen at the first null of this context (at
+    // most 40 GiB -- C5: 5.53 s per null with 16 GiB batches, 5.31 s with 40; C3 indifferent; cudaMemGetInfo was seen to take hundreds of ms on a busy device: ask once per context).  Per batch:
     // gather -> GEMM -> fix-ups, all on the context's stream and without a host synchronisation in between (the fix-up
     // kernel reads the bucket counters on the device; they are logged and looked at once, after the last batch).
     // Measured and dropped: the gather of batch b + 1 and the fix-ups of batch b - 1 on a second stream under the GEMM
@@ -1769,10 +1769,10 @@ void tc_perm_counts(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, uin
     if (ctx->bcat_budget == 0) {
         size_t free_b = 0, total_b = 0;
         SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
+        ctx->bcat_budget = std::max<size_t>(free_b / 4, 1);
     }
     const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes * slots_for(pl, 1)),
-                                                    16ull << 30),
+                                                    40ull << 30),
                                    ctx->ws_bcat.n);
     int64_t max_slots = std::max<int64_t>(slots_for(pl, 1), static_cast<int64_t>(budget / slot_bytes));
     max_slots = std::min<int64_t>(max_slots, 65535ll * (pl->mpad >= 64 ? pl->n_cg : 1));
@@ -2162,15 +2162,15 @@ bool tc_perm_counts_z(sb_enrich* e, const int32_t* perm_dev, int64_t num_perm, u
         SB_LAUNCH_CHECK(ctx);
     }
 
-    // batches as in tc_perm_counts: gathered tiles <= ~1/8 of the free memory seen at the first null (<= 16 GiB)
+    // batches as in tc_perm_counts: gathered tiles <= ~1/4 of the free memory seen at the first null (<= 40 GiB)
     const size_t tile_b = static_cast<size_t>(TC_KT) * 192;
     const size_t slot_bytes = static_cast<size_t>(pl->n_kt) * tile_b;
     if (ctx->bcat_budget == 0) {
         size_t free_b = 0, total_b = 0;
         SB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        ctx->bcat_budget = std::max<size_t>(free_b / 8, 1);
+        ctx->bcat_budget = std::max<size_t>(free_b / 4, 1);
     }
-    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes * pl->n_cg), 16ull << 30),
+    const size_t budget = std::max(std::min<size_t>(std::max<size_t>(ctx->bcat_budget, slot_bytes * pl->n_cg), 40ull << 30),
                                    ctx->ws_bcat.n);
     int64_t pb = std::max<int64_t>(1, static_cast<int64_t>(budget / slot_bytes) / pl->n_cg);
     pb = std::min<int64_t>(std::min<int64_t>(pb, 65535), std::min<int64_t>(16384, num_perm));

@@ -1693,8 +1693,9 @@ static void run_batch_gemm(sb_enrich* e, TcPlan* pl, const TcOperand& op, int mo
     const int want_chunks = static_cast<int>(sb_ceil_div(4 * (ctx->num_sms / 2), base_units));
     q_per = std::min<int>(q_per, std::max<int>(1, q_total / std::max(1, want_chunks)));
     q_per = std::max(1, std::min(q_per, q_total));
-    gp.q_per = q_per;
-    gp.q_chunks = static_cast<int32_t>(sb_ceil_div(q_total, gp.q_per));
+    gp.q_chunks = static_cast<int32_t>(sb_ceil_div(q_total, q_per));
+    gp.q_per = static_cast<int32_t>(sb_ceil_div(q_total, gp.q_chunks));  // equal chunks: a short last chunk pays the
+                                                                          // per-unit overhead for a few slots only
     const int64_t units = static_cast<int64_t>(base_units) * gp.q_chunks;
     SB_CHECK(units < (1ll << 31), "too many work units in one batch (%lld)", (long long)units);
     static const bool trace = getenv("SB_TRACE") != nullptr;

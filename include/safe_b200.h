@@ -220,6 +220,13 @@ int sb_enrich_null_add_stream(sb_enrich* e, sb_perm_stream* s, int64_t num_perm)
  * so the foreign draws overlap with its own device work.  The ranks' counts add up to the full null
  * (sb_enrich_null_counts_dev + one all-reduce, then sb_enrich_null_set_perms). */
 int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num_perm, int world, int rank);
+/* Optional read-ahead for the call above (the reference draws its permutations inside the loop, safe_extras.py:56-58;
+ * here the draws may start before the plan exists): a background thread starts drawing rank `rank`'s share of the next
+ * num_perm permutations at once -- while the caller uploads the attribute matrix, say -- and the following
+ * sb_enrich_null_add_stream[_shard] with the same (num_perm, world, rank) consumes the rows as they become ready.
+ * (sb_perm_stream_next with the same num_perm does too, for world == 1).  Shares above 2 GB of gather rows are not
+ * read ahead (the call is then a no-op). */
+int sb_perm_stream_prefetch(sb_perm_stream* s, int64_t num_perm, int world, int rank);
 
 /* Tail of SAFE.compute_pvalues_by_randomization (safe.py:526-554) and of SAFE.compute_pvalues (safe.py:466-472):
  *   p = counts / P (NaN where the observed score is NaN); optional Benjamini-Hochberg adjustment of every row across

@@ -79,6 +79,7 @@ SIGNATURES = {
     "sb_perm_stream_destroy": (C.c_int, [_vp]),
     "sb_perm_stream_next": (C.c_int, [_vp, _i64, _vp]),
     "sb_perm_stream_state": (C.c_int, [_vp, _vp, C.POINTER(_i32), C.POINTER(_i64)]),
+    "sb_perm_stream_prefetch": (C.c_int, [_vp, _i64, C.c_int, C.c_int]),
     "sb_enrich_null_add_stream": (C.c_int, [_vp, _vp, _i64]),
     "sb_enrich_null_add_stream_shard": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int]),
     "sb_enrich_null_finalize": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_double, C.c_int, C.c_double,
@@ -529,6 +530,12 @@ class PermStream:
 
     def skip(self, num_perm):
         _check(self.lib, self.lib.sb_perm_stream_next(self.h, int(num_perm), None))
+
+    def prefetch(self, num_perm, world=1, rank=0):
+        """Start drawing this rank's share of the next num_perm permutations in the background; the following
+        Enrichment.null_add_stream(self, num_perm, world, rank) consumes them as they become ready."""
+        _check(self.lib, self.lib.sb_perm_stream_prefetch(self.h, int(num_perm), int(world), int(rank)))
+        return self
 
     def state(self):
         """(key[624] uint32, pos, permutations drawn)"""

@@ -12,6 +12,7 @@
 // piece into a pinned ring while the device counts the previous one.
 #include <algorithm>
 #include <condition_variable>
+#include <cstring>
 #include <mutex>
 #include <random>
 #include <thread>
@@ -28,6 +29,20 @@ struct sb_perm_stream {
     uint32_t tempered[624];           // outputs of the current key block
     int pos = 624;
     int64_t drawn = 0;                // permutations produced so far
+
+    // Optional read-ahead of one rank's share of a null (sb_perm_stream_prefetch): a background thread walks the piece
+    // schedule of sb_enrich_null_add_stream_shard, keeps this rank's gather rows and drops the others, so that the
+    // draws overlap with whatever the caller does before the null starts (uploading the attribute matrix).
+    std::thread pf_thread;
+    std::vector<int32_t> pf_rows;     // this rank's permutations in schedule order, [pf_mine][n]
+    int64_t pf_num_perm = -1, pf_mine = 0, pf_ready = 0;
+    int pf_world = 0, pf_rank = 0;
+    std::mutex pf_mu;
+    std::condition_variable pf_cv;
+    void pf_join() {
+        if (pf_thread.joinable()) pf_thread.join();
+    }
+    ~sb_perm_stream() { pf_join(); }
 
     void seed(uint32_t s) {
         key[0] = s;
@@ -183,6 +198,15 @@ int sb_perm_stream_destroy(sb_perm_stream* s) {
 int sb_perm_stream_next(sb_perm_stream* s, int64_t num_perm, int32_t* rows_out_host) {
     SB_API_BEGIN
     SB_CHECK(s && num_perm >= 0, "sb_perm_stream_next: bad argument");
+    if (s->pf_num_perm >= 0) {  // a read-ahead is pending: it must be exactly these permutations
+        SB_CHECK(s->pf_world == 1 && s->pf_num_perm == num_perm,
+                 "sb_perm_stream_next: the stream's read-ahead was started for another request");
+        s->pf_join();
+        if (rows_out_host) std::memcpy(rows_out_host, s->pf_rows.data(), s->pf_rows.size() * sizeof(int32_t));
+        s->pf_num_perm = -1;
+        std::vector<int32_t>().swap(s->pf_rows);
+        return 0;
+    }
     for (int64_t p = 0; p < num_perm; ++p) s->next_into(rows_out_host ? rows_out_host + p * s->n : nullptr);
     SB_API_END
 }
@@ -190,9 +214,69 @@ int sb_perm_stream_next(sb_perm_stream* s, int64_t num_perm, int32_t* rows_out_h
 int sb_perm_stream_state(sb_perm_stream* s, uint32_t* key624_out, int32_t* pos_out, int64_t* drawn_out) {
     SB_API_BEGIN
     SB_CHECK(s, "sb_perm_stream_state: NULL handle");
+    s->pf_join();
     if (key624_out) std::copy(s->key, s->key + 624, key624_out);
     if (pos_out) *pos_out = s->pos;
     if (drawn_out) *drawn_out = s->drawn;
+    SB_API_END
+}
+
+namespace {
+// Piece schedule of a streamed null.  One rank: pieces double from 16 permutations (the device gets work at once) up
+// to `piece`.  Several ranks: equal pieces dealt round-robin, ~4 per rank, so that drawing the other ranks' pieces
+// (the RNG cannot jump) overlaps with counting one's own instead of preceding it.
+struct PieceSchedule {
+    int64_t piece, dealt;
+    int world;
+    PieceSchedule(int64_t n, int64_t num_perm, int world_) : world(world_) {
+        piece = std::max<int64_t>(1, std::min<int64_t>(128, (64ll << 20) / n));
+        dealt = std::max<int64_t>(1, std::min(piece, std::max<int64_t>(8, (num_perm + world * 4 - 1) / (world * 4))));
+    }
+    int64_t size(int64_t q) const {
+        if (world > 1) return dealt;
+        return q < 4 ? std::min<int64_t>(piece, 16ll << q) : piece;
+    }
+};
+}  // namespace
+
+int sb_perm_stream_prefetch(sb_perm_stream* s, int64_t num_perm, int world, int rank) {
+    SB_API_BEGIN
+    SB_CHECK(s && num_perm >= 0, "sb_perm_stream_prefetch: bad argument");
+    SB_CHECK(world >= 1 && rank >= 0 && rank < world, "sb_perm_stream_prefetch: rank %d of %d", rank, world);
+    SB_CHECK(!s->pf_thread.joinable() && s->pf_num_perm < 0, "sb_perm_stream_prefetch: a read-ahead is already pending");
+    const PieceSchedule sched(s->n, num_perm, world);
+    int64_t mine = 0;
+    for (int64_t q = 0, left = num_perm; left > 0; ++q) {
+        const int64_t np = std::min(sched.size(q), left);
+        if (q % world == rank) mine += np;
+        left -= np;
+    }
+    // beyond 2 GB of gather rows the null draws its pieces itself, as without a read-ahead
+    if (num_perm == 0 || static_cast<size_t>(mine) * s->n * sizeof(int32_t) > (2ull << 30)) return 0;
+    s->pf_rows.resize(static_cast<size_t>(mine) * s->n);
+    s->pf_num_perm = num_perm;
+    s->pf_world = world;
+    s->pf_rank = rank;
+    s->pf_mine = mine;
+    s->pf_ready = 0;
+    s->pf_thread = std::thread([s, sched, num_perm, world, rank] {
+        int64_t at = 0;
+        for (int64_t q = 0, left = num_perm; left > 0; ++q) {
+            const int64_t np = std::min(sched.size(q), left);
+            left -= np;
+            if (q % world != rank) {  // another rank's piece: drawn and dropped
+                for (int64_t p = 0; p < np; ++p) s->next_into(nullptr);
+                continue;
+            }
+            for (int64_t p = 0; p < np; ++p) s->next_into(s->pf_rows.data() + (at + p) * s->n);
+            at += np;
+            {
+                std::lock_guard<std::mutex> lk(s->pf_mu);
+                s->pf_ready = at;
+            }
+            s->pf_cv.notify_all();
+        }
+    });
     SB_API_END
 }
 
@@ -209,15 +293,12 @@ int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num
     ctx->bind();
     cudaStream_t st = ctx->stream;
     const int64_t n = e->n;
-    // Piece schedule.  One rank: pieces double from 16 permutations (the device gets work at once) up to `piece`.
-    // Several ranks: equal pieces dealt round-robin, ~4 per rank, so that drawing the other ranks' pieces (the RNG
-    // cannot jump) overlaps with counting one's own instead of preceding it.
-    const int64_t piece = std::max<int64_t>(1, std::min<int64_t>(128, (64ll << 20) / n));
-    const int64_t dealt = std::max<int64_t>(1, std::min(piece, std::max<int64_t>(8, (num_perm + world * 4 - 1) / (world * 4))));
-    auto piece_size = [&](int64_t q) {
-        if (world > 1) return dealt;
-        return q < 4 ? std::min<int64_t>(piece, 16ll << q) : piece;
-    };
+    const PieceSchedule sched(n, num_perm, world);
+    const int64_t piece = sched.piece;
+    auto piece_size = [&](int64_t q) { return sched.size(q); };
+    const bool ahead = s->pf_num_perm >= 0;  // a read-ahead of exactly this null is running or done
+    SB_CHECK(!ahead || (s->pf_num_perm == num_perm && s->pf_world == world && s->pf_rank == rank),
+             "sb_enrich_null_add_stream: the stream's read-ahead was started for another null");
     int64_t mine = 0;
     for (int64_t q = 0, left = num_perm; left > 0; ++q) {
         const int64_t np = std::min(piece_size(q), left);
@@ -235,6 +316,35 @@ int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num
     bool abort = false;
     std::thread producer([&] {
         int slot = 0;
+        if (ahead) {
+            // the rows are (being) drawn by the read-ahead thread: this one only stages them, piece by piece, into
+            // the pinned ring as they become ready
+            int64_t at = 0;
+            for (int64_t q = 0, left = num_perm; left > 0; ++q) {
+                const int64_t np = std::min(piece_size(q), left);
+                left -= np;
+                if (q % world != rank) continue;
+                {
+                    std::unique_lock<std::mutex> lk(s->pf_mu);
+                    s->pf_cv.wait(lk, [&] { return s->pf_ready >= at + np; });
+                }
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return filled[slot] == 0 || abort; });
+                    if (abort) return;
+                }
+                std::memcpy(ring + static_cast<size_t>(slot) * piece * n, s->pf_rows.data() + at * n,
+                            static_cast<size_t>(np) * n * sizeof(int32_t));
+                at += np;
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    filled[slot] = np;
+                }
+                cv.notify_all();
+                slot = (slot + 1) % kRing;
+            }
+            return;
+        }
         for (int64_t q = 0, left = num_perm; left > 0; ++q) {
             const int64_t np = std::min(piece_size(q), left);
             left -= np;
@@ -294,6 +404,11 @@ int sb_enrich_null_add_stream_shard(sb_enrich* e, sb_perm_stream* s, int64_t num
         cv.notify_all();
     }
     producer.join();
+    if (ahead) {  // (on an error the read-ahead still finishes its draws: the stream must end where upstream's would)
+        s->pf_join();
+        s->pf_num_perm = -1;
+        std::vector<int32_t>().swap(s->pf_rows);
+    }
     if (!error.empty()) fail("%s", error.c_str());
     for (int i = 0; i < 7; ++i) e->stats[i] = e->null_stats[i];
     SB_API_END

@@ -140,6 +140,7 @@ class SafeB200Mixin:
     # is the largest part of the call, so a caller who needs, say, only the NES can ask for ("nes", "nes_binary").
     host_outputs = ("ns", "pvalues_neg", "pvalues_pos", "nes", "nes_binary")
     _plan = None  # enrichment plan of the compute_pvalues call in progress
+    _ahead = None  # (stream, num_permutations, world, rank): RNG read-ahead started before the plan was uploaded
     _tail = None  # (nes_binary, num_neighborhoods_enriched) handed from the enrichment branch to compute_pvalues
 
     # ---------------------------------------------------------------------------------- stage 1
@@ -213,15 +214,16 @@ class SafeB200Mixin:
         # The attribute matrix goes to the device once; the look at its values (NaN share per attribute, anything
         # other than 0 / 1 / NaN -- safe.py:453-458) happens there, and the same plan serves the chosen test.
         self._tail = None
-        with self._plan_scope() as plan:
-            nans, num_other_values = plan.attr_summary()
-            if np.any(nans / plan.n > 0.5):
-                logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored "
-                                "for calculating enrichment.\n'Consider setting sf.background = ''network''.'")
-            if self.enrichment_type == "hypergeometric" or (self.enrichment_type == "auto" and num_other_values == 0):
-                self.compute_pvalues_by_hypergeom(**kwargs)
-            else:
-                self.compute_pvalues_by_randomization(**kwargs)
+        if self.enrichment_type not in ("hypergeometric", "auto"):
+            # randomization whatever the attribute values are: the permutation draws do not need the device, so
+            # they start now and overlap with the upload of the attribute matrix (2 GB at N = 100 000 x M = 5000)
+            self._start_read_ahead(kwargs)
+        try:
+            self._compute_pvalues_on_plan(kwargs)
+        finally:
+            if self._ahead is not None:        # an error before the null consumed it
+                self._ahead[0].close()
+                self._ahead = None
 
         if self._tail is not None:
             # nes_binary and the per-attribute sums came out of the same kernel pass as the NES (safe.py:466-472)
@@ -233,6 +235,48 @@ class SafeB200Mixin:
             self.nes_binary[idx] = np.abs(self.nes[idx]) > -np.log10(self.enrichment_threshold)
             enriched = np.sum(self.nes_binary, axis=0)
         self.attributes["num_neighborhoods_enriched"] = enriched
+
+    def _randomization_permutations(self, kwargs):
+        """num_permutations as compute_pvalues_by_randomization will use it (kwarg + safe.py:503-504 rounding)."""
+        if "num_permutations" in kwargs:
+            self.num_permutations = kwargs["num_permutations"]
+        num_processes = kwargs.get("processes", 1)
+        self.validate_config()
+        if num_processes > 1:
+            # safe.py:503-504 rounds the permutation count up to a multiple of the worker count
+            per = int(np.ceil(self.num_permutations / num_processes))
+            self.num_permutations = per * num_processes
+
+    def _start_read_ahead(self, kwargs):
+        self._ahead = None
+        self._randomization_permutations(kwargs)
+        dist = active_group(self.multi_gpu)
+        if not native_seed(self.random_seed) or (dist and self.random_seed is None):
+            return                              # NumPy's own seeding path / the error is raised by the branch method
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist else (1, 0)
+        stream = perm_stream(self.node2attribute, self.random_seed)
+        stream.prefetch(self.num_permutations, world, rank)
+        self._ahead = (stream, self.num_permutations, world, rank)
+
+    def _take_stream(self, world, rank):
+        """The read-ahead stream of this call when it matches, else a fresh one."""
+        ahead, self._ahead = self._ahead, None
+        if ahead is not None:
+            if ahead[1:] == (self.num_permutations, world, rank):
+                return ahead[0]
+            ahead[0].close()
+        return perm_stream(self.node2attribute, self.random_seed)
+
+    def _compute_pvalues_on_plan(self, kwargs):
+        with self._plan_scope() as plan:
+            nans, num_other_values = plan.attr_summary()
+            if np.any(nans / plan.n > 0.5):
+                logging.warning("WARNING: more than 50% of nodes in the network are set to NaN and will be ignored "
+                                "for calculating enrichment.\n'Consider setting sf.background = ''network''.'")
+            if self.enrichment_type == "hypergeometric" or (self.enrichment_type == "auto" and num_other_values == 0):
+                self.compute_pvalues_by_hypergeom(**kwargs)
+            else:
+                self.compute_pvalues_by_randomization(**kwargs)
 
     @contextlib.contextmanager
     def _plan_scope(self):
@@ -270,14 +314,7 @@ class SafeB200Mixin:
         logging.info("Using randomization to calculate enrichment...")
         # (the reference sleeps 1 s here to keep its progress bar tidy, safe.py:484; not reproduced)
 
-        if "num_permutations" in kwargs:
-            self.num_permutations = kwargs["num_permutations"]
-        num_processes = kwargs.get("processes", 1)
-        self.validate_config()
-        if num_processes > 1:
-            # safe.py:503-504 rounds the permutation count up to a multiple of the worker count
-            per = int(np.ceil(self.num_permutations / num_processes))
-            self.num_permutations = per * num_processes
+        self._randomization_permutations(kwargs)
 
         # The host replays the reference's RNG stream piece by piece (background thread) while the device counts
         # the previous piece; counts -> p-values -> (FDR) -> NES -> nes_binary happen on the device in one tail
@@ -299,7 +336,7 @@ class SafeB200Mixin:
                 # half the bytes of the two arrays
                 import torch
                 device = torch.device("cuda", plan.ctx.device)
-                stream = perm_stream(self.node2attribute, self.random_seed)
+                stream = self._take_stream(dist.get_world_size(), dist.get_rank())
                 plan.null_add_stream(stream, self.num_permutations, dist.get_world_size(), dist.get_rank())
                 stream.sync_numpy()
                 stream.close()
@@ -325,7 +362,7 @@ class SafeB200Mixin:
             elif native_seed(self.random_seed):
                 # one C call: a producer thread replays the RNG stream piece by piece into pinned memory while the
                 # device counts the previous piece
-                stream = perm_stream(self.node2attribute, self.random_seed)
+                stream = self._take_stream(1, 0)
                 plan.null_add_stream(stream, self.num_permutations)
                 stream.sync_numpy()          # the global generator ends where upstream's would
                 stream.close()

@@ -206,6 +206,32 @@ def test_native_perm_stream_replays_numpy(n, perms, seed):
     assert np.array_equal(np.random.get_state()[1], state[1])
 
 
+def test_perm_stream_read_ahead():
+    """sb_perm_stream_prefetch: the rows drawn in the background are the stream's next rows, the generator ends where
+    the synchronous replay ends, and a request that does not match the read-ahead is refused."""
+    from safepy_b200 import _lib
+    n, perms, seed = 900, 37, 5
+    rng = np.random.default_rng(3)
+    attrs = rng.standard_normal((n, 2)).astype(np.float32)
+    attrs[rng.random(n) < 0.2] = np.nan
+    idx = np.nonzero(np.sum(~np.isnan(attrs), axis=1))[0]
+    ref = orc.perm_gather_rows(attrs, perms, seed)
+    state = np.random.get_state()
+    stream = _lib.PermStream(n, idx, seed).prefetch(perms)
+    assert np.array_equal(stream.next(perms), ref)
+    key, pos, drawn = stream.state()
+    assert drawn == perms and pos == state[2] and np.array_equal(key, state[1])
+    stream.close()
+    # a rank's share of a dealt null: the state afterwards is that of ALL permutations (foreign pieces are drawn too)
+    stream = _lib.PermStream(n, idx, seed).prefetch(perms, world=2, rank=1)
+    with pytest.raises(_lib.SafeB200Error, match="another request"):
+        stream.next(perms)
+    key, pos, drawn = stream.state()                   # waits for the read-ahead
+    assert drawn == perms and pos == state[2] and np.array_equal(key, state[1])
+    stream.close()
+    _lib.PermStream(n, idx, seed).prefetch(perms).close()      # closing with a read-ahead in flight joins it
+
+
 def test_perm_stream_rejects_bad_input():
     from safepy_b200 import _lib
     with pytest.raises(ValueError):

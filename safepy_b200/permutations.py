@@ -10,8 +10,25 @@ import numpy as np
 
 
 def rows_with_data(node2attribute):
-    """indx_vals of safe_extras.py:51."""
-    return np.nonzero(np.sum(~np.isnan(node2attribute), axis=1))[0]
+    """indx_vals of safe_extras.py:51: the rows with at least one non-NaN entry, ascending.
+
+    Upstream evaluates np.sum(~np.isnan(B), axis=1) over the whole matrix (1 s for 100 000 x 5000 float32).  A row is
+    settled by its first non-NaN entry, so a few leading columns settle almost every row and only the rest is scanned
+    in full."""
+    a = np.asarray(node2attribute)
+    if a.ndim != 2:
+        return np.nonzero(np.sum(~np.isnan(a), axis=1))[0]
+    has = np.zeros(a.shape[0], dtype=bool)
+    open_rows = np.arange(a.shape[0])
+    for j in range(min(4, a.shape[1])):
+        if open_rows.size * 8 < a.shape[0]:
+            break
+        found = ~np.isnan(a[open_rows, j])
+        has[open_rows[found]] = True
+        open_rows = open_rows[~found]
+    if open_rows.size:
+        has[open_rows] = ~np.isnan(a[open_rows]).all(axis=1)
+    return np.nonzero(has)[0]
 
 
 def native_seed(random_seed):

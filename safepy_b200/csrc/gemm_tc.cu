@@ -14,9 +14,11 @@
 // between the two CTAs' shared memories, so every byte of the gathered operand that leaves L2 feeds 256 rows.
 // A is kept as bit tiles: for every non-empty 256 x 64 tile one 64-bit mask per row (stored as two words, split_mask).
 // The masks ride along with the gathered tiles through the smem ring, expander warps turn them into int8 0 / 1 in
-// TMEM with byte permutes (no table), and the MMA takes its A operand from TMEM.  Gathered tiles are stored in HBM in the tensor core's canonical
-// no-swizzle MN-major core-matrix order, one half per CTA, so one 1-D bulk async copy (TMA engine, UBLKCP) lands a
-// half tile MMA-ready.  (A variant in which the kernel gathered the rows itself with 16-byte LDGSTS was measured at
+// TMEM with byte permutes (no table), and the MMA takes its A operand from TMEM.  Gathered tiles are stored in HBM in
+// the tensor core's canonical no-swizzle MN-major core-matrix order, one half per CTA, so one 1-D bulk async copy
+// (TMA engine, UBLKCP) lands a half tile MMA-ready.  The z-score null (neighborhood_score_type = 'z-score',
+// safe_extras.py:19-31) runs through the same kernel with six digit planes per 32 attributes and its own epilogue
+// (TCK_Z, see "z-score null" below).  (A variant in which the kernel gathered the rows itself with 16-byte LDGSTS was measured at
 // 387 ms vs 226 ms for the C3 null -- 16 cache lines per instruction at ~2 cycles per L1TEX wavefront, on a shared
 // memory pipe the expanders already kept half busy; see profiles/r2a_bench_c3_fused_ldgsts_gather.json.)
 #include <algorithm>

@@ -34,7 +34,7 @@ namespace {
 // memory are otherwise bound by one thread: the driver stages them through its own pinned buffer with a
 // single-threaded memcpy, and for a freshly allocated destination that thread also takes every first-touch page fault.
 struct HostRing {
-    static constexpr int kSlots = 16;
+    static constexpr int kSlots = 32;
     static constexpr size_t kSlot = 4u << 20;
     struct Task {
         int slot;
@@ -61,7 +61,7 @@ struct HostRing {
             used[i] = false;
         }
         const unsigned hw = std::thread::hardware_concurrency();
-        workers = static_cast<int>(std::max(2u, std::min(16u, hw ? hw : 2u)));
+        workers = static_cast<int>(std::max(2u, std::min(static_cast<unsigned>(kSlots), hw ? hw : 2u)));
         for (int w = 0; w < workers; ++w) std::thread([this] { run(); }).detach();
     }
     void run() {
